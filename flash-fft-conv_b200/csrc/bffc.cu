@@ -1,0 +1,305 @@
+// bffc.cu — host side of the C ABI declared in include/bffc.h (plan tables, TMA descriptors, launches).
+//
+// Replaces, for the fused FFT-convolution path only:
+//   FlashFFTConv.__init__ tables            (reference flashfftconv/conv.py:72-551)
+//   k_f permutation + cast per call         (conv.py:640, :676, :1423-1424)
+//   pybind entry + C++ dispatch + launcher  (csrc/flashfftconv/monarch.cpp:16-56,
+//                                            monarch_cuda/monarch_fwd.h:296-376,
+//                                            monarch_cuda_interface_fwd_bf16.cu:656-760)
+// No torch types cross this boundary; there is no CPU fallback.
+#include "bffc.h"
+#include "fwd_r128.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                           \
+  do {                                                                                           \
+    cudaError_t e_ = (expr);                                                                     \
+    if (e_ != cudaSuccess) return fail(BFFC_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled g_encode = nullptr;
+std::once_flag g_encode_once;
+
+int get_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres) ==
+            cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  });
+  return g_encode ? 0 : fail(BFFC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+}
+
+int check_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(BFFC_ERR_NO_DEVICE, "no CUDA device available (bffc has no CPU fallback)");
+  }
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major != 10) {
+    cudaGetLastError();
+    return fail(BFFC_ERR_NO_DEVICE, "device %d is not sm_100 (compute capability major %d)", dev, major);
+  }
+  return 0;
+}
+
+uint16_t f2bf(double x) {  // round-to-nearest-even float -> bf16 bits
+  float f = static_cast<float>(x);
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  uint32_t r = 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>((u + r) >> 16);
+}
+
+// A 16x16 (K x N) real matrix built from an 8x8 complex multiplier G[kidx][nidx]:
+//   rows (K): kmap[kk] = (part, kidx), cols (N): [re nidx 0..7 | im nidx 0..7]
+//   [re][re]=Gr  [re][im]=Gi  [im][re]=-Gi  [im][im]=Gr
+// stored as the canonical no-swizzle K-major UMMA B layout: element (n,k) at
+//   (n>>3)*256 + (k>>3)*128 + (n&7)*16 + (k&7)*2     (SBO=256, LBO=128)
+template <class GFn>
+void fill_small(uint8_t* dst, const int* kpart, const int* kidx, GFn G) {
+  for (int kk = 0; kk < 16; ++kk)
+    for (int n = 0; n < 16; ++n) {
+      const int npart = n >> 3, nidx = n & 7;
+      double gr, gi;
+      G(kidx[kk], nidx, gr, gi);
+      double v;
+      if (kpart[kk] == 0) v = (npart == 0) ? gr : gi;
+      else v = (npart == 0) ? -gi : gr;
+      const uint16_t b = f2bf(v);
+      const size_t off = size_t(n >> 3) * 256 + size_t(kk >> 3) * 128 + size_t(n & 7) * 16 + size_t(kk & 7) * 2;
+      memcpy(dst + off, &b, 2);
+    }
+}
+
+__global__ void kf_pack_kernel(const float2* __restrict__ kf_nat, uint32_t* __restrict__ kf_eng,
+                               const int* __restrict__ perm, int N, float scale, int conj) {
+  const int h = blockIdx.y;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < N; e += gridDim.x * blockDim.x) {
+    float2 v = kf_nat[size_t(h) * N + perm[e]];
+    v.x *= scale;
+    v.y *= conj ? -scale : scale;
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.x, v.y);
+    kf_eng[size_t(h) * N + e] = *reinterpret_cast<uint32_t*>(&b);
+  }
+}
+
+}  // namespace
+
+struct bffc_plan {
+  int N;
+  int dtype;
+  int device;
+  __nv_bfloat16* dftC = nullptr;
+  __nv_bfloat16* dftS = nullptr;
+  uint8_t* bsmall = nullptr;
+  int* perm = nullptr;  // engine index -> natural frequency index
+  int num_sms = 0;
+};
+
+extern "C" {
+
+int bffc_abi_version(void) { return BFFC_ABI_VERSION; }
+const char* bffc_last_error(void) { return g_err; }
+int bffc_last_launch_count(void) { return g_launches; }
+
+int bffc_supported(int seqlen, int dtype) { return (seqlen == 8192 && dtype == BFFC_DTYPE_BF16) ? 1 : 0; }
+
+int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
+  if (!out) return fail(BFFC_ERR_INVALID, "plan output pointer is null");
+  *out = nullptr;
+  if (dtype != BFFC_DTYPE_BF16 && dtype != BFFC_DTYPE_FP16) return fail(BFFC_ERR_INVALID, "unknown dtype %d", dtype);
+  if (!bffc_supported(seqlen, dtype))
+    return fail(BFFC_ERR_UNSUPPORTED, "seqlen %d / dtype %d not supported by this build", seqlen, dtype);
+  if (int rc = check_device()) return rc;
+  if (int rc = get_encode()) return rc;
+
+  bffc_plan* p = new bffc_plan();
+  p->N = seqlen;
+  p->dtype = dtype;
+  CUDA_TRY(cudaGetDevice(&p->device));
+  CUDA_TRY(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
+
+  const double PI = 3.14159265358979323846;
+  // outer radix-128 DFT, cos / sin planes (symmetric, K-major rows)
+  std::vector<uint16_t> c(128 * 128), s(128 * 128);
+  for (int m = 0; m < 128; ++m)
+    for (int k = 0; k < 128; ++k) {
+      const double ang = 2.0 * PI * double((m * k) & 127) / 128.0;
+      c[m * 128 + k] = f2bf(cos(ang));
+      s[m * 128 + k] = f2bf(sin(ang));
+    }
+  CUDA_TRY(cudaMalloc(&p->dftC, c.size() * 2));
+  CUDA_TRY(cudaMalloc(&p->dftS, s.size() * 2));
+  CUDA_TRY(cudaMemcpy(p->dftC, c.data(), c.size() * 2, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(p->dftS, s.data(), s.size() * 2, cudaMemcpyHostToDevice));
+
+  // inner 64 = 8 x 8 stage matrices (see fwd_r128.cuh for the K orders)
+  std::vector<uint8_t> small(bffc::r128::kNumSmall * bffc::r128::kSmallBytes, 0);
+  int part_nat[16], idx_nat[16], part_c[16], idx_c[16];
+  for (int kk = 0; kk < 16; ++kk) {
+    part_nat[kk] = kk >> 3;  idx_nat[kk] = kk & 7;                 // [re 0..7 | im 0..7]
+    const int cc = kk >> 3, r = kk & 7;                            // c-major: [re 4c..4c+3 | im 4c..4c+3]
+    part_c[kk] = r >> 2;     idx_c[kk] = 4 * cc + (r & 3);
+  }
+  // B2a: F8[j1,a] = exp(-2 pi i j1 a / 8)
+  fill_small(small.data() + 0 * 512, part_c, idx_c, [&](int j1, int a, double& gr, double& gi) {
+    const double ang = -2.0 * PI * double((j1 * a) & 7) / 8.0;
+    gr = cos(ang); gi = sin(ang);
+  });
+  for (int a = 0; a < 8; ++a) {
+    // B2b[a]: G_a[j2,d] = exp(-2 pi i (a j2 / 64 + j2 d / 8))
+    fill_small(small.data() + (1 + a) * 512, part_nat, idx_nat, [&](int j2, int d, double& gr, double& gi) {
+      const double ang = -2.0 * PI * double((a * j2 + 8 * j2 * d) & 63) / 64.0;
+      gr = cos(ang); gi = sin(ang);
+    });
+    // B3b[a]: H_a[d,j2] = exp(+2 pi i (j2 d / 8 + a j2 / 64))
+    fill_small(small.data() + (9 + a) * 512, part_nat, idx_nat, [&](int d, int j2, double& gr, double& gi) {
+      const double ang = 2.0 * PI * double((a * j2 + 8 * j2 * d) & 63) / 64.0;
+      gr = cos(ang); gi = sin(ang);
+    });
+  }
+  // B3a: iF8[a,j1] = exp(+2 pi i a j1 / 8)
+  fill_small(small.data() + 17 * 512, part_nat, idx_nat, [&](int a, int j1, double& gr, double& gi) {
+    const double ang = 2.0 * PI * double((j1 * a) & 7) / 8.0;
+    gr = cos(ang); gi = sin(ang);
+  });
+  CUDA_TRY(cudaMalloc(&p->bsmall, small.size()));
+  CUDA_TRY(cudaMemcpy(p->bsmall, small.data(), small.size(), cudaMemcpyHostToDevice));
+
+  // engine order: e = k1*64 + 8*a + d  <->  natural k = k1 + 128*(a + 8*d)
+  std::vector<int> perm(seqlen);
+  for (int k1 = 0; k1 < 128; ++k1)
+    for (int a = 0; a < 8; ++a)
+      for (int d = 0; d < 8; ++d) perm[k1 * 64 + 8 * a + d] = k1 + 128 * (a + 8 * d);
+  CUDA_TRY(cudaMalloc(&p->perm, perm.size() * sizeof(int)));
+  CUDA_TRY(cudaMemcpy(p->perm, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice));
+
+  CUDA_TRY(cudaFuncSetAttribute(bffc::r128::fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                bffc::r128::kSmemTotal));
+  CUDA_TRY(cudaFuncSetAttribute(bffc::r128::fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                bffc::r128::kSmemTotal));
+  *out = p;
+  return BFFC_OK;
+}
+
+int bffc_plan_destroy(bffc_plan* p) {
+  if (!p) return BFFC_OK;
+  cudaFree(p->dftC);
+  cudaFree(p->dftS);
+  cudaFree(p->bsmall);
+  cudaFree(p->perm);
+  delete p;
+  return BFFC_OK;
+}
+
+int bffc_kf_pack(const bffc_plan* p, const void* kf_natural, void* kf_engine, int H, int conj, void* stream) {
+  if (!p || !kf_natural || !kf_engine || H <= 0) return fail(BFFC_ERR_INVALID, "bffc_kf_pack: bad argument");
+  dim3 grid((p->N + 255) / 256 > 64 ? 64 : (p->N + 255) / 256, H);
+  kf_pack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float2*>(kf_natural), static_cast<uint32_t*>(kf_engine), p->perm, p->N, 1.0f / float(p->N),
+      conj);
+  CUDA_TRY(cudaGetLastError());
+  return BFFC_OK;
+}
+
+int bffc_dkf_unpack(const bffc_plan*, const void*, void*, int, void*) {
+  return fail(BFFC_ERR_UNSUPPORTED, "bffc_dkf_unpack: backward not implemented yet");
+}
+
+size_t bffc_workspace_bytes(const bffc_plan*, int, int, int) { return 0; }
+
+static int make_map(CUtensorMap* map, const void* base, int BH, int L) {
+  // (B*H, L) bf16 viewed as [seq][row = L/64][col = 64]; box = one (128 x 64) tile, 128B swizzle;
+  // rows >= L/64 are out of bounds: zero-filled on load (implicit padding), dropped on store.
+  cuuint64_t dims[3] = {64, cuuint64_t(L / 64), cuuint64_t(BH)};
+  cuuint64_t strides[2] = {128, cuuint64_t(L) * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(BFFC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+  return 0;
+}
+
+static int launch_fwd(const bffc_plan* p, const void* u, const void* kf, void* y, int B, int H, int L, float* dbg,
+                      int dbg_stages, int max_units, void* stream) {
+  if (!p || !u || !kf || !y) return fail(BFFC_ERR_INVALID, "bffc_fwd: null pointer");
+  if (B <= 0 || H <= 0 || L <= 0 || L > p->N) return fail(BFFC_ERR_INVALID, "bffc_fwd: bad shape B=%d H=%d L=%d", B, H, L);
+  if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "bffc_fwd: L=%d must be a multiple of 64 in this build", L);
+  if ((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(kf)) & 15)
+    return fail(BFFC_ERR_INVALID, "bffc_fwd: u, y and kf must be 16-byte aligned");
+  CUtensorMap tm_u, tm_y;
+  if (int rc = make_map(&tm_u, u, B * H, L)) return rc;
+  if (int rc = make_map(&tm_y, y, B * H, L)) return rc;
+  bffc::FwdParams prm;
+  prm.kf = static_cast<const uint32_t*>(kf);
+  prm.dftC = p->dftC;
+  prm.dftS = p->dftS;
+  prm.bsmall = p->bsmall;
+  prm.B = B;
+  prm.H = H;
+  prm.pairs = (B + 1) / 2;
+  prm.ksteps = (L / 64 + 15) / 16;
+  prm.units = H * prm.pairs;
+  if (max_units > 0 && prm.units > max_units) prm.units = max_units;
+  prm.dbg = dbg;
+  prm.dbg_stages = dbg_stages;
+  int grid = (prm.units + 1) / 2;
+  if (grid > p->num_sms) grid = p->num_sms;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dbg)
+    bffc::r128::fwd_kernel<true><<<grid, bffc::r128::kThreads, bffc::r128::kSmemTotal, st>>>(tm_u, tm_y, prm);
+  else
+    bffc::r128::fwd_kernel<false><<<grid, bffc::r128::kThreads, bffc::r128::kSmemTotal, st>>>(tm_u, tm_y, prm);
+  CUDA_TRY(cudaGetLastError());
+  g_launches = 1;
+  return BFFC_OK;
+}
+
+int bffc_fwd(const bffc_plan* p, const void* u, const void* kf, const void* pregate, const void* postgate, void* y,
+             int B, int H, int L, void*, size_t, void* stream) {
+  if ((pregate == nullptr) != (postgate == nullptr))
+    return fail(BFFC_ERR_INVALID, "bffc_fwd: pregate and postgate must both be given or both be null");
+  if (pregate) return fail(BFFC_ERR_UNSUPPORTED, "bffc_fwd: gating not implemented yet");
+  return launch_fwd(p, u, kf, y, B, H, L, nullptr, 0, 0, stream);
+}
+
+int bffc_bwd(const bffc_plan*, const void*, const void*, const void*, const void*, const void*, const void*, void*,
+             void*, void*, void*, int, int, int, void*, size_t, void*) {
+  return fail(BFFC_ERR_UNSUPPORTED, "bffc_bwd: not implemented yet");
+}
+
+int bffc_debug_fwd_stages(const bffc_plan* p, const void* u, const void* kf, void* y, int B, int H, int L, float* dump,
+                          int max_stages, void* stream) {
+  if (!dump || max_stages <= 0) return -BFFC_ERR_INVALID;
+  int rc = launch_fwd(p, u, kf, y, B, H, L, dump, max_stages, 1, stream);
+  if (rc) return -rc;
+  return max_stages < 6 ? max_stages : 6;
+}
+
+}  // extern "C"

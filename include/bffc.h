@@ -1,0 +1,119 @@
+/*
+ * bffc.h — C ABI of the B200-native FFT long-convolution engine ("bffc").
+ *
+ * This is the drop-in boundary for ONE path of HazyResearch/flash-fft-conv: the fused
+ * FFT convolution  y = postgate * irfft-like( FFT_N(pad(u*pregate)) * FFT_N(pad(k)) )[:L]
+ * behind  FlashFFTConv(seqlen, dtype)(u, k, pregate, postgate).
+ *
+ * Reference interfaces each entry point replaces (paths relative to the reference repo):
+ *   bffc_fwd          <- monarch_conv_forward_* / butterfly_*_forward pybind ops
+ *                        (csrc/flashfftconv/monarch.cpp:16-56, called from
+ *                        flashfftconv/conv.py:566-1734 and 3239-3853)
+ *   bffc_bwd          <- monarch_conv_backward_* ops (monarch.cpp:27-37; conv.py:1737-3233,
+ *                        3856-4958) incl. the host-side dk_f.sum(0) and forward recompute
+ *                        (monarch_cuda_interface_bwd_bf16.cu:798-808,1107-1114)
+ *   bffc_kf_layout    <- the k_f Monarch digit permutations done in Python per call
+ *                        (conv.py:640, :676, :1423-1424, :1632-1633) and their inverses
+ *                        for dk_f (conv.py:1818, :1862, :2954)
+ *   bffc_plan_*       <- FlashFFTConv.__init__ constant tables (conv.py:72-551)
+ *
+ * Conventions: plain pointers and sizes only, all data pointers are DEVICE pointers on the
+ * current CUDA device, all work is enqueued on the caller's `stream` (the reference used the
+ * legacy default stream).  The caller owns every buffer.  Return value 0 = success, non-zero =
+ * error; bffc_last_error() gives a message (thread-local).  No CPU fallback exists: on a machine
+ * without an sm_100 GPU every compute entry point fails with BFFC_ERR_NO_DEVICE.
+ */
+#ifndef BFFC_H_
+#define BFFC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFFC_ABI_VERSION 1
+
+/* element types of u / y / gates */
+#define BFFC_DTYPE_BF16 0
+#define BFFC_DTYPE_FP16 1
+
+/* error codes */
+#define BFFC_OK 0
+#define BFFC_ERR_INVALID 1     /* bad argument (shape, alignment, dtype)            */
+#define BFFC_ERR_UNSUPPORTED 2 /* seqlen / option not implemented                    */
+#define BFFC_ERR_NO_DEVICE 3   /* no CUDA device, or device is not sm_100            */
+#define BFFC_ERR_CUDA 4        /* a CUDA runtime / driver call or a launch failed    */
+
+typedef struct bffc_plan bffc_plan; /* opaque; immutable after creation; thread-safe to share */
+
+int bffc_abi_version(void);
+const char* bffc_last_error(void);
+
+/* 1 if `seqlen` (FFT size N) is supported by this build for `dtype`, else 0. No GPU needed. */
+int bffc_supported(int seqlen, int dtype);
+
+/*
+ * Create the per-(seqlen, dtype) plan on the current device: DFT matrices, stage twiddles and
+ * the k_f layout map live in device memory owned by the plan (replaces the register_buffer()
+ * tables of FlashFFTConv.__init__, conv.py:72-551).
+ */
+int bffc_plan_create(bffc_plan** plan, int seqlen, int dtype);
+int bffc_plan_destroy(bffc_plan* plan);
+
+/*
+ * Frequency-domain filter layout.  The engine consumes k_f = FFT_N(k)/N as packed complex
+ * (re, im) pairs in the plan's own digit order ("engine order"), H x N entries, element type
+ * = plan dtype (4 bytes per complex entry).
+ *
+ * bffc_kf_pack:   kf_natural : (H, N) complex64 (interleaved float2), natural frequency order,
+ *                 NOT yet scaled.  Writes kf_engine (H*N*4 bytes): engine order, scaled by 1/N,
+ *                 optionally conjugated (conj != 0, used by backward for du).
+ * bffc_dkf_unpack: dkf_engine : (H, N) float2 in engine order (as written by bffc_bwd)
+ *                 -> dkf_natural (H, N) complex64 natural order (conv.py:1818/1862/2954 analogue).
+ */
+int bffc_kf_pack(const bffc_plan* plan, const void* kf_natural, void* kf_engine, int H, int conj,
+                 void* stream);
+int bffc_dkf_unpack(const bffc_plan* plan, const void* dkf_engine, void* dkf_natural, int H,
+                    void* stream);
+
+/* Scratch the caller must provide to bffc_fwd / bffc_bwd (0 for fully fused sizes). */
+size_t bffc_workspace_bytes(const bffc_plan* plan, int B, int H, int L);
+
+/*
+ * Forward.  u, y, pregate, postgate: (B, H, L) contiguous, plan dtype, L <= N, L even.
+ * kf_engine: from bffc_kf_pack.  pregate/postgate: both NULL or both non-NULL
+ * (conv.py:557-558).  y[b,h,:] = postgate * circular_conv_N(pad(u*pregate), pad(k))[:L].
+ */
+int bffc_fwd(const bffc_plan* plan, const void* u, const void* kf_engine, const void* pregate,
+             const void* postgate, void* y, int B, int H, int L, void* workspace,
+             size_t workspace_bytes, void* stream);
+
+/*
+ * Backward.  dout, u (and gates) as in forward.  kf_engine_conj: bffc_kf_pack(..., conj=1).
+ * Outputs: du (B,H,L) plan dtype; dkf_engine (H, N) float2 fp32 accumulated over B inside the
+ * kernel (overwritten, not accumulated across calls); dpregate/dpostgate (B,H,L) plan dtype when
+ * gated (else NULL).  kf_engine (non-conjugated) is required when gated (forward recompute for
+ * dpostgate happens inside the same launch).
+ */
+int bffc_bwd(const bffc_plan* plan, const void* dout, const void* u, const void* kf_engine,
+             const void* kf_engine_conj, const void* pregate, const void* postgate, void* du,
+             void* dkf_engine, void* dpregate, void* dpostgate, int B, int H, int L,
+             void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernel launches the last bffc_fwd / bffc_bwd on this thread enqueued (bench.py). */
+int bffc_last_launch_count(void);
+
+/*
+ * Debug/bring-up hook (tests only): runs the forward for ONE (b-pair, h) unit and dumps the
+ * fp32 TMEM accumulator image after every MMA stage into `dump` (stages x 128 lanes x 128 cols
+ * floats).  Returns the number of stages written, or a negative error code.
+ */
+int bffc_debug_fwd_stages(const bffc_plan* plan, const void* u, const void* kf_engine, void* y,
+                          int B, int H, int L, float* dump, int max_stages, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFFC_H_ */
