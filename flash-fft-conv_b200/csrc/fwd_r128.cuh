@@ -208,7 +208,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   for (int unit = u_begin, n = 0; unit < u_end; ++unit, ++n) {
     const int slot = n & 1;
     const uint32_t sX = s_slot0 + slot * kSlotBytes;   // re tile; im tile at +kTileBytes
-    const bool first = kDebug && (gp == 0) && (n == 0);
+    const bool first = kDebug && (unit == 0);
     const int h = unit / p.pairs;
 
     // ---------------- stage 1: D1 = F128 * X   (lane = k1, cols [0,64) re, [64,128) im)
