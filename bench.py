@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for the fused FFT-convolution hot path.
+
+  python bench.py --gpus N --steps K --warmup W            # our sm_100a engine
+  python bench.py --impl reference --gpus N --steps K ...  # reference arm: the reference's CPU path
+                                                           # (tests/test_flashfftconv.py:5-13 oracle port)
+
+One "step" = one pass of the hot path over one synthetic batch of BASELINE.json's configs[1]
+(N=8192, B=16, H=768, bf16, ungated, L=N) per GPU.  Prints ONE JSON line (rank 0).  Multi-GPU runs shard
+B x H with no data-path collective (every (b,h) convolution is independent): each rank owns its own H=768
+channel block (weak scaling); NCCL is used only for the barrier / max-over-ranks timing.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'flash-fft-conv_b200'))
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (N, B, H, L, gated)
+    'c2': (8192, 16, 768, 8192, False),       # BASELINE.json configs[1]: M2-BERT dims, the metric's config
+}
+
+
+def algorithmic_bytes(N, B, H, L, gated):
+    """fwd ungated 4L per conv (+4L gates when gated) plus k_f once per channel (4N)."""
+    return (8 if gated else 4) * L * B * H + 4 * N * H
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md 'clocks line')."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                      '-i', str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(',')]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = []
+        for i, name in [(3, 'hw_slowdown'), (4, 'hw_thermal_slowdown'), (5, 'sw_thermal_slowdown'), (6, 'sw_power_cap')]:
+            if any(s[i].lower().startswith('active') for s in self.samples):
+                reasons.append(name)
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons,
+                'samples': len(self.samples)}
+
+
+def cpu_baseline(N, L, gated, budget_s=12.0):
+    """The reference's CPU path (oracle port of tests/test_flashfftconv.py:5-13) on the host cores,
+    on a bounded sample of the same workload: S convolutions of the true N / L, all threads."""
+    from oracle.fftconv_oracle import ref_fft_conv, ref_fft_conv_gated
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs, Hs = 4, 64                                    # 256 convolutions per call
+    g = torch.Generator().manual_seed(0)
+    u = torch.randn(Bs, Hs, L, generator=g).to(torch.bfloat16)
+    k = torch.randn(Hs, L, generator=g) / L ** 0.5
+    if gated:
+        pg = torch.randn(Bs, Hs, L, generator=g).to(torch.bfloat16)
+        qg = torch.randn(Bs, Hs, L, generator=g).to(torch.bfloat16)
+        fn = lambda: ref_fft_conv_gated(u, k, pg, qg, N)
+    else:
+        fn = lambda: ref_fft_conv(u, k, N)
+    fn()
+    t0 = time.perf_counter(); n = 0
+    while True:
+        fn(); n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 200:
+            break
+    return {'value': Bs * Hs * n / dt, 'unit': 'convs/s', 'cores': cores, 'kind': 'port',
+            'sample': f'{n} calls x {Bs * Hs} convs (B={Bs},H={Hs}) at N={N}, L={L}, fp32 torch.fft on CPU'}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    return rank, world, local
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    N, B, H, L, gated = WORKLOADS[args.workload]
+    from oracle.fftconv_oracle import ref_fft_conv
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs, Hs = 4, 64
+    g = torch.Generator().manual_seed(0)
+    u = torch.randn(Bs, Hs, L, generator=g).to(torch.bfloat16)
+    k = torch.randn(Hs, L, generator=g) / L ** 0.5
+    for _ in range(args.warmup):
+        ref_fft_conv(u, k, N)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ref_fft_conv(u, k, N)
+    dt = time.perf_counter() - t0
+    val = Bs * Hs * args.steps / dt
+    sample = f'each step = {Bs * Hs} convs (B={Bs},H={Hs}) of the N={N}, L={L} workload; fp32 torch.fft, {cores} threads'
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'fftconv_fwd_convs_per_sec', 'value': val, 'unit': 'convs/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{args.workload}: N={N} B={B} H={H} L={L} ungated (bounded CPU sample)'},
+        'cpu_baseline': {'value': val, 'unit': 'convs/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': 'convs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0}))
+
+
+def run_ours(args):
+    rank, world, local = dist_setup(args.gpus)
+    import __graft_entry__ as ge
+    ge.build()
+    from flashfftconv import FlashFFTConv, _lib
+    from flashfftconv.conv import _pack_kf, _ptr, _stream
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    N, B, H, L, gated = WORKLOADS[args.workload]
+    torch.manual_seed(1234 + rank)
+    conv = FlashFFTConv(N, dtype=torch.bfloat16).to(dev)
+    plan = conv.plan(dev)
+    u = torch.randn(B, H, L, device=dev).to(torch.bfloat16)
+    k = torch.randn(H, L, device=dev) / L ** 0.5
+    convs_per_step = B * H
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    # ---- (1) device-resident whole step through the public forward (k -> k_f -> fused conv)
+    for _ in range(args.warmup):
+        y = conv(u, k)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    launches = 0
+    e0.record()
+    for _ in range(args.steps):
+        y = conv(u, k)
+        launches += 1 + _lib.lib().bffc_last_launch_count()          # kf_pack + fused conv (our kernels only)
+    e1.record()
+    barrier()
+    step_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+
+    # ---- (2) dominant kernel alone (k_f pre-packed), CUDA events on the launching stream -> roofline
+    kf = _pack_kf(conv, plan, k, 0)
+    yk = torch.empty_like(u)
+
+    def kern():
+        _lib.check(_lib.lib().bffc_fwd(plan.handle, _ptr(u), _ptr(kf), None, None, _ptr(yk), B, H, L, None, 0, _stream()))
+    for _ in range(max(3, args.warmup)):
+        kern()
+    torch.cuda.synchronize()
+    k0 = torch.cuda.Event(enable_timing=True); k1 = torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        kern()
+    k1.record(); torch.cuda.synchronize()
+    kern_ms = k0.elapsed_time(k1) / args.steps
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    # ---- (3) end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    u_h = u.cpu().pin_memory(); k_h = k.cpu().pin_memory()
+    y_h = torch.empty_like(u_h).pin_memory()
+    u_d = torch.empty_like(u); k_d = torch.empty_like(k)
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step():
+        u_d.copy_(u_h, non_blocking=True); k_d.copy_(k_h, non_blocking=True)
+        yy = conv(u_d, k_d)
+        y_h.copy_(yy, non_blocking=True)
+    e2e_step()
+    barrier()
+    s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    s1.record()
+    barrier()
+    e2e_ms = max_over_ranks(s0.elapsed_time(s1) / e2e_steps)
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s'
+    abytes = algorithmic_bytes(N, B, H, L, gated)
+    achieved = abytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json'))).get(args.workload)
+    except Exception:
+        pass
+    out = {
+        'metric': 'fftconv_fwd_convs_per_sec', 'value': convs_per_step * world / (step_ms * 1e-3), 'unit': 'convs/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_ms,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+        'config': {'workload': f'{args.workload}: FlashFFTConv({N}, bf16) fwd, B={B} H={H} L={L} ungated per GPU '
+                               f'(BASELINE.json configs[1]); step = k->k_f (torch.fft + bffc_kf_pack) + fused conv',
+                   'l2': 'inputs+outputs 403 MB per step exceed the 126 MB L2 (no flush needed)',
+                   'sharding': 'B x H sharded over ranks, no data-path collective'},
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
+                     'traffic': traffic, 'kernel': 'bffc::r128::fwd_kernel', 'kernel_ms': kern_ms,
+                     'algorithmic_bytes': abytes, 'peak_source': peak_src,
+                     'kernel_convs_per_sec': convs_per_step / (kern_ms * 1e-3)},
+        'e2e': {'value': convs_per_step * world / (e2e_ms * 1e-3), 'unit': 'convs/s',
+                'h2d_bytes_per_step': u_h.numel() * 2 + k_h.numel() * 4, 'd2h_bytes_per_step': y_h.numel() * 2,
+                'ms_per_step': e2e_ms},
+        'gpu_launches': launches,
+        'clocks': sampler.summary() if sampler else None,
+    }
+    out['cpu_baseline'] = cpu_baseline(N, L, gated) if world == 1 else None
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1 and args.impl == 'ours':
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

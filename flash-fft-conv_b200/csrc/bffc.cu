@@ -74,27 +74,6 @@ uint16_t f2bf(double x) {  // round-to-nearest-even float -> bf16 bits
   return static_cast<uint16_t>((u + r) >> 16);
 }
 
-// A 16x16 (K x N) real matrix built from an 8x8 complex multiplier G[kidx][nidx]:
-//   rows (K): kmap[kk] = (part, kidx), cols (N): [re nidx 0..7 | im nidx 0..7]
-//   [re][re]=Gr  [re][im]=Gi  [im][re]=-Gi  [im][im]=Gr
-// stored as the canonical no-swizzle K-major UMMA B layout: element (n,k) at
-//   (n>>3)*256 + (k>>3)*128 + (n&7)*16 + (k&7)*2     (SBO=256, LBO=128)
-template <class GFn>
-void fill_small(uint8_t* dst, const int* kpart, const int* kidx, GFn G) {
-  for (int kk = 0; kk < 16; ++kk)
-    for (int n = 0; n < 16; ++n) {
-      const int npart = n >> 3, nidx = n & 7;
-      double gr, gi;
-      G(kidx[kk], nidx, gr, gi);
-      double v;
-      if (kpart[kk] == 0) v = (npart == 0) ? gr : gi;
-      else v = (npart == 0) ? -gi : gr;
-      const uint16_t b = f2bf(v);
-      const size_t off = size_t(n >> 3) * 256 + size_t(kk >> 3) * 128 + size_t(n & 7) * 16 + size_t(kk & 7) * 2;
-      memcpy(dst + off, &b, 2);
-    }
-}
-
 __global__ void kf_pack_kernel(const float2* __restrict__ kf_nat, uint32_t* __restrict__ kf_eng,
                                const int* __restrict__ perm, int N, float scale, int conj) {
   const int h = blockIdx.y;
@@ -115,7 +94,7 @@ struct bffc_plan {
   int device;
   __nv_bfloat16* dftC = nullptr;
   __nv_bfloat16* dftS = nullptr;
-  uint8_t* bsmall = nullptr;
+  uint8_t* gtiles = nullptr;
   int* perm = nullptr;  // engine index -> natural frequency index
   int num_sms = 0;
 };
@@ -157,44 +136,26 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   CUDA_TRY(cudaMemcpy(p->dftC, c.data(), c.size() * 2, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(p->dftS, s.data(), s.size() * 2, cudaMemcpyHostToDevice));
 
-  // inner 64 = 8 x 8 stage matrices (see fwd_r128.cuh for the K orders)
-  std::vector<uint8_t> small(bffc::r128::kNumSmall * bffc::r128::kSmallBytes, 0);
-  int part_nat[16], idx_nat[16], part_c[16], idx_c[16];
-  for (int kk = 0; kk < 16; ++kk) {
-    part_nat[kk] = kk >> 3;  idx_nat[kk] = kk & 7;                 // [re 0..7 | im 0..7]
-    const int cc = kk >> 3, r = kk & 7;                            // c-major: [re 4c..4c+3 | im 4c..4c+3]
-    part_c[kk] = r >> 2;     idx_c[kk] = 4 * cc + (r & 3);
-  }
-  // B2a: F8[j1,a] = exp(-2 pi i j1 a / 8)
-  fill_small(small.data() + 0 * 512, part_c, idx_c, [&](int j1, int a, double& gr, double& gi) {
-    const double ang = -2.0 * PI * double((j1 * a) & 7) / 8.0;
-    gr = cos(ang); gi = sin(ang);
-  });
-  for (int a = 0; a < 8; ++a) {
-    // B2b[a]: G_a[j2,d] = exp(-2 pi i (a j2 / 64 + j2 d / 8))
-    fill_small(small.data() + (1 + a) * 512, part_nat, idx_nat, [&](int j2, int d, double& gr, double& gi) {
-      const double ang = -2.0 * PI * double((a * j2 + 8 * j2 * d) & 63) / 64.0;
-      gr = cos(ang); gi = sin(ang);
-    });
-    // B3b[a]: H_a[d,j2] = exp(+2 pi i (j2 d / 8 + a j2 / 64))
-    fill_small(small.data() + (9 + a) * 512, part_nat, idx_nat, [&](int d, int j2, double& gr, double& gi) {
-      const double ang = 2.0 * PI * double((a * j2 + 8 * j2 * d) & 63) / 64.0;
-      gr = cos(ang); gi = sin(ang);
-    });
-  }
-  // B3a: iF8[a,j1] = exp(+2 pi i a j1 / 8)
-  fill_small(small.data() + 17 * 512, part_nat, idx_nat, [&](int a, int j1, double& gr, double& gi) {
-    const double ang = 2.0 * PI * double((j1 * a) & 7) / 8.0;
-    gr = cos(ang); gi = sin(ang);
-  });
-  CUDA_TRY(cudaMalloc(&p->bsmall, small.size()));
-  CUDA_TRY(cudaMemcpy(p->bsmall, small.data(), small.size(), cudaMemcpyHostToDevice));
+  // DFT-64 planes for the row-local stage: G = exp(-2 pi i k n / 64) = Gr + i Gi.  Stored as the MN-major
+  // B operand image: row k (K index) = 64 bf16 = 128 B, 16-byte chunk c of row k at chunk position c ^ (k & 7)
+  // (the 128B swizzle TMA / UMMA use), planes Gr then Gi.
+  std::vector<uint8_t> gt(2 * bffc::r128::kGTileBytes, 0);
+  for (int k = 0; k < 64; ++k)
+    for (int n = 0; n < 64; ++n) {
+      const double ang = -2.0 * PI * double((k * n) & 63) / 64.0;
+      const uint16_t gr = f2bf(cos(ang)), gi = f2bf(sin(ang));
+      const size_t off = size_t(k) * 128 + (size_t((n >> 3) ^ (k & 7)) << 4) + size_t(n & 7) * 2;
+      memcpy(gt.data() + off, &gr, 2);
+      memcpy(gt.data() + bffc::r128::kGTileBytes + off, &gi, 2);
+    }
+  CUDA_TRY(cudaMalloc(&p->gtiles, gt.size()));
+  CUDA_TRY(cudaMemcpy(p->gtiles, gt.data(), gt.size(), cudaMemcpyHostToDevice));
 
-  // engine order: e = k1*64 + 8*a + d  <->  natural k = k1 + 128*(a + 8*d)
+  // engine order: e = ((c*128 + k1)*4 + r), k2 = 4c + r  <->  natural k = k1 + 128*k2
   std::vector<int> perm(seqlen);
-  for (int k1 = 0; k1 < 128; ++k1)
-    for (int a = 0; a < 8; ++a)
-      for (int d = 0; d < 8; ++d) perm[k1 * 64 + 8 * a + d] = k1 + 128 * (a + 8 * d);
+  for (int c = 0; c < 16; ++c)
+    for (int k1 = 0; k1 < 128; ++k1)
+      for (int r = 0; r < 4; ++r) perm[(c * 128 + k1) * 4 + r] = k1 + 128 * (4 * c + r);
   CUDA_TRY(cudaMalloc(&p->perm, perm.size() * sizeof(int)));
   CUDA_TRY(cudaMemcpy(p->perm, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice));
 
@@ -210,7 +171,7 @@ int bffc_plan_destroy(bffc_plan* p) {
   if (!p) return BFFC_OK;
   cudaFree(p->dftC);
   cudaFree(p->dftS);
-  cudaFree(p->bsmall);
+  cudaFree(p->gtiles);
   cudaFree(p->perm);
   delete p;
   return BFFC_OK;
@@ -260,7 +221,10 @@ static int launch_fwd(const bffc_plan* p, const void* u, const void* kf, void* y
   prm.kf = static_cast<const uint32_t*>(kf);
   prm.dftC = p->dftC;
   prm.dftS = p->dftS;
-  prm.bsmall = p->bsmall;
+  prm.gtiles = p->gtiles;
+  prm.pregate = nullptr;
+  prm.postgate = nullptr;
+  prm.L = L;
   prm.B = B;
   prm.H = H;
   prm.pairs = (B + 1) / 2;
@@ -299,7 +263,7 @@ int bffc_debug_fwd_stages(const bffc_plan* p, const void* u, const void* kf, voi
   if (!dump || max_stages <= 0) return -BFFC_ERR_INVALID;
   int rc = launch_fwd(p, u, kf, y, B, H, L, dump, max_stages, 1, stream);
   if (rc) return -rc;
-  return max_stages < 6 ? max_stages : 6;
+  return max_stages < 4 ? max_stages : 4;
 }
 
 }  // extern "C"

@@ -1,4 +1,4 @@
-// Fused forward FFT-convolution kernel, N = 128 x 64 (= 8192), bf16, sm_100a.
+// Fused forward FFT-convolution kernel, N = 128 x 64 (= 8192), bf16, sm_100a.   (v2)
 //
 // Path replaced (reference): monarch_conv_cuda_kernel<32,8,8192,...>
 // (csrc/flashfftconv/monarch_cuda/kernels_bf16/monarch_cuda_32_16_16_kernel_bf16.h:15-801) and its
@@ -6,32 +6,37 @@
 //
 //  * two real sequences (b, b+1) of one channel h are packed as ONE complex sequence z = u_b + i u_{b+1};
 //    conv(z, k) = conv(u_b,k) + i conv(u_{b+1},k) because k is real, so no Hermitian split is needed.
-//  * N = 128 * 64, n = i*64 + j.  Stage 1 contracts i with the 128x128 DFT matrix as the tcgen05 A operand
-//    (resident in TMEM for the whole kernel) and the TMA-loaded (128 x 64) input tile as an MN-major B
-//    operand: D1[k1, j] lands in TMEM with lane = k1.
-//  * everything between stage 1 and the last stage is "row local": lane k1 owns the 64-point transform
-//    over j, done as 8 x 8 with tiny (N=16,K=16) MMAs whose A operand is re-packed in TMEM by the owning
-//    thread (tcgen05.ld -> twiddle in fp32 registers -> bf16x2 -> tcgen05.st).  The inner twiddles
-//    W_64^{a*j2} are folded into the per-block B matrices; the lane dependent twiddle W_N^{k1*j} is
-//    factored as W^{8*k1*j1} (pass 1) * W^{k1*j2} (pass 2) so each thread keeps only 16 complex factors.
-//  * the last stage contracts k1 (the lane index), so its input is written to shared memory as the
-//    MN-major B operand; the output accumulator has lane = i and is stored with TMA.
-//  * a CTA runs two independent "pipelines" (warpgroups); while one waits on its MMAs the other runs its
-//    CUDA-core pass.  No intermediate ever touches HBM.
+//  * N = 128 * 64, n = i*64 + j.  Stage 1 contracts i: the 128x128 DFT matrix (cos / sin planes) is the
+//    tcgen05 A operand and stays resident in TMEM for the whole kernel; the TMA-loaded (128 x 64) input tile
+//    is the MN-major B operand.  D1[k1, j] lands in TMEM with lane = k1.
+//  * stage 2 is "row local": lane k1 owns the 64-point transform over j.  The owning threads re-pack the
+//    accumulator in TMEM as the next A operand (tcgen05.ld -> twiddle W_N^{k1 j} in fp32 registers ->
+//    bf16x2 -> tcgen05.st) and one radix-64 complex MMA (4 real K=64 chains against the DFT-64 cos / sin
+//    tiles in shared memory) produces Z[k1, k2], frequency k = k1 + 128*k2.
+//  * pass 3 multiplies by k_f (pre-permuted to this order, "engine order"), stage 3 is the inverse radix-64.
+//  * stage 4 contracts k1 (the lane index), so pass 5 writes its input to shared memory as the MN-major B
+//    operand (same swizzled layout TMA produces); the output accumulator has lane = i; pass 6 converts to
+//    bf16 and the tile is stored with TMA.
+//  * a CTA runs two independent pipelines of 256 threads (two warpgroups each: the warpgroups split the
+//    columns of every pass).  While one pipeline waits on its MMAs the other runs its CUDA-core pass.
+//    No intermediate ever touches HBM.
 #pragma once
 #include "ptx.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 namespace bffc {
 
 struct FwdParams {
-  const uint32_t* kf;        // [H][128][64] packed (re | im<<16) bf16, engine order, scaled 1/N
+  const uint32_t* kf;        // [rows][16][128][4] packed (re | im<<16) bf16, engine order, scaled 1/N
   const __nv_bfloat16* dftC; // [128][128] cos(2*pi*m*k/128)
   const __nv_bfloat16* dftS; // [128][128] sin(2*pi*m*k/128)
-  const uint8_t* bsmall;     // kNumSmall x 512 B, canonical no-swizzle K-major 16x16 bf16 B matrices
-  int B, H;                  // batch, channels
+  const uint8_t* gtiles;     // DFT-64 tiles: Gr then Gi, each 64 rows x 128 B, 128B-swizzled image
+  const uint32_t* pregate;   // optional (B,H,L) bf16, or null
+  const uint32_t* postgate;
+  int B, H, L;               // batch, channels, sequence length
   int pairs;                 // ceil(B/2)
-  int ksteps;                // number of 16-row K steps of the input tile that are non-zero (L/64/16 up)
+  int ksteps;                // number of 16-row K steps of the input tile that are non-zero
   int units;                 // H * pairs
   float* dbg;                // optional stage dump [stage][128][128]
   int dbg_stages;
@@ -39,45 +44,46 @@ struct FwdParams {
 
 namespace r128 {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
+constexpr int kPipeThreads = 256;
 constexpr int kTileBytes = 128 * 128;          // one (128 rows x 64 bf16) tile
 constexpr int kSlotBytes = 2 * kTileBytes;     // re tile + im tile
-constexpr int kNumSmall = 18;                  // B2a, B2b[8], B3b[8], B3a
-constexpr int kSmallBytes = 512;
+constexpr int kGTileBytes = 64 * 128;          // one DFT-64 plane
 constexpr int kSmemData = 4 * kSlotBytes;      // 2 pipelines x 2 slots
-constexpr int kSmemSmall = kNumSmall * kSmallBytes;
+constexpr int kSmemG = 2 * kGTileBytes;
 constexpr int kSmemBars = 64;
-constexpr int kSmemTotal = kSmemData + kSmemSmall + kSmemBars + 1024;  // + alignment slack
+constexpr int kSmemTotal = kSmemData + kSmemG + kSmemBars + 1024;  // + alignment slack
 
 // TMEM columns
-constexpr uint32_t kColC = 0, kColS = 64;                 // DFT cos / sin, bf16 K-major A operand
+constexpr uint32_t kColC = 0, kColS = 64;                 // DFT-128 cos / sin, bf16 K-major A operand
 DEVINL constexpr uint32_t colD(int pipe) { return 128 + 192 * pipe; }        // 128 fp32 cols
 DEVINL constexpr uint32_t colA(int pipe) { return 128 + 192 * pipe + 128; }  // 64 cols (bf16x2)
 
 constexpr uint32_t ID_N128_MN = make_idesc(1, 128, true, false);
 constexpr uint32_t ID_N64_MN = make_idesc(1, 64, true, false);
 constexpr uint32_t ID_N64_MN_NEG = make_idesc(1, 64, true, true);
-constexpr uint32_t ID_N16_K = make_idesc(1, 16, false, false);
 
 DEVINL void cmul(float ar, float ai, float br, float bi, float& cr, float& ci) {
   cr = ar * br - ai * bi;
   ci = ar * bi + ai * br;
 }
+DEVINL uint64_t tile_desc(uint32_t saddr) { return make_sdesc(saddr, kTileBytes, 1024, 2); }
 
 template <bool kDebug>
 __global__ void __launch_bounds__(kThreads, 1)
 fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_y, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t s_small = sbase + kSmemData;
-  const uint32_t s_bars = s_small + kSmemSmall;
+  const uint32_t s_g = sbase + kSmemData;            // Gr tile, Gi tile
+  const uint32_t s_bars = s_g + kSmemG;
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));  // generic pointer to aligned base
 
   const int tid = threadIdx.x;
-  const int pipe = tid >> 7;           // warpgroup = pipeline
+  const int pipe = tid >> 8;           // pipeline = pair of warpgroups
+  const int half = (tid >> 7) & 1;     // which 32-column half of every pass this warpgroup handles
   const int lane = tid & 127;          // TMEM lane owned by this thread (= k1, later = i)
   const int warp_q = (tid >> 5) & 3;   // TMEM sub-partition of this warp
-  const bool leader = (lane == 0);
+  const bool leader = ((tid & 255) == 0);
 
   const uint32_t bar_tma0 = s_bars + pipe * 24;       // two TMA barriers
   const uint32_t bar_mma = s_bars + pipe * 24 + 16;   // one MMA barrier
@@ -98,25 +104,25 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
     tmem_alloc(s_tmemptr, 512);
     tmem_relinquish();
   }
-  // small B matrices -> smem (generic proxy writes, later read by the MMA/async proxy)
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(p.bsmall);
+  {  // DFT-64 tiles -> smem (generic proxy writes, later read by the MMA/async proxy)
+    const uint4* src = reinterpret_cast<const uint4*>(p.gtiles);
     uint4* dst = reinterpret_cast<uint4*>(gen_base + kSmemData);
-    for (int i = tid; i < kSmemSmall / 16; i += kThreads) dst[i] = src[i];
+    for (int i = tid; i < kSmemG / 16; i += kThreads) dst[i] = src[i];
   }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + kSmemData + kSmemSmall + 48);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + kSmemData + kSmemG + 48);
   const uint32_t tlane = tmem_base + (uint32_t(warp_q * 32) << 16);  // this warp's lane window
 
-  // DFT matrices -> TMEM (pipeline 0 loads cos, pipeline 1 loads sin); row = lane, 128 bf16 = 64 cols
+  // DFT-128 matrices -> TMEM: pipeline 0 loads cos, pipeline 1 loads sin; row = lane (128 bf16 = 64 cols),
+  // each warpgroup of the pipeline loads 32 of the 64 columns.
   {
-    const uint4* row = reinterpret_cast<const uint4*>((pipe == 0 ? p.dftC : p.dftS) + lane * 128);
-    const uint32_t tcol = tlane + (pipe == 0 ? kColC : kColS);
+    const uint4* row = reinterpret_cast<const uint4*>((pipe == 0 ? p.dftC : p.dftS) + lane * 128) + half * 8;
+    const uint32_t tcol = tlane + (pipe == 0 ? kColC : kColS) + 32 * half;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 2; ++q) {
       uint32_t v[16];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
@@ -128,15 +134,13 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
     tmem_st_wait();
   }
 
-  // lane dependent twiddles, factored:  W_N^{k1*j} = twA[j1] * twB[j2],  j = 8*j1 + j2
-  float twAr[8], twAi[8], twBr[8], twBi[8];
+  // lane dependent twiddles W_N^{k1*j}, j = 32*half + t, kept as packed half2 (cos, sin): |x| <= 1, 2^-12 rel.
+  __half2 tw[32];
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
+  for (int t = 0; t < 32; ++t) {
     float s, c;
-    sincospif(-2.0f * float((lane * 8 * t) & 8191) / 8192.0f, &s, &c);
-    twAr[t] = c; twAi[t] = s;
-    sincospif(-2.0f * float(lane * t) / 8192.0f, &s, &c);
-    twBr[t] = c; twBi[t] = s;
+    sincospif(-2.0f * float((lane * (32 * half + t)) & 8191) / 8192.0f, &s, &c);
+    tw[t] = __floats2half2_rn(c, s);
   }
 
   tc_fence_before();
@@ -157,6 +161,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   const uint32_t tC0 = tmem_base + kColC;
   const uint32_t tS0 = tmem_base + kColS;
   const uint32_t bar_id = 1 + pipe;
+  const uint32_t sGr = s_g, sGi = s_g + kGTileBytes;
 
   auto seq_index = [&](int unit, int which) {   // global sequence index (b*H + h) of the re / im member
     const int h = unit / p.pairs, pr = unit - h * p.pairs;
@@ -178,11 +183,11 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
     mma_phase ^= 1;
     tc_fence_after();
   };
-  // all 128 threads finished writing TMEM (st) / smem; hand over to the MMA issuer
+  // all 256 threads of the pipeline finished writing TMEM (st) / smem; hand over to the MMA issuer
   auto sync_pipe_tmem = [&]() {
     tmem_st_wait();
     tc_fence_before();
-    named_bar_sync(bar_id, 128);
+    named_bar_sync(bar_id, kPipeThreads);
   };
   int dbg_stage = 0;
   auto dump = [&](bool first) {
@@ -190,17 +195,28 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
       if (first && p.dbg != nullptr && dbg_stage < p.dbg_stages) {
         float* o = p.dbg + (size_t(dbg_stage) * 128 + lane) * 128;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t v[32];
-          tmem_ld32(tD + 32 * c, v);
+          tmem_ld32(tD + 64 * c + 32 * half, v);
           tmem_ld_wait();
           reg_fence(v);
 #pragma unroll
-          for (int t = 0; t < 32; ++t) o[32 * c + t] = __uint_as_float(v[t]);
+          for (int t = 0; t < 32; ++t) o[64 * c + 32 * half + t] = __uint_as_float(v[t]);
         }
       }
       ++dbg_stage;
     }
+  };
+  // 16 complex values of this thread's half -> A operand layout
+  //   A: re part cols [0,32) (K index = column index 0..63), im part cols [32,64)
+  auto pack_store_A = [&](const float (&vr)[16], const float (&vi)[16], int sub) {
+    uint32_t o[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = pack_bf16x2(vr[2 * q], vr[2 * q + 1]);
+    tmem_st8(tA + 16 * half + 8 * sub, o);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = pack_bf16x2(vi[2 * q], vi[2 * q + 1]);
+    tmem_st8(tA + 32 + 16 * half + 8 * sub, o);
   };
 
   if (leader && u_begin < u_end) issue_load(u_begin, 0);
@@ -216,206 +232,124 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
       mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
       tc_fence_after();
       // D[:,0:128]  = C * [Xr | Xi]
-      for (int s = 0; s < p.ksteps; ++s)
-        mma_ts(tD0, tC0 + 8 * s, make_sdesc(sX + s * 2048, kTileBytes, 1024, 2), ID_N128_MN, s > 0);
+      for (int s = 0; s < p.ksteps; ++s) mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, s > 0);
       // D[:,0:64]  += S * Xi ;  D[:,64:128] += (-S) * Xr        (F = C - iS)
       for (int s = 0; s < p.ksteps; ++s)
-        mma_ts(tD0, tS0 + 8 * s, make_sdesc(sX + kTileBytes + s * 2048, kTileBytes, 1024, 2), ID_N64_MN, 1);
-      for (int s = 0; s < p.ksteps; ++s)
-        mma_ts(tD0 + 64, tS0 + 8 * s, make_sdesc(sX + s * 2048, kTileBytes, 1024, 2), ID_N64_MN_NEG, 1);
+        mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN, 1);
+      for (int s = 0; s < p.ksteps; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN_NEG, 1);
       mma_commit(bar_mma);
       if (unit + 1 < u_end) {      // prefetch next unit into the other slot (its last reader: TMA store)
         tma_store_wait_read0();
         issue_load(unit + 1, slot ^ 1);
       }
     }
+    // k_f for pass 3: 32 packed complex of this (lane, half), coalesced 16 B per thread per chunk
+    uint4 kfv[8];
+    {
+      const uint4* kfp = reinterpret_cast<const uint4*>(p.kf) + (size_t(h) * 16 + 8 * half) * 128 + lane;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) kfv[c] = __ldg(kfp + c * 128);
+    }
     wait_mma();
     dump(first);
 
-    // ---------------- pass 1: * W^{8*k1*j1}, pack A1: block j2 = cols [8*j2, 8*j2+8)
-    //   K order inside block: c-major, [re j1=4c..4c+3 | im j1=4c..4c+3]
+    // ---------------- pass 1: * W^{k1*j} -> A1
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t re[32], im[32];
-      tmem_ld32(tD + 32 * c, re);
-      tmem_ld32(tD + 64 + 32 * c, im);
+    for (int sub = 0; sub < 2; ++sub) {
+      uint32_t re[16], im[16];
+      tmem_ld16(tD + 32 * half + 16 * sub, re);
+      tmem_ld16(tD + 64 + 32 * half + 16 * sub, im);
       tmem_ld_wait();
       reg_fence(re); reg_fence(im);
+      float vr[16], vi[16];
 #pragma unroll
-      for (int j2 = 0; j2 < 8; ++j2) {
-        float vr[4], vi[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-          cmul(__uint_as_float(re[8 * r + j2]), __uint_as_float(im[8 * r + j2]), twAr[4 * c + r], twAi[4 * c + r],
-               vr[r], vi[r]);
-        tmem_st4(tA + 8 * j2 + 4 * c, pack_bf16x2(vr[0], vr[1]), pack_bf16x2(vr[2], vr[3]),
-                 pack_bf16x2(vi[0], vi[1]), pack_bf16x2(vi[2], vi[3]));
+      for (int t = 0; t < 16; ++t) {
+        const float2 w = __half22float2(tw[16 * sub + t]);
+        cmul(__uint_as_float(re[t]), __uint_as_float(im[t]), w.x, w.y, vr[t], vi[t]);
       }
+      pack_store_A(vr, vi, sub);
     }
     sync_pipe_tmem();
-    // ---------------- stage 2a: contract j1 (8 blocks, one per j2)  D block j2 = cols [16*j2,+16) [re a | im a]
+    // ---------------- stage 2: radix-64 over j.  G = Gr + i Gi = exp(-2 pi i j k2 / 64)
+    //   D[:,0:64] = re*Gr - im*Gi ;  D[:,64:128] = re*Gi + im*Gr
     if (leader) {
       tc_fence_after();
-      const uint64_t b2a = make_sdesc(s_small + 0 * kSmallBytes, 128, 256, 0);
-#pragma unroll
-      for (int j2 = 0; j2 < 8; ++j2) mma_ts(tD0 + 16 * j2, tA0 + 8 * j2, b2a, ID_N16_K, 0);
+      for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 8 * s, tile_desc(sGr + s * 2048), ID_N64_MN, s > 0);
+      for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 32 + 8 * s, tile_desc(sGi + s * 2048), ID_N64_MN_NEG, 1);
+      for (int s = 0; s < 4; ++s) mma_ts(tD0 + 64, tA0 + 8 * s, tile_desc(sGi + s * 2048), ID_N64_MN, s > 0);
+      for (int s = 0; s < 4; ++s) mma_ts(tD0 + 64, tA0 + 32 + 8 * s, tile_desc(sGr + s * 2048), ID_N64_MN, 1);
       mma_commit(bar_mma);
     }
     wait_mma();
     dump(first);
 
-    // ---------------- pass 2: * W^{k1*j2}; regroup to blocks by a: A2 block a = [re j2 0..7 | im j2 0..7]
+    // ---------------- pass 3: * k_f  (frequency k = k1 + 128*k2) -> A3 (same layout as A1)
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t re[8][4], im[8][4];
-#pragma unroll
-      for (int j2 = 0; j2 < 8; ++j2) {
-        tmem_ld4(tD + 16 * j2 + 4 * c, re[j2]);
-        tmem_ld4(tD + 16 * j2 + 8 + 4 * c, im[j2]);
-      }
+    for (int sub = 0; sub < 2; ++sub) {
+      uint32_t re[16], im[16];
+      tmem_ld16(tD + 32 * half + 16 * sub, re);
+      tmem_ld16(tD + 64 + 32 * half + 16 * sub, im);
       tmem_ld_wait();
       reg_fence(re); reg_fence(im);
+      float vr[16], vi[16];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        float vr[8], vi[8];
-#pragma unroll
-        for (int j2 = 0; j2 < 8; ++j2)
-          cmul(__uint_as_float(re[j2][a]), __uint_as_float(im[j2][a]), twBr[j2], twBi[j2], vr[j2], vi[j2]);
-        uint32_t o[8];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          o[q] = pack_bf16x2(vr[2 * q], vr[2 * q + 1]);
-          o[4 + q] = pack_bf16x2(vi[2 * q], vi[2 * q + 1]);
-        }
-        tmem_st8(tA + 8 * (4 * c + a), o);
+      for (int t = 0; t < 16; ++t) {
+        const uint4 kq = kfv[4 * sub + (t >> 2)];
+        const uint32_t kw = (t & 3) == 0 ? kq.x : (t & 3) == 1 ? kq.y : (t & 3) == 2 ? kq.z : kq.w;
+        cmul(__uint_as_float(re[t]), __uint_as_float(im[t]), __uint_as_float(kw << 16),
+             __uint_as_float(kw & 0xffff0000u), vr[t], vi[t]);
       }
+      pack_store_A(vr, vi, sub);
     }
     sync_pipe_tmem();
-    // ---------------- stage 2b: contract j2 (block a uses its own B with W_64^{a*j2} folded in)
+    // ---------------- stage 3: inverse radix-64.  conj G:  D[:,0:64] = re*Gr + im*Gi ; D[:,64:128] = -re*Gi + im*Gr
     if (leader) {
       tc_fence_after();
-#pragma unroll
-      for (int a = 0; a < 8; ++a)
-        mma_ts(tD0 + 16 * a, tA0 + 8 * a, make_sdesc(s_small + (1 + a) * kSmallBytes, 128, 256, 0), ID_N16_K, 0);
-      mma_commit(bar_mma);
-    }
-    // k_f row of this lane: 64 packed complex; issue the loads before blocking on the MMA barrier
-    const uint4* kfrow = reinterpret_cast<const uint4*>(p.kf + (size_t(h) * 128 + lane) * 64);
-    wait_mma();
-    dump(first);
-
-    // ---------------- pass 3: * k_f  (frequency k = k1 + 128*(a + 8*d)); same block layout in and out
-#pragma unroll
-    for (int a = 0; a < 8; ++a) {
-      uint32_t d[16];
-      tmem_ld16(tD + 16 * a, d);
-      const uint4 k0 = __ldg(kfrow + 2 * a), k1v = __ldg(kfrow + 2 * a + 1);
-      const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1v.x, k1v.y, k1v.z, k1v.w};
-      tmem_ld_wait();
-      reg_fence(d);
-      float vr[8], vi[8];
-#pragma unroll
-      for (int t = 0; t < 8; ++t)
-        cmul(__uint_as_float(d[t]), __uint_as_float(d[8 + t]), __uint_as_float(kw[t] << 16),
-             __uint_as_float(kw[t] & 0xffff0000u), vr[t], vi[t]);
-      uint32_t o[8];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        o[q] = pack_bf16x2(vr[2 * q], vr[2 * q + 1]);
-        o[4 + q] = pack_bf16x2(vi[2 * q], vi[2 * q + 1]);
-      }
-      tmem_st8(tA + 8 * a, o);
-    }
-    sync_pipe_tmem();
-    // ---------------- stage 3b: inverse of 2b (contract d -> j2)
-    if (leader) {
-      tc_fence_after();
-#pragma unroll
-      for (int a = 0; a < 8; ++a)
-        mma_ts(tD0 + 16 * a, tA0 + 8 * a, make_sdesc(s_small + (9 + a) * kSmallBytes, 128, 256, 0), ID_N16_K, 0);
+      for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 8 * s, tile_desc(sGr + s * 2048), ID_N64_MN, s > 0);
+      for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 32 + 8 * s, tile_desc(sGi + s * 2048), ID_N64_MN, 1);
+      for (int s = 0; s < 4; ++s) mma_ts(tD0 + 64, tA0 + 8 * s, tile_desc(sGi + s * 2048), ID_N64_MN_NEG, s > 0);
+      for (int s = 0; s < 4; ++s) mma_ts(tD0 + 64, tA0 + 32 + 8 * s, tile_desc(sGr + s * 2048), ID_N64_MN, 1);
       mma_commit(bar_mma);
     }
     wait_mma();
     dump(first);
 
-    // ---------------- pass 4: * conj W^{k1*j2}; regroup to blocks by j2: A4 block j2 = [re a | im a]
+    // ---------------- pass 5: * conj W^{k1*j}; write row k1 of the B operand [Yr | Yi] (MN-major, 128B swizzle)
+    //                  into the (now free) input slot.  16-byte chunk index = j / 8.
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t re[8][4], im[8][4];
-#pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        tmem_ld4(tD + 16 * a + 4 * c, re[a]);
-        tmem_ld4(tD + 16 * a + 8 + 4 * c, im[a]);
-      }
+    for (int sub = 0; sub < 2; ++sub) {
+      uint32_t re[16], im[16];
+      tmem_ld16(tD + 32 * half + 16 * sub, re);
+      tmem_ld16(tD + 64 + 32 * half + 16 * sub, im);
       tmem_ld_wait();
       reg_fence(re); reg_fence(im);
+      float vr[16], vi[16];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int j2 = 4 * c + t;
-        float vr[8], vi[8];
-#pragma unroll
-        for (int a = 0; a < 8; ++a)
-          cmul(__uint_as_float(re[a][t]), __uint_as_float(im[a][t]), twBr[j2], -twBi[j2], vr[a], vi[a]);
-        uint32_t o[8];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          o[q] = pack_bf16x2(vr[2 * q], vr[2 * q + 1]);
-          o[4 + q] = pack_bf16x2(vi[2 * q], vi[2 * q + 1]);
-        }
-        tmem_st8(tA + 8 * j2, o);
+      for (int t = 0; t < 16; ++t) {
+        const float2 w = __half22float2(tw[16 * sub + t]);
+        cmul(__uint_as_float(re[t]), __uint_as_float(im[t]), w.x, -w.y, vr[t], vi[t]);
       }
-    }
-    sync_pipe_tmem();
-    // ---------------- stage 3a: inverse of 2a (contract a -> j1), D block j2 = [re j1 | im j1]
-    if (leader) {
-      tc_fence_after();
-      const uint64_t b3a = make_sdesc(s_small + 17 * kSmallBytes, 128, 256, 0);
 #pragma unroll
-      for (int j2 = 0; j2 < 8; ++j2) mma_ts(tD0 + 16 * j2, tA0 + 8 * j2, b3a, ID_N16_K, 0);
-      mma_commit(bar_mma);
-    }
-    wait_mma();
-    dump(first);
-
-    // ---------------- pass 5: * conj W^{8*k1*j1}; write rows k1 of the B operand [Yr | Yi] (MN-major, 128B
-    //                  swizzle) into the (now free) input slot.  16-byte chunk index = j1.
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t re[8][4], im[8][4];
-#pragma unroll
-      for (int j2 = 0; j2 < 8; ++j2) {
-        tmem_ld4(tD + 16 * j2 + 4 * c, re[j2]);
-        tmem_ld4(tD + 16 * j2 + 8 + 4 * c, im[j2]);
-      }
-      tmem_ld_wait();
-      reg_fence(re); reg_fence(im);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int j1 = 4 * c + t;
-        float vr[8], vi[8];
-#pragma unroll
-        for (int j2 = 0; j2 < 8; ++j2)
-          cmul(__uint_as_float(re[j2][t]), __uint_as_float(im[j2][t]), twAr[j1], -twAi[j1], vr[j2], vi[j2]);
-        const uint32_t off = uint32_t(lane) * 128u + (uint32_t(j1 ^ (lane & 7)) << 4);
-        st_shared_v4(sX + off, pack_bf16x2(vr[0], vr[1]), pack_bf16x2(vr[2], vr[3]), pack_bf16x2(vr[4], vr[5]),
-                     pack_bf16x2(vr[6], vr[7]));
-        st_shared_v4(sX + kTileBytes + off, pack_bf16x2(vi[0], vi[1]), pack_bf16x2(vi[2], vi[3]),
-                     pack_bf16x2(vi[4], vi[5]), pack_bf16x2(vi[6], vi[7]));
+      for (int cc = 0; cc < 2; ++cc) {
+        const int chunk = 4 * half + 2 * sub + cc;
+        const uint32_t off = uint32_t(lane) * 128u + (uint32_t(chunk ^ (lane & 7)) << 4);
+        st_shared_v4(sX + off, pack_bf16x2(vr[8 * cc + 0], vr[8 * cc + 1]), pack_bf16x2(vr[8 * cc + 2], vr[8 * cc + 3]),
+                     pack_bf16x2(vr[8 * cc + 4], vr[8 * cc + 5]), pack_bf16x2(vr[8 * cc + 6], vr[8 * cc + 7]));
+        st_shared_v4(sX + kTileBytes + off, pack_bf16x2(vi[8 * cc + 0], vi[8 * cc + 1]),
+                     pack_bf16x2(vi[8 * cc + 2], vi[8 * cc + 3]), pack_bf16x2(vi[8 * cc + 4], vi[8 * cc + 5]),
+                     pack_bf16x2(vi[8 * cc + 6], vi[8 * cc + 7]));
       }
     }
     fence_proxy_async_smem();
     tc_fence_before();
-    named_bar_sync(bar_id, 128);
+    named_bar_sync(bar_id, kPipeThreads);
     // ---------------- stage 4: D4 = conj(F128) * Y   (lane = i, cols [0,64) -> seq b, [64,128) -> seq b+1)
     if (leader) {
       tc_fence_after();
-      for (int s = 0; s < 8; ++s)
-        mma_ts(tD0, tC0 + 8 * s, make_sdesc(sX + s * 2048, kTileBytes, 1024, 2), ID_N128_MN, s > 0);
+      for (int s = 0; s < 8; ++s) mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, s > 0);
       // D[:,0:64] += (-S) * Yi ;  D[:,64:128] += S * Yr       (conj F = C + iS)
-      for (int s = 0; s < 8; ++s)
-        mma_ts(tD0, tS0 + 8 * s, make_sdesc(sX + kTileBytes + s * 2048, kTileBytes, 1024, 2), ID_N64_MN_NEG, 1);
-      for (int s = 0; s < 8; ++s)
-        mma_ts(tD0 + 64, tS0 + 8 * s, make_sdesc(sX + s * 2048, kTileBytes, 1024, 2), ID_N64_MN, 1);
+      for (int s = 0; s < 8; ++s) mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN_NEG, 1);
+      for (int s = 0; s < 8; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN, 1);
       mma_commit(bar_mma);
     }
     wait_mma();
@@ -423,30 +357,28 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
 
     // ---------------- pass 6: fp32 -> bf16, rows i of the two output tiles (128B swizzle), TMA store
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t re[32], im[32];
-      tmem_ld32(tD + 32 * c, re);
-      tmem_ld32(tD + 64 + 32 * c, im);
-      tmem_ld_wait();
-      reg_fence(re); reg_fence(im);
+    for (int part = 0; part < 2; ++part) {          // 0: re -> sequence b, 1: im -> sequence b+1
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int cc = 4 * c + t;
-        const uint32_t off = uint32_t(lane) * 128u + (uint32_t(cc ^ (lane & 7)) << 4);
-        st_shared_v4(sX + off, pack_bf16x2(__uint_as_float(re[8 * t + 0]), __uint_as_float(re[8 * t + 1])),
-                     pack_bf16x2(__uint_as_float(re[8 * t + 2]), __uint_as_float(re[8 * t + 3])),
-                     pack_bf16x2(__uint_as_float(re[8 * t + 4]), __uint_as_float(re[8 * t + 5])),
-                     pack_bf16x2(__uint_as_float(re[8 * t + 6]), __uint_as_float(re[8 * t + 7])));
-        st_shared_v4(sX + kTileBytes + off,
-                     pack_bf16x2(__uint_as_float(im[8 * t + 0]), __uint_as_float(im[8 * t + 1])),
-                     pack_bf16x2(__uint_as_float(im[8 * t + 2]), __uint_as_float(im[8 * t + 3])),
-                     pack_bf16x2(__uint_as_float(im[8 * t + 4]), __uint_as_float(im[8 * t + 5])),
-                     pack_bf16x2(__uint_as_float(im[8 * t + 6]), __uint_as_float(im[8 * t + 7])));
+      for (int sub = 0; sub < 2; ++sub) {
+        uint32_t v[16];
+        tmem_ld16(tD + 64 * part + 32 * half + 16 * sub, v);
+        tmem_ld_wait();
+        reg_fence(v);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int chunk = 4 * half + 2 * sub + cc;
+          const uint32_t off = uint32_t(lane) * 128u + (uint32_t(chunk ^ (lane & 7)) << 4);
+          st_shared_v4(sX + part * kTileBytes + off,
+                       pack_bf16x2(__uint_as_float(v[8 * cc + 0]), __uint_as_float(v[8 * cc + 1])),
+                       pack_bf16x2(__uint_as_float(v[8 * cc + 2]), __uint_as_float(v[8 * cc + 3])),
+                       pack_bf16x2(__uint_as_float(v[8 * cc + 4]), __uint_as_float(v[8 * cc + 5])),
+                       pack_bf16x2(__uint_as_float(v[8 * cc + 6]), __uint_as_float(v[8 * cc + 7])));
+        }
       }
     }
     fence_proxy_async_smem();
     tc_fence_before();
-    named_bar_sync(bar_id, 128);
+    named_bar_sync(bar_id, kPipeThreads);
     if (leader) {
       const int pr = unit - h * p.pairs;
       tma_store_3d(&tm_y, sX, 0, 0, seq_index(unit, 0));

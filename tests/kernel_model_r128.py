@@ -25,17 +25,23 @@ def bf16_round(x):
 
 
 def engine_perm():
-    """engine index e = k1*64 + 8a + d  ->  natural frequency k = k1 + 128*(a + 8d)."""
-    k1 = np.arange(128)[:, None, None]
-    a = np.arange(8)[None, :, None]
-    d = np.arange(8)[None, None, :]
-    return (k1 + 128 * (a + 8 * d)).reshape(-1)
+    """engine index e = (c*128 + k1)*4 + r, k2 = 4c + r  ->  natural frequency k = k1 + 128*k2."""
+    c = np.arange(16)[:, None, None]
+    k1 = np.arange(128)[None, :, None]
+    r = np.arange(4)[None, None, :]
+    return (k1 + 128 * (4 * c + r)).reshape(-1)
+
+
+def half_round(x):
+    return np.asarray(x, dtype=np.float16).astype(np.float64)
 
 
 def model_fwd(x0, x1, kf_nat, quant=False, ksteps=8):
     """x0, x1: real sequences (length L <= N, zero padded here); kf_nat: FFT_N(k) natural order (complex).
-    Returns (y0, y1, stages) with stages = list of six (128,128) float64 images."""
+    Returns (y0, y1, stages) with stages = list of four (128,128) float64 TMEM images
+    (cols [0,64) real part, [64,128) imaginary part): D1 outer DFT, D2 spectrum, D3 after inverse radix-64, D4."""
     q = bf16_round if quant else (lambda v: np.asarray(v, dtype=np.float64))
+    qh = half_round if quant else (lambda v: np.asarray(v, dtype=np.float64))
     xr = np.zeros(N); xr[: len(x0)] = x0
     xi = np.zeros(N); xi[: len(x1)] = x1
     Xr = q(xr.reshape(R, M)); Xi = q(xi.reshape(R, M))       # tiles [i][j]
@@ -51,47 +57,27 @@ def model_fwd(x0, x1, kf_nat, quant=False, ksteps=8):
     Y = Dre + 1j * Dim                                         # [k1][j]
     k1 = np.arange(R)[:, None]
     j = np.arange(M)[None, :]
-    j1, j2 = j // 8, j % 8
-    twA = np.exp(-2j * np.pi * (k1 * 8 * j1) / N)
-    twB = np.exp(-2j * np.pi * (k1 * j2) / N)
+    tw = np.exp(-2j * np.pi * ((k1 * j) % N) / N)
+    tw = qh(tw.real) + 1j * qh(tw.imag)                        # kernel keeps the twiddles as half2
     # pass 1
-    Y1 = Y * twA
+    Y1 = Y * tw
     Y1 = q(Y1.real) + 1j * q(Y1.imag)
-    Y1 = Y1.reshape(R, 8, 8)                                   # [k1][j1][j2]
-    # stage 2a: contract j1 with F8[j1,a]
-    e8 = np.arange(8)
-    F8 = np.exp(-2j * np.pi * (e8[:, None] * e8[None, :]) / 8)
-    F8q = q(F8.real) + 1j * q(F8.imag)
-    U = np.einsum('kjt,ja->kta', Y1, F8q)                      # [k1][j2][a]
-    stages.append(np.concatenate([U.real, U.imag], axis=2).reshape(R, 128))   # block j2: [re a | im a]
-    # pass 2: * twB[j2]; regroup [k1][a][j2]
-    U2 = U * np.exp(-2j * np.pi * (np.arange(R)[:, None, None] * e8[None, :, None]) / N)
-    U2 = q(U2.real) + 1j * q(U2.imag)
-    U2 = U2.transpose(0, 2, 1)                                 # [k1][a][j2]
-    # stage 2b: block a: G_a[j2,d] = exp(-2 pi i (a j2/64 + j2 d/8))
-    a_ = e8[:, None, None]; j2_ = e8[None, :, None]; d_ = e8[None, None, :]
-    G = np.exp(-2j * np.pi * (a_ * j2_ / 64.0 + j2_ * d_ / 8.0))           # [a][j2][d]
-    Gq = q(G.real) + 1j * q(G.imag)
-    Z = np.einsum('kat,atd->kad', U2, Gq)                      # [k1][a][d]
-    stages.append(np.concatenate([Z.real, Z.imag], axis=2).reshape(R, 128))   # block a: [re d | im d]
-    # pass 3: * k_f (engine order), scaled 1/N, bf16
-    kfe = (np.asarray(kf_nat)[engine_perm()] / N).reshape(R, 8, 8)
+    # stage 2: radix-64, G[j,k2] = exp(-2 pi i j k2 / 64)
+    e = np.arange(M)
+    angg = -2 * np.pi * ((e[:, None] * e[None, :]) % 64) / 64.0
+    G = q(np.cos(angg)) + 1j * q(np.sin(angg))
+    Z = Y1 @ G                                                  # [k1][k2]
+    stages.append(np.concatenate([Z.real, Z.imag], axis=1))
+    # pass 3: * k_f[k1 + 128*k2] / N, bf16
+    kfe = (np.asarray(kf_nat).reshape(M, R).T) / N             # [k1][k2]
     kfe = q(kfe.real) + 1j * q(kfe.imag)
     V = Z * kfe
     V = q(V.real) + 1j * q(V.imag)
-    # stage 3b: H_a[d,j2] = conj(G_a[j2,d])
-    Hq = np.conj(Gq).transpose(0, 2, 1)                        # [a][d][j2]
-    Ui = np.einsum('kad,adt->kat', V, Hq)                      # [k1][a][j2]
-    stages.append(np.concatenate([Ui.real, Ui.imag], axis=2).reshape(R, 128))  # block a: [re j2 | im j2]
-    # pass 4: * conj twB[j2]; regroup [k1][j2][a]
-    Ui = Ui * np.exp(2j * np.pi * (np.arange(R)[:, None, None] * e8[None, None, :]) / N)
-    Ui = q(Ui.real) + 1j * q(Ui.imag)
-    Ui = Ui.transpose(0, 2, 1)                                 # [k1][j2][a]
-    # stage 3a: iF8[a,j1]
-    Yi = np.einsum('kta,aj->ktj', Ui, np.conj(F8q))            # [k1][j2][j1]
-    stages.append(np.concatenate([Yi.real, Yi.imag], axis=2).reshape(R, 128))  # block j2: [re j1 | im j1]
-    # pass 5: * conj twA[j1] -> smem rows [k1][j = 8 j1 + j2]
-    Yn = Yi.transpose(0, 2, 1).reshape(R, M) * np.conj(twA)
+    # stage 3: inverse radix-64
+    Yi = V @ np.conj(G)                                         # [k1][j]
+    stages.append(np.concatenate([Yi.real, Yi.imag], axis=1))
+    # pass 5: * conj tw -> smem rows
+    Yn = Yi * np.conj(tw)
     Yr = q(Yn.real); Yim = q(Yn.imag)
     # stage 4: conj F = C + iS
     Ore = C @ Yr - S @ Yim

@@ -107,7 +107,7 @@ def test_kernel_model_exact_and_quantised():
     k = rng.standard_normal(N) / np.sqrt(N)
     kf = np.fft.fft(k, N)
     y0, y1, stages = km.model_fwd(x0, x1, kf)
-    assert len(stages) == 6 and all(s.shape == (128, 128) for s in stages)
+    assert len(stages) == 4 and all(s.shape == (128, 128) for s in stages)
     assert np.abs(y0 - km.ref_conv(x0, k)).max() < 1e-10
     assert np.abs(y1 - km.ref_conv(x1, k)).max() < 1e-10
     # padded input (only 4 of 8 K-steps of stage 1 non-zero)

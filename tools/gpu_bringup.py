@@ -29,16 +29,16 @@ def main():
     k = torch.randn(H, L, device=dev) / (L ** 0.5)
     kf = _pack_kf(mod, plan, k, 0)
     y = torch.zeros_like(u)
-    dump = torch.zeros(6, 128, 128, device=dev, dtype=torch.float32)
-    rc = _lib.lib().bffc_debug_fwd_stages(plan.handle, _ptr(u), _ptr(kf), _ptr(y), B, H, L, _ptr(dump), 6, _stream())
+    dump = torch.zeros(4, 128, 128, device=dev, dtype=torch.float32)
+    rc = _lib.lib().bffc_debug_fwd_stages(plan.handle, _ptr(u), _ptr(kf), _ptr(y), B, H, L, _ptr(dump), 4, _stream())
     torch.cuda.synchronize()
     print('debug rc', rc, flush=True)
     kf_nat = torch.fft.fft(k.float(), n=N)[0].cpu().numpy().astype(np.complex128)
     x0 = u[0, 0].float().cpu().numpy().astype(np.float64); x1 = u[1, 0].float().cpu().numpy().astype(np.float64)
     y0m, y1m, st = km.model_fwd(x0, x1, kf_nat, quant=True)
     d = dump.cpu().numpy().astype(np.float64)
-    names = ['D1 outer DFT', 'D2a', 'D2b', 'D3b', 'D3a', 'D4 out']
-    for s in range(6):
+    names = ['D1 outer DFT', 'D2 spectrum', 'D3 inverse64', 'D4 out']
+    for s in range(4):
         ref = st[s]; got = d[s]
         err = np.abs(got - ref).max(); sc = np.abs(ref).max()
         print(f'stage {s} {names[s]:14s} max|ref|={sc:.4e} max err={err:.4e} rel={err/sc:.3e}', flush=True)
