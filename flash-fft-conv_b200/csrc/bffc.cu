@@ -9,6 +9,7 @@
 // No torch types cross this boundary; there is no CPU fallback.
 #include "bffc.h"
 #include "fwd_r128.cuh"
+#include "dkf_r128.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -74,15 +75,18 @@ uint16_t f2bf(double x) {  // round-to-nearest-even float -> bf16 bits
   return static_cast<uint16_t>((u + r) >> 16);
 }
 
-__global__ void kf_pack_kernel(const float2* __restrict__ kf_nat, uint32_t* __restrict__ kf_eng,
-                               const int* __restrict__ perm, int N, float scale, int conj) {
+__global__ void kf_pack_kernel(const float* __restrict__ kf_nat, uint32_t* __restrict__ kf_eng,
+                               const int* __restrict__ perm, int N, int pair_stride, float scale, int conj) {
   const int h = blockIdx.y;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < N; e += gridDim.x * blockDim.x) {
-    float2 v = kf_nat[size_t(h) * N + perm[e]];
-    v.x *= scale;
-    v.y *= conj ? -scale : scale;
-    __nv_bfloat162 b = __floats2bfloat162_rn(v.x, v.y);
-    kf_eng[size_t(h) * N + e] = *reinterpret_cast<uint32_t*>(&b);
+  const float* src = kf_nat + size_t(h) * N * 2;      // interleaved (re, im) fp32
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < N; w += gridDim.x * blockDim.x) {
+    const int pw = perm[w];
+    const int part = pw & 1;
+    const float sc = (part && conj) ? -scale : scale;
+    const float a = src[pw] * sc;                      // element k      (re or im)
+    const float b = src[pw + 2 * pair_stride] * sc;    // element k + pair_stride
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    kf_eng[size_t(h) * N + w] = *reinterpret_cast<uint32_t*>(&v);
   }
 }
 
@@ -139,30 +143,41 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   // DFT-64 planes for the row-local stage: G = exp(-2 pi i k n / 64) = Gr + i Gi.  Stored as the MN-major
   // B operand image: row k (K index) = 64 bf16 = 128 B, 16-byte chunk c of row k at chunk position c ^ (k & 7)
   // (the 128B swizzle TMA / UMMA use), planes Gr then Gi.
-  std::vector<uint8_t> gt(2 * bffc::r128::kGTileBytes, 0);
+  std::vector<uint8_t> gt(4 * bffc::r128::kGTileBytes, 0);   // tiles: Gr, Gi, -Gi, Gr
   for (int k = 0; k < 64; ++k)
     for (int n = 0; n < 64; ++n) {
       const double ang = -2.0 * PI * double((k * n) & 63) / 64.0;
-      const uint16_t gr = f2bf(cos(ang)), gi = f2bf(sin(ang));
+      const uint16_t gr = f2bf(cos(ang)), gi = f2bf(sin(ang)), ngi = f2bf(-sin(ang));
       const size_t off = size_t(k) * 128 + (size_t((n >> 3) ^ (k & 7)) << 4) + size_t(n & 7) * 2;
+      const size_t T = bffc::r128::kGTileBytes;
       memcpy(gt.data() + off, &gr, 2);
-      memcpy(gt.data() + bffc::r128::kGTileBytes + off, &gi, 2);
+      memcpy(gt.data() + T + off, &gi, 2);
+      memcpy(gt.data() + 2 * T + off, &ngi, 2);
+      memcpy(gt.data() + 3 * T + off, &gr, 2);
     }
   CUDA_TRY(cudaMalloc(&p->gtiles, gt.size()));
   CUDA_TRY(cudaMemcpy(p->gtiles, gt.data(), gt.size(), cudaMemcpyHostToDevice));
 
-  // engine order: e = ((c*128 + k1)*4 + r), k2 = 4c + r  <->  natural k = k1 + 128*k2
+  // engine order (32-bit words): w = (c*128 + k1)*4 + 2*pp + part holds the bf16 pair
+  //   (part ? imag : real) of k_f at k2 = 4c + 2pp and k2 + 1, natural frequency k = k1 + 128*k2.
+  // perm[w] = natural index of the first element * 2 + part; the second element is 128 further.
   std::vector<int> perm(seqlen);
   for (int c = 0; c < 16; ++c)
     for (int k1 = 0; k1 < 128; ++k1)
-      for (int r = 0; r < 4; ++r) perm[(c * 128 + k1) * 4 + r] = k1 + 128 * (4 * c + r);
+      for (int pp = 0; pp < 2; ++pp)
+        for (int part = 0; part < 2; ++part)
+          perm[(c * 128 + k1) * 4 + 2 * pp + part] = (k1 + 128 * (4 * c + 2 * pp)) * 2 + part;
   CUDA_TRY(cudaMalloc(&p->perm, perm.size() * sizeof(int)));
   CUDA_TRY(cudaMemcpy(p->perm, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice));
 
-  CUDA_TRY(cudaFuncSetAttribute(bffc::r128::fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_TRY(cudaFuncSetAttribute(bffc::r128::fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 bffc::r128::kSmemTotal));
-  CUDA_TRY(cudaFuncSetAttribute(bffc::r128::fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_TRY(cudaFuncSetAttribute(bffc::r128::fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 bffc::r128::kSmemTotal));
+  CUDA_TRY(cudaFuncSetAttribute(bffc::r128::fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                bffc::r128::kSmemTotalGated));
+  CUDA_TRY(cudaFuncSetAttribute(bffc::r128::dkf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                bffc::r128::kSmemTotalDkf));
   *out = p;
   return BFFC_OK;
 }
@@ -181,14 +196,19 @@ int bffc_kf_pack(const bffc_plan* p, const void* kf_natural, void* kf_engine, in
   if (!p || !kf_natural || !kf_engine || H <= 0) return fail(BFFC_ERR_INVALID, "bffc_kf_pack: bad argument");
   dim3 grid((p->N + 255) / 256 > 64 ? 64 : (p->N + 255) / 256, H);
   kf_pack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float2*>(kf_natural), static_cast<uint32_t*>(kf_engine), p->perm, p->N, 1.0f / float(p->N),
+      static_cast<const float*>(kf_natural), static_cast<uint32_t*>(kf_engine), p->perm, p->N, 128, 1.0f / float(p->N),
       conj);
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
 
-int bffc_dkf_unpack(const bffc_plan*, const void*, void*, int, void*) {
-  return fail(BFFC_ERR_UNSUPPORTED, "bffc_dkf_unpack: backward not implemented yet");
+int bffc_dkf_unpack(const bffc_plan* p, const void* dkf_engine, void* dkf_natural, int H, void* stream) {
+  if (!p || !dkf_engine || !dkf_natural || H <= 0) return fail(BFFC_ERR_INVALID, "bffc_dkf_unpack: bad argument");
+  dim3 grid(32, H);
+  bffc::r128::dkf_unpack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float2*>(dkf_engine), static_cast<float2*>(dkf_natural), p->N);
+  CUDA_TRY(cudaGetLastError());
+  return BFFC_OK;
 }
 
 size_t bffc_workspace_bytes(const bffc_plan*, int, int, int) { return 0; }
@@ -207,23 +227,26 @@ static int make_map(CUtensorMap* map, const void* base, int BH, int L) {
   return 0;
 }
 
-static int launch_fwd(const bffc_plan* p, const void* u, const void* kf, void* y, int B, int H, int L, float* dbg,
-                      int dbg_stages, int max_units, void* stream) {
+static int launch_fwd(const bffc_plan* p, const void* u, const void* kf, const void* pregate, const void* postgate,
+                      void* y, int B, int H, int L, float* dbg, int dbg_stages, int max_units, void* stream) {
   if (!p || !u || !kf || !y) return fail(BFFC_ERR_INVALID, "bffc_fwd: null pointer");
   if (B <= 0 || H <= 0 || L <= 0 || L > p->N) return fail(BFFC_ERR_INVALID, "bffc_fwd: bad shape B=%d H=%d L=%d", B, H, L);
   if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "bffc_fwd: L=%d must be a multiple of 64 in this build", L);
   if ((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(kf)) & 15)
     return fail(BFFC_ERR_INVALID, "bffc_fwd: u, y and kf must be 16-byte aligned");
-  CUtensorMap tm_u, tm_y;
+  if ((reinterpret_cast<uintptr_t>(pregate) | reinterpret_cast<uintptr_t>(postgate)) & 15)
+    return fail(BFFC_ERR_INVALID, "bffc_fwd: gates must be 16-byte aligned");
+  CUtensorMap tm_u, tm_y, tm_g;
   if (int rc = make_map(&tm_u, u, B * H, L)) return rc;
   if (int rc = make_map(&tm_y, y, B * H, L)) return rc;
+  if (int rc = make_map(&tm_g, pregate ? pregate : u, B * H, L)) return rc;
   bffc::FwdParams prm;
   prm.kf = static_cast<const uint32_t*>(kf);
   prm.dftC = p->dftC;
   prm.dftS = p->dftS;
   prm.gtiles = p->gtiles;
-  prm.pregate = nullptr;
-  prm.postgate = nullptr;
+  prm.pregate = static_cast<const uint32_t*>(pregate);
+  prm.postgate = static_cast<const uint32_t*>(postgate);
   prm.L = L;
   prm.B = B;
   prm.H = H;
@@ -236,10 +259,13 @@ static int launch_fwd(const bffc_plan* p, const void* u, const void* kf, void* y
   int grid = (prm.units + 1) / 2;
   if (grid > p->num_sms) grid = p->num_sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  using namespace bffc::r128;
   if (dbg)
-    bffc::r128::fwd_kernel<true><<<grid, bffc::r128::kThreads, bffc::r128::kSmemTotal, st>>>(tm_u, tm_y, prm);
+    fwd_kernel<true, false><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
+  else if (pregate)
+    fwd_kernel<false, true><<<grid, kThreads, kSmemTotalGated, st>>>(tm_u, tm_y, tm_g, prm);
   else
-    bffc::r128::fwd_kernel<false><<<grid, bffc::r128::kThreads, bffc::r128::kSmemTotal, st>>>(tm_u, tm_y, prm);
+    fwd_kernel<false, false><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
   CUDA_TRY(cudaGetLastError());
   g_launches = 1;
   return BFFC_OK;
@@ -249,19 +275,45 @@ int bffc_fwd(const bffc_plan* p, const void* u, const void* kf, const void* preg
              int B, int H, int L, void*, size_t, void* stream) {
   if ((pregate == nullptr) != (postgate == nullptr))
     return fail(BFFC_ERR_INVALID, "bffc_fwd: pregate and postgate must both be given or both be null");
-  if (pregate) return fail(BFFC_ERR_UNSUPPORTED, "bffc_fwd: gating not implemented yet");
-  return launch_fwd(p, u, kf, y, B, H, L, nullptr, 0, 0, stream);
+  return launch_fwd(p, u, kf, pregate, postgate, y, B, H, L, nullptr, 0, 0, stream);
 }
 
-int bffc_bwd(const bffc_plan*, const void*, const void*, const void*, const void*, const void*, const void*, void*,
-             void*, void*, void*, int, int, int, void*, size_t, void*) {
-  return fail(BFFC_ERR_UNSUPPORTED, "bffc_bwd: not implemented yet");
+int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf, const void* kf_conj,
+             const void* pregate, const void* postgate, void* du, void* dkf, void* dpregate, void* dpostgate, int B, int H,
+             int L, void*, size_t, void* stream) {
+  if ((pregate == nullptr) != (postgate == nullptr))
+    return fail(BFFC_ERR_INVALID, "bffc_bwd: pregate and postgate must both be given or both be null");
+  if (pregate) return fail(BFFC_ERR_UNSUPPORTED, "bffc_bwd: gated backward not implemented yet");
+  (void)kf; (void)dpregate; (void)dpostgate;
+  if (!p || !dout || !u || !kf_conj || !du || !dkf) return fail(BFFC_ERR_INVALID, "bffc_bwd: null pointer");
+  // du = corr(dout, k) = circular conv with conj(k_f): the forward kernel on dout (kernels_bf16/..._bwd_kernel_bf16.h:740-815)
+  if (int rc = launch_fwd(p, dout, kf_conj, nullptr, nullptr, du, B, H, L, nullptr, 0, 0, stream)) return rc;
+  // dk_f = sum_b FFT(dout) * conj(FFT(u))
+  if ((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(dkf)) & 15)
+    return fail(BFFC_ERR_INVALID, "bffc_bwd: u and dkf must be 16-byte aligned");
+  CUtensorMap tm_u, tm_d;
+  if (int rc = make_map(&tm_u, u, B * H, L)) return rc;
+  if (int rc = make_map(&tm_d, dout, B * H, L)) return rc;
+  bffc::DkfParams prm;
+  prm.dftC = p->dftC;
+  prm.dftS = p->dftS;
+  prm.gtiles = p->gtiles;
+  prm.dkf = static_cast<float2*>(dkf);
+  prm.B = B; prm.H = H; prm.L = L;
+  prm.pairs = (B + 1) / 2;
+  prm.ksteps = (L / 64 + 15) / 16;
+  int grid = H < p->num_sms ? H : p->num_sms;
+  bffc::r128::dkf_kernel<<<grid, bffc::r128::kThreads, bffc::r128::kSmemTotalDkf, static_cast<cudaStream_t>(stream)>>>(
+      tm_u, tm_d, prm);
+  CUDA_TRY(cudaGetLastError());
+  g_launches = 2;
+  return BFFC_OK;
 }
 
 int bffc_debug_fwd_stages(const bffc_plan* p, const void* u, const void* kf, void* y, int B, int H, int L, float* dump,
                           int max_stages, void* stream) {
   if (!dump || max_stages <= 0) return -BFFC_ERR_INVALID;
-  int rc = launch_fwd(p, u, kf, y, B, H, L, dump, max_stages, 1, stream);
+  int rc = launch_fwd(p, u, kf, nullptr, nullptr, y, B, H, L, dump, max_stages, 1, stream);
   if (rc) return -rc;
   return max_stages < 4 ? max_stages : 4;
 }

@@ -1,0 +1,259 @@
+// Backward filter-gradient kernel, N = 128 x 64 (= 8192), bf16, sm_100a.
+//
+// Path replaced (reference): the dk_f part of monarch_conv_bwd_cuda_kernel
+// (kernels_bf16/monarch_cuda_32_16_16_bwd_kernel_bf16.h:505-509,571-581,711-734: D = FFT(dout), X = FFT(u),
+// dk_f partial = sum over the CTA's batch tile of D * conj(X)) plus the host-side `dk_f_out.sum(0)` over the
+// (B/Bt, H, N, 2) bf16 partials (monarch_cuda_interface_bwd_bf16.cu:820,1107).  Here the sum over the whole
+// batch is accumulated in fp32 registers inside one CTA per channel; nothing but the final (H, N) complex
+// fp32 gradient is written.
+//
+// Pair packing: z_u = u_b + i u_{b+1}, z_d = dout_b + i dout_{b+1}.  FFT(z_d) * conj(FFT(z_u)) is the spectrum
+// of corr(d_b,u_b) + corr(d_{b+1},u_{b+1}) + i (cross terms); the cross terms are purely imaginary in the time
+// domain, and the caller takes the real part of the inverse FFT (as the reference does, conv.py:1817-1820),
+// so summing the packed products over pairs gives exactly dk.  An odd batch is completed with an all-zero
+// partner (TMA out-of-bounds fill).
+//
+// Machine mapping: pipeline 0 (threads 0..255) transforms the u pair, pipeline 1 the dout pair, with the
+// same stage-1 / pass-1 / stage-2 chain as the forward kernel (fwd_r128.cuh); then all 512 threads read
+// both spectra from TMEM and accumulate 16 complex products each.
+#pragma once
+#include "fwd_r128.cuh"
+
+namespace bffc {
+
+struct DkfParams {
+  const __nv_bfloat16* dftC;
+  const __nv_bfloat16* dftS;
+  const uint8_t* gtiles;
+  float2* dkf;               // [H][4][128][16] complex fp32: k2 = 16*q + t, frequency k = k1 + 128*k2
+  int B, H, L, pairs, ksteps;
+};
+
+namespace r128 {
+
+constexpr int kSmemTotalDkf = kSmemData + kSmemG + kSmemBars + 1024;
+
+__global__ void __launch_bounds__(kThreads, 1)
+dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_d, const DkfParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_g = sbase + kSmemData;
+  const uint32_t s_bars = s_g + kSmemG;
+  uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
+
+  const int tid = threadIdx.x;
+  const int pipe = tid >> 8;           // 0: u, 1: dout
+  const int half = (tid >> 7) & 1;
+  const int lane = tid & 127;
+  const int warp_q = (tid >> 5) & 3;
+  const bool lead_warp = ((tid & 255) < 32);
+
+  const uint32_t bar_tma0 = s_bars + pipe * 24;
+  const uint32_t bar_mma = s_bars + pipe * 24 + 16;
+  const uint32_t s_tmemptr = s_bars + 48;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_u);
+    tma_prefetch_desc(&tm_d);
+  }
+  if ((tid & 255) == 0) {
+    mbar_init(bar_tma0, 1);
+    mbar_init(bar_tma0 + 8, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (tid < 32) {
+    tmem_alloc(s_tmemptr, 512);
+    tmem_relinquish();
+  }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.gtiles);
+    uint4* dst = reinterpret_cast<uint4*>(gen_base + kSmemData);
+    for (int i = tid; i < kSmemG / 16; i += kThreads) dst[i] = src[i];
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + kSmemData + kSmemG + 48);
+  const uint32_t tlane = tmem_base + (uint32_t(warp_q * 32) << 16);
+  {
+    const uint4* row = reinterpret_cast<const uint4*>((pipe == 0 ? p.dftC : p.dftS) + lane * 128) + half * 8;
+    const uint32_t tcol = tlane + (pipe == 0 ? kColC : kColS) + 32 * half;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      uint32_t v[16];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        uint4 w = row[q * 4 + r];
+        v[4 * r + 0] = w.x; v[4 * r + 1] = w.y; v[4 * r + 2] = w.z; v[4 * r + 3] = w.w;
+      }
+      tmem_st16(tcol + 16 * q, v);
+    }
+    tmem_st_wait();
+  }
+  __half2 twc[16], tws[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    float s0, c0, s1, c1;
+    sincospif(-2.0f * float((lane * (32 * half + 2 * q)) & 8191) / 8192.0f, &s0, &c0);
+    sincospif(-2.0f * float((lane * (32 * half + 2 * q + 1)) & 8191) / 8192.0f, &s1, &c1);
+    twc[q] = __floats2half2_rn(c0, c1);
+    tws[q] = __floats2half2_rn(s0, s1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const uint32_t s_slot0 = sbase + pipe * 2 * kSlotBytes;
+  const uint32_t tD = tlane + colD(pipe);
+  const uint32_t tA = tlane + colA(pipe);
+  const uint32_t tDu = tlane + colD(0), tDd = tlane + colD(1);
+  const uint32_t tD0 = tmem_base + colD(pipe);
+  const uint32_t tA0 = tmem_base + colA(pipe);
+  const uint32_t tC0 = tmem_base + kColC;
+  const uint32_t tS0 = tmem_base + kColS;
+  const uint32_t bar_id = 1 + pipe;
+  const uint32_t sG0 = s_g;
+  const CUtensorMap* tm = (pipe == 0) ? &tm_u : &tm_d;
+  const int BH = p.B * p.H;
+
+  // units of this CTA: (h, pr) for h = blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int nh = (p.H - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int n_units = nh * p.pairs;
+  auto unit_h = [&](int n) { return int(blockIdx.x) + (n / p.pairs) * int(gridDim.x); };
+  auto issue_load = [&](int n, int slot) {
+    const int h = unit_h(n), pr = n % p.pairs;
+    const int b0 = 2 * pr, b1 = 2 * pr + 1;
+    const uint32_t bar = bar_tma0 + 8 * slot;
+    const uint32_t dst = s_slot0 + slot * kSlotBytes;
+    mbar_expect_tx(bar, kSlotBytes);
+    tma_load_3d(dst, tm, bar, 0, 0, b0 * p.H + h);
+    tma_load_3d(dst + kTileBytes, tm, bar, 0, 0, b1 < p.B ? b1 * p.H + h : BH);   // out of bounds -> zeros
+  };
+  uint32_t mma_phase = 0;
+  auto wait_mma = [&]() {
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+  };
+
+  if (lead_warp && n_units > 0) {
+    if (elect_one()) issue_load(0, 0);
+    __syncwarp();
+  }
+
+  f32x2 acc_r[8], acc_i[8];      // 16 complex accumulators: k2 = 16*(2*pipe+half) + 2*q + {0,1}
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { acc_r[q] = 0ull; acc_i[q] = 0ull; }
+
+  for (int n = 0; n < n_units; ++n) {
+    const int slot = n & 1;
+    const uint32_t sX = s_slot0 + slot * kSlotBytes;
+    // ---------------- stage 1
+    if (lead_warp) {
+      mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        for (int s = 0; s < p.ksteps; ++s) mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, s > 0);
+        for (int s = 0; s < p.ksteps; ++s)
+          mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN, 1);
+        for (int s = 0; s < p.ksteps; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN_NEG, 1);
+        mma_commit(bar_mma);
+        if (n + 1 < n_units) issue_load(n + 1, slot ^ 1);   // other slot: its stage 1 finished a unit ago
+      }
+      __syncwarp();
+    }
+    wait_mma();
+    // ---------------- pass 1
+#pragma unroll
+    for (int sub = 0; sub < 2; ++sub) {
+      uint32_t re[16], im[16];
+      tmem_ld16(tD + 32 * half + 16 * sub, re);
+      tmem_ld16(tD + 64 + 32 * half + 16 * sub, im);
+      tmem_ld_wait();
+      reg_fence(re); reg_fence(im);
+      uint32_t ore[8], oim[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float2 c = __half22float2(twc[8 * sub + q]), sn = __half22float2(tws[8 * sub + q]);
+        f32x2 vr, vi;
+        cmul2(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), pk2(c.x, c.y), pk2(sn.x, sn.y), vr, vi);
+        ore[q] = pack_bf16x2_v(vr);
+        oim[q] = pack_bf16x2_v(vi);
+      }
+      tmem_st8(tA + 16 * half + 8 * sub, ore);
+      tmem_st8(tA + 32 + 16 * half + 8 * sub, oim);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    named_bar_sync(bar_id, kPipeThreads);
+    // ---------------- stage 2
+    if (lead_warp) {
+      tc_fence_after();
+      if (elect_one()) {
+        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 8 * s, pair_desc(sG0 + s * 2048, 8192), ID_N128_MN, s > 0);
+        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 32 + 8 * s, pair_desc(sG0 + 16384 + s * 2048, 8192), ID_N128_MN, 1);
+        mma_commit(bar_mma);
+      }
+      __syncwarp();
+    }
+    wait_mma();
+    // ---------------- both spectra are in TMEM: accumulate Zd * conj(Zu) over this thread's 16 frequencies
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    {
+      const int qd = 2 * pipe + half;
+      uint32_t ur[16], ui[16], dr[16], di[16];
+      tmem_ld16(tDu + 16 * qd, ur);
+      tmem_ld16(tDu + 64 + 16 * qd, ui);
+      tmem_ld16(tDd + 16 * qd, dr);
+      tmem_ld16(tDd + 64 + 16 * qd, di);
+      tmem_ld_wait();
+      reg_fence(ur); reg_fence(ui); reg_fence(dr); reg_fence(di);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const f32x2 a = pk2u(dr[2 * q], dr[2 * q + 1]), b = pk2u(di[2 * q], di[2 * q + 1]);
+        const f32x2 c = pk2u(ur[2 * q], ur[2 * q + 1]), d = pk2u(ui[2 * q], ui[2 * q + 1]);
+        // (a + ib)(c - id) = (ac + bd) + i(bc - ad)
+        acc_r[q] = fma2(a, c, fma2(b, d, acc_r[q]));
+        acc_i[q] = fma2(b, c, acc_i[q]);
+        acc_i[q] = sub2(acc_i[q], mul2(a, d));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();       // D regions may be overwritten by the next stage 1
+    tc_fence_after();
+    // ---------------- channel finished: write its gradient spectrum
+    if ((n + 1) % p.pairs == 0) {
+      const int h = unit_h(n);
+      const int qd = 2 * pipe + half;
+      float4* out = reinterpret_cast<float4*>(p.dkf + ((size_t(h) * 4 + qd) * 128 + lane) * 16);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float r0, r1, i0, i1;
+        upk2(acc_r[q], r0, r1);
+        upk2(acc_i[q], i0, i1);
+        out[q] = make_float4(r0, i0, r1, i1);
+        acc_r[q] = 0ull; acc_i[q] = 0ull;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem_base, 512);
+}
+
+// dk_f engine order -> natural order complex64 (reference analogue: the inverse permutation at conv.py:1818)
+__global__ void dkf_unpack_kernel(const float2* __restrict__ eng, float2* __restrict__ nat, int N) {
+  const int h = blockIdx.y;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
+    const int k1 = k & 127, k2 = k >> 7;
+    nat[size_t(h) * N + k] = eng[((size_t(h) * 4 + (k2 >> 4)) * 128 + k1) * 16 + (k2 & 15)];
+  }
+}
+
+}  // namespace r128
+}  // namespace bffc

@@ -28,10 +28,10 @@
 namespace bffc {
 
 struct FwdParams {
-  const uint32_t* kf;        // [rows][16][128][4] packed (re | im<<16) bf16, engine order, scaled 1/N
+  const uint32_t* kf;        // [rows][16][128][4] bf16x2 words (kr0,kr1)(ki0,ki1)(kr2,kr3)(ki2,ki3), engine order, /N
   const __nv_bfloat16* dftC; // [128][128] cos(2*pi*m*k/128)
   const __nv_bfloat16* dftS; // [128][128] sin(2*pi*m*k/128)
-  const uint8_t* gtiles;     // DFT-64 tiles: Gr then Gi, each 64 rows x 128 B, 128B-swizzled image
+  const uint8_t* gtiles;     // DFT-64 tiles Gr, Gi, -Gi, Gr: each 64 rows x 128 B, 128B-swizzled image
   const uint32_t* pregate;   // optional (B,H,L) bf16, or null
   const uint32_t* postgate;
   int B, H, L;               // batch, channels, sequence length
@@ -50,9 +50,11 @@ constexpr int kTileBytes = 128 * 128;          // one (128 rows x 64 bf16) tile
 constexpr int kSlotBytes = 2 * kTileBytes;     // re tile + im tile
 constexpr int kGTileBytes = 64 * 128;          // one DFT-64 plane
 constexpr int kSmemData = 4 * kSlotBytes;      // 2 pipelines x 2 slots
-constexpr int kSmemG = 2 * kGTileBytes;
+constexpr int kSmemG = 4 * kGTileBytes;        // Gr, Gi, -Gi, Gr  (pairs at LBO 8K / 16K)
 constexpr int kSmemBars = 64;
+constexpr int kSmemGate = 2 * kSlotBytes;      // gated only: one pregate slot per pipeline
 constexpr int kSmemTotal = kSmemData + kSmemG + kSmemBars + 1024;  // + alignment slack
+constexpr int kSmemTotalGated = kSmemTotal + kSmemGate + 1024;
 
 // TMEM columns
 constexpr uint32_t kColC = 0, kColS = 64;                 // DFT-128 cos / sin, bf16 K-major A operand
@@ -68,14 +70,32 @@ DEVINL void cmul(float ar, float ai, float br, float bi, float& cr, float& ci) {
   ci = ar * bi + ai * br;
 }
 DEVINL uint64_t tile_desc(uint32_t saddr) { return make_sdesc(saddr, kTileBytes, 1024, 2); }
+// N=128 B operand made of two 64-column tiles `lbo` bytes apart
+DEVINL uint64_t pair_desc(uint32_t saddr, uint32_t lbo) { return make_sdesc(saddr, lbo, 1024, 2); }
 
-template <bool kDebug>
+DEVINL uint32_t hmul2_bf16(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+DEVINL uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// kGated: y = postgate * conv(u * pregate, k)  (reference: GatedFlashFFTConvFunc, conv.py:3239-3325).  The
+// pregate tiles arrive by TMA next to the input tiles and are multiplied in shared memory (bf16 product, as
+// the reference's __hmul2 on load, monarch_cuda_32_16_16_kernel_bf16.h:550-585); the postgate is read with
+// coalesced 16-byte loads in the output pass and applied to the bf16-rounded result.
+template <bool kDebug, bool kGated>
 __global__ void __launch_bounds__(kThreads, 1)
-fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_y, const FwdParams p) {
+fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_y,
+           const __grid_constant__ CUtensorMap tm_g, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_g = sbase + kSmemData;            // Gr tile, Gi tile
   const uint32_t s_bars = s_g + kSmemG;
+  const uint32_t s_gate0 = s_bars + kSmemBars + 960;   // (gated only) keeps 1024-byte alignment
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));  // generic pointer to aligned base
 
   const int tid = threadIdx.x;
@@ -83,7 +103,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   const int half = (tid >> 7) & 1;     // which 32-column half of every pass this warpgroup handles
   const int lane = tid & 127;          // TMEM lane owned by this thread (= k1, later = i)
   const int warp_q = (tid >> 5) & 3;   // TMEM sub-partition of this warp
-  const bool leader = ((tid & 255) == 0);
+  const bool lead_warp = ((tid & 255) < 32);   // warp that issues this pipeline's TMA / MMA (one elected lane)
 
   const uint32_t bar_tma0 = s_bars + pipe * 24;       // two TMA barriers
   const uint32_t bar_mma = s_bars + pipe * 24 + 16;   // one MMA barrier
@@ -93,8 +113,9 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   if (tid == 0) {
     tma_prefetch_desc(&tm_u);
     tma_prefetch_desc(&tm_y);
+    if (kGated) tma_prefetch_desc(&tm_g);
   }
-  if (leader) {
+  if ((tid & 255) == 0) {
     mbar_init(bar_tma0, 1);
     mbar_init(bar_tma0 + 8, 1);
     mbar_init(bar_mma, 1);
@@ -134,13 +155,16 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
     tmem_st_wait();
   }
 
-  // lane dependent twiddles W_N^{k1*j}, j = 32*half + t, kept as packed half2 (cos, sin): |x| <= 1, 2^-12 rel.
-  __half2 tw[32];
+  // lane dependent twiddles W_N^{k1*j} = c + i s, j = 32*half + 2q + {0,1}: kept as half2 pairs over two
+  // adjacent points (|x| <= 1, 2^-12 relative) so the fp32x2 complex multiply can use them directly.
+  __half2 twc[16], tws[16];
 #pragma unroll
-  for (int t = 0; t < 32; ++t) {
-    float s, c;
-    sincospif(-2.0f * float((lane * (32 * half + t)) & 8191) / 8192.0f, &s, &c);
-    tw[t] = __floats2half2_rn(c, s);
+  for (int q = 0; q < 16; ++q) {
+    float s0, c0, s1, c1;
+    sincospif(-2.0f * float((lane * (32 * half + 2 * q)) & 8191) / 8192.0f, &s0, &c0);
+    sincospif(-2.0f * float((lane * (32 * half + 2 * q + 1)) & 8191) / 8192.0f, &s1, &c1);
+    twc[q] = __floats2half2_rn(c0, c1);
+    tws[q] = __floats2half2_rn(s0, s1);
   }
 
   tc_fence_before();
@@ -161,7 +185,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   const uint32_t tC0 = tmem_base + kColC;
   const uint32_t tS0 = tmem_base + kColS;
   const uint32_t bar_id = 1 + pipe;
-  const uint32_t sGr = s_g, sGi = s_g + kGTileBytes;
+  const uint32_t sG0 = s_g;   // tiles: +0 Gr, +8K Gi, +16K -Gi, +24K Gr
 
   auto seq_index = [&](int unit, int which) {   // global sequence index (b*H + h) of the re / im member
     const int h = unit / p.pairs, pr = unit - h * p.pairs;
@@ -172,9 +196,14 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   auto issue_load = [&](int unit, int slot) {
     const uint32_t bar = bar_tma0 + 8 * slot;
     const uint32_t dst = s_slot0 + slot * kSlotBytes;
-    mbar_expect_tx(bar, kSlotBytes);
+    mbar_expect_tx(bar, kGated ? 2 * kSlotBytes : kSlotBytes);
     tma_load_3d(dst, &tm_u, bar, 0, 0, seq_index(unit, 0));
     tma_load_3d(dst + kTileBytes, &tm_u, bar, 0, 0, seq_index(unit, 1));
+    if (kGated) {   // single pregate slot per pipeline: free again once pass 0 of the current unit is done
+      const uint32_t gd = s_gate0 + pipe * kSlotBytes;
+      tma_load_3d(gd, &tm_g, bar, 0, 0, seq_index(unit, 0));
+      tma_load_3d(gd + kTileBytes, &tm_g, bar, 0, 0, seq_index(unit, 1));
+    }
   };
 
   uint32_t mma_phase = 0;
@@ -207,19 +236,11 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
       ++dbg_stage;
     }
   };
-  // 16 complex values of this thread's half -> A operand layout
-  //   A: re part cols [0,32) (K index = column index 0..63), im part cols [32,64)
-  auto pack_store_A = [&](const float (&vr)[16], const float (&vi)[16], int sub) {
-    uint32_t o[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) o[q] = pack_bf16x2(vr[2 * q], vr[2 * q + 1]);
-    tmem_st8(tA + 16 * half + 8 * sub, o);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) o[q] = pack_bf16x2(vi[2 * q], vi[2 * q + 1]);
-    tmem_st8(tA + 32 + 16 * half + 8 * sub, o);
-  };
+  if (lead_warp && u_begin < u_end) {
+    if (elect_one()) issue_load(u_begin, 0);
+    __syncwarp();
+  }
 
-  if (leader && u_begin < u_end) issue_load(u_begin, 0);
 
   for (int unit = u_begin, n = 0; unit < u_end; ++unit, ++n) {
     const int slot = n & 1;
@@ -227,10 +248,26 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
     const bool first = kDebug && (unit == 0);
     const int h = unit / p.pairs;
 
-    // ---------------- stage 1: D1 = F128 * X   (lane = k1, cols [0,64) re, [64,128) im)
-    if (leader) {
+    if (kGated) {
+      // ---------------- pass 0: X <- bf16(u * pregate), in place in shared memory (same swizzled positions)
       mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
+      const uint32_t sG = s_gate0 + pipe * kSlotBytes;
+#pragma unroll
+      for (int part = 0; part < 2; ++part)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t off = part * kTileBytes + uint32_t(lane) * 128u + uint32_t(4 * half + c) * 16u;
+          const uint4 a = ld_shared_v4(sX + off), g = ld_shared_v4(sG + off);
+          st_shared_v4(sX + off, hmul2_bf16(a.x, g.x), hmul2_bf16(a.y, g.y), hmul2_bf16(a.z, g.z), hmul2_bf16(a.w, g.w));
+        }
+      fence_proxy_async_smem();
+      named_bar_sync(bar_id, kPipeThreads);
+    }
+    // ---------------- stage 1: D1 = F128 * X   (lane = k1, cols [0,64) re, [64,128) im)
+    if (lead_warp) {
+      if (!kGated) mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
       tc_fence_after();
+      if (elect_one()) {
       // D[:,0:128]  = C * [Xr | Xi]
       for (int s = 0; s < p.ksteps; ++s) mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, s > 0);
       // D[:,0:64]  += S * Xi ;  D[:,64:128] += (-S) * Xr        (F = C - iS)
@@ -242,6 +279,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
         tma_store_wait_read0();
         issue_load(unit + 1, slot ^ 1);
       }
+      }
+      __syncwarp();
     }
     // k_f for pass 3: 32 packed complex of this (lane, half), coalesced 16 B per thread per chunk
     uint4 kfv[8];
@@ -253,7 +292,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
     wait_mma();
     dump(first);
 
-    // ---------------- pass 1: * W^{k1*j} -> A1
+    // ---------------- pass 1: * W^{k1*j} -> A1  (re part cols [0,32): K index = j, im part cols [32,64))
 #pragma unroll
     for (int sub = 0; sub < 2; ++sub) {
       uint32_t re[16], im[16];
@@ -261,24 +300,29 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
       tmem_ld16(tD + 64 + 32 * half + 16 * sub, im);
       tmem_ld_wait();
       reg_fence(re); reg_fence(im);
-      float vr[16], vi[16];
+      uint32_t ore[8], oim[8];
 #pragma unroll
-      for (int t = 0; t < 16; ++t) {
-        const float2 w = __half22float2(tw[16 * sub + t]);
-        cmul(__uint_as_float(re[t]), __uint_as_float(im[t]), w.x, w.y, vr[t], vi[t]);
+      for (int q = 0; q < 8; ++q) {
+        const float2 c = __half22float2(twc[8 * sub + q]), sn = __half22float2(tws[8 * sub + q]);
+        f32x2 vr, vi;
+        cmul2(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), pk2(c.x, c.y), pk2(sn.x, sn.y), vr, vi);
+        ore[q] = pack_bf16x2_v(vr);
+        oim[q] = pack_bf16x2_v(vi);
       }
-      pack_store_A(vr, vi, sub);
+      tmem_st8(tA + 16 * half + 8 * sub, ore);
+      tmem_st8(tA + 32 + 16 * half + 8 * sub, oim);
     }
     sync_pipe_tmem();
     // ---------------- stage 2: radix-64 over j.  G = Gr + i Gi = exp(-2 pi i j k2 / 64)
-    //   D[:,0:64] = re*Gr - im*Gi ;  D[:,64:128] = re*Gi + im*Gr
-    if (leader) {
+    //   D[:,0:128] = re * [Gr | Gi] + im * [-Gi | Gr]
+    if (lead_warp) {
       tc_fence_after();
-      for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 8 * s, tile_desc(sGr + s * 2048), ID_N64_MN, s > 0);
-      for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 32 + 8 * s, tile_desc(sGi + s * 2048), ID_N64_MN_NEG, 1);
-      for (int s = 0; s < 4; ++s) mma_ts(tD0 + 64, tA0 + 8 * s, tile_desc(sGi + s * 2048), ID_N64_MN, s > 0);
-      for (int s = 0; s < 4; ++s) mma_ts(tD0 + 64, tA0 + 32 + 8 * s, tile_desc(sGr + s * 2048), ID_N64_MN, 1);
-      mma_commit(bar_mma);
+      if (elect_one()) {
+        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 8 * s, pair_desc(sG0 + s * 2048, 8192), ID_N128_MN, s > 0);
+        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 32 + 8 * s, pair_desc(sG0 + 16384 + s * 2048, 8192), ID_N128_MN, 1);
+        mma_commit(bar_mma);
+      }
+      __syncwarp();
     }
     wait_mma();
     dump(first);
@@ -291,25 +335,30 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
       tmem_ld16(tD + 64 + 32 * half + 16 * sub, im);
       tmem_ld_wait();
       reg_fence(re); reg_fence(im);
-      float vr[16], vi[16];
+      uint32_t ore[8], oim[8];
 #pragma unroll
-      for (int t = 0; t < 16; ++t) {
-        const uint4 kq = kfv[4 * sub + (t >> 2)];
-        const uint32_t kw = (t & 3) == 0 ? kq.x : (t & 3) == 1 ? kq.y : (t & 3) == 2 ? kq.z : kq.w;
-        cmul(__uint_as_float(re[t]), __uint_as_float(im[t]), __uint_as_float(kw << 16),
-             __uint_as_float(kw & 0xffff0000u), vr[t], vi[t]);
+      for (int q = 0; q < 8; ++q) {
+        const uint4 kq = kfv[4 * sub + (q >> 1)];
+        const uint32_t wr = (q & 1) ? kq.z : kq.x, wi = (q & 1) ? kq.w : kq.y;
+        f32x2 vr, vi;
+        cmul2(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), pk2u(wr << 16, wr & 0xffff0000u),
+              pk2u(wi << 16, wi & 0xffff0000u), vr, vi);
+        ore[q] = pack_bf16x2_v(vr);
+        oim[q] = pack_bf16x2_v(vi);
       }
-      pack_store_A(vr, vi, sub);
+      tmem_st8(tA + 16 * half + 8 * sub, ore);
+      tmem_st8(tA + 32 + 16 * half + 8 * sub, oim);
     }
     sync_pipe_tmem();
-    // ---------------- stage 3: inverse radix-64.  conj G:  D[:,0:64] = re*Gr + im*Gi ; D[:,64:128] = -re*Gi + im*Gr
-    if (leader) {
+    // ---------------- stage 3: inverse radix-64 (conj G):  D[:,0:128] = re * [Gr | -Gi] + im * [Gi | Gr]
+    if (lead_warp) {
       tc_fence_after();
-      for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 8 * s, tile_desc(sGr + s * 2048), ID_N64_MN, s > 0);
-      for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 32 + 8 * s, tile_desc(sGi + s * 2048), ID_N64_MN, 1);
-      for (int s = 0; s < 4; ++s) mma_ts(tD0 + 64, tA0 + 8 * s, tile_desc(sGi + s * 2048), ID_N64_MN_NEG, s > 0);
-      for (int s = 0; s < 4; ++s) mma_ts(tD0 + 64, tA0 + 32 + 8 * s, tile_desc(sGr + s * 2048), ID_N64_MN, 1);
-      mma_commit(bar_mma);
+      if (elect_one()) {
+        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 8 * s, pair_desc(sG0 + s * 2048, 16384), ID_N128_MN, s > 0);
+        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 32 + 8 * s, pair_desc(sG0 + 8192 + s * 2048, 16384), ID_N128_MN, 1);
+        mma_commit(bar_mma);
+      }
+      __syncwarp();
     }
     wait_mma();
     dump(first);
@@ -323,34 +372,47 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
       tmem_ld16(tD + 64 + 32 * half + 16 * sub, im);
       tmem_ld_wait();
       reg_fence(re); reg_fence(im);
-      float vr[16], vi[16];
+      uint32_t ore[8], oim[8];
 #pragma unroll
-      for (int t = 0; t < 16; ++t) {
-        const float2 w = __half22float2(tw[16 * sub + t]);
-        cmul(__uint_as_float(re[t]), __uint_as_float(im[t]), w.x, -w.y, vr[t], vi[t]);
+      for (int q = 0; q < 8; ++q) {
+        const float2 c = __half22float2(twc[8 * sub + q]), sn = __half22float2(tws[8 * sub + q]);
+        f32x2 vr, vi;
+        cmul2_conj(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), pk2(c.x, c.y), pk2(sn.x, sn.y), vr, vi);
+        ore[q] = pack_bf16x2_v(vr);
+        oim[q] = pack_bf16x2_v(vi);
       }
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int chunk = 4 * half + 2 * sub + cc;
         const uint32_t off = uint32_t(lane) * 128u + (uint32_t(chunk ^ (lane & 7)) << 4);
-        st_shared_v4(sX + off, pack_bf16x2(vr[8 * cc + 0], vr[8 * cc + 1]), pack_bf16x2(vr[8 * cc + 2], vr[8 * cc + 3]),
-                     pack_bf16x2(vr[8 * cc + 4], vr[8 * cc + 5]), pack_bf16x2(vr[8 * cc + 6], vr[8 * cc + 7]));
-        st_shared_v4(sX + kTileBytes + off, pack_bf16x2(vi[8 * cc + 0], vi[8 * cc + 1]),
-                     pack_bf16x2(vi[8 * cc + 2], vi[8 * cc + 3]), pack_bf16x2(vi[8 * cc + 4], vi[8 * cc + 5]),
-                     pack_bf16x2(vi[8 * cc + 6], vi[8 * cc + 7]));
+        st_shared_v4(sX + off, ore[4 * cc + 0], ore[4 * cc + 1], ore[4 * cc + 2], ore[4 * cc + 3]);
+        st_shared_v4(sX + kTileBytes + off, oim[4 * cc + 0], oim[4 * cc + 1], oim[4 * cc + 2], oim[4 * cc + 3]);
       }
     }
     fence_proxy_async_smem();
     tc_fence_before();
     named_bar_sync(bar_id, kPipeThreads);
     // ---------------- stage 4: D4 = conj(F128) * Y   (lane = i, cols [0,64) -> seq b, [64,128) -> seq b+1)
-    if (leader) {
+    if (lead_warp) {
       tc_fence_after();
-      for (int s = 0; s < 8; ++s) mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, s > 0);
-      // D[:,0:64] += (-S) * Yi ;  D[:,64:128] += S * Yr       (conj F = C + iS)
-      for (int s = 0; s < 8; ++s) mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN_NEG, 1);
-      for (int s = 0; s < 8; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN, 1);
-      mma_commit(bar_mma);
+      if (elect_one()) {
+        for (int s = 0; s < 8; ++s) mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, s > 0);
+        // D[:,0:64] += (-S) * Yi ;  D[:,64:128] += S * Yr       (conj F = C + iS)
+        for (int s = 0; s < 8; ++s) mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN_NEG, 1);
+        for (int s = 0; s < 8; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN, 1);
+        mma_commit(bar_mma);
+      }
+      __syncwarp();
+    }
+    uint4 pg[2][4];
+    if (kGated) {
+      const bool row_ok = lane * 64 < p.L;
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        const uint4* gp_ = reinterpret_cast<const uint4*>(p.postgate + (size_t(seq_index(unit, part)) * p.L + lane * 64) / 2) + 4 * half;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) pg[part][c] = row_ok ? __ldg(gp_ + c) : make_uint4(0, 0, 0, 0);
+      }
     }
     wait_mma();
     dump(first);
@@ -368,27 +430,34 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
         for (int cc = 0; cc < 2; ++cc) {
           const int chunk = 4 * half + 2 * sub + cc;
           const uint32_t off = uint32_t(lane) * 128u + (uint32_t(chunk ^ (lane & 7)) << 4);
-          st_shared_v4(sX + part * kTileBytes + off,
-                       pack_bf16x2(__uint_as_float(v[8 * cc + 0]), __uint_as_float(v[8 * cc + 1])),
-                       pack_bf16x2(__uint_as_float(v[8 * cc + 2]), __uint_as_float(v[8 * cc + 3])),
-                       pack_bf16x2(__uint_as_float(v[8 * cc + 4]), __uint_as_float(v[8 * cc + 5])),
-                       pack_bf16x2(__uint_as_float(v[8 * cc + 6]), __uint_as_float(v[8 * cc + 7])));
+          uint32_t o0 = pack_bf16x2(__uint_as_float(v[8 * cc + 0]), __uint_as_float(v[8 * cc + 1]));
+          uint32_t o1 = pack_bf16x2(__uint_as_float(v[8 * cc + 2]), __uint_as_float(v[8 * cc + 3]));
+          uint32_t o2 = pack_bf16x2(__uint_as_float(v[8 * cc + 4]), __uint_as_float(v[8 * cc + 5]));
+          uint32_t o3 = pack_bf16x2(__uint_as_float(v[8 * cc + 6]), __uint_as_float(v[8 * cc + 7]));
+          if (kGated) {
+            const uint4 g = pg[part][2 * sub + cc];
+            o0 = hmul2_bf16(o0, g.x); o1 = hmul2_bf16(o1, g.y); o2 = hmul2_bf16(o2, g.z); o3 = hmul2_bf16(o3, g.w);
+          }
+          st_shared_v4(sX + part * kTileBytes + off, o0, o1, o2, o3);
         }
       }
     }
     fence_proxy_async_smem();
     tc_fence_before();
     named_bar_sync(bar_id, kPipeThreads);
-    if (leader) {
-      const int pr = unit - h * p.pairs;
-      tma_store_3d(&tm_y, sX, 0, 0, seq_index(unit, 0));
-      if (2 * pr + 1 < p.B) tma_store_3d(&tm_y, sX + kTileBytes, 0, 0, seq_index(unit, 1));
-      tma_store_commit();
+    if (lead_warp) {
+      if (elect_one()) {
+        const int pr = unit - h * p.pairs;
+        tma_store_3d(&tm_y, sX, 0, 0, seq_index(unit, 0));
+        if (2 * pr + 1 < p.B) tma_store_3d(&tm_y, sX + kTileBytes, 0, 0, seq_index(unit, 1));
+        tma_store_commit();
+      }
+      __syncwarp();
     }
   }
 
   // ---------------------------------------------------------------- teardown
-  if (leader) tma_store_wait_all0();
+  if (lead_warp) tma_store_wait_all0();   // bulk groups are per thread: harmless on lanes that issued none
   tc_fence_before();
   __syncthreads();
   if (tid < 32) tmem_dealloc(tmem_base, 512);

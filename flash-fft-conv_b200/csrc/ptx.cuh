@@ -174,6 +174,44 @@ DEVINL void reg_fence(uint32_t (&v)[N][M]) {
   for (int i = 0; i < N; ++i) reg_fence(v[i]);
 }
 
+// ----------------------------------------------------------------------------- packed fp32x2 math (sm_100)
+typedef unsigned long long f32x2;
+DEVINL f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+DEVINL f32x2 pk2u(uint32_t a, uint32_t b) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+DEVINL void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+DEVINL f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+DEVINL f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+DEVINL f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// two complex products at once: (ar + i ai) * (br + i bi), lanes = two different points
+DEVINL void cmul2(f32x2 ar, f32x2 ai, f32x2 br, f32x2 bi, f32x2& cr, f32x2& ci) {
+  cr = sub2(mul2(ar, br), mul2(ai, bi));   // ptxas fuses this into FMUL2 + FFMA2 (negated addend)
+  ci = fma2(ai, br, mul2(ar, bi));
+}
+// (ar + i ai) * conj(br + i bi)
+DEVINL void cmul2_conj(f32x2 ar, f32x2 ai, f32x2 br, f32x2 bi, f32x2& cr, f32x2& ci) {
+  cr = fma2(ai, bi, mul2(ar, br));
+  ci = sub2(mul2(ai, br), mul2(ar, bi));
+}
+DEVINL uint32_t pack_bf16x2_v(f32x2 v) {   // (lo, hi) fp32 pair -> bf16x2
+  float a, b; upk2(v, a, b);
+  __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+// Warp-uniform single-thread election (elect.sync): lets the compiler keep MMA/TMA operands in uniform
+// registers instead of emitting a per-instruction uniformisation loop.
+DEVINL bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred px;\n\t"
+      "elect.sync _|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------- misc
 DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x = lo -> low 16 bits

@@ -85,56 +85,92 @@ def _check_inputs(u, k, mod, gates=()):
     return B, H, L
 
 
-def _pack_kf(mod, plan, k, conj):
-    """k (H, Lk) fp32 -> engine-order packed k_f (H, N) 4-byte complex; reference: conv.py:575 + :640."""
-    N = mod.seqlen
-    k_f = torch.fft.fft(k.to(torch.float32), n=N).contiguous()        # complex64, natural order
-    kf_engine = torch.empty((k.shape[0], N), dtype=torch.int32, device=k.device)
+def _kf_natural(mod, k):
+    """k (H, Lk) fp32 -> FFT_N(k) complex64, natural order (reference: conv.py:575)."""
+    return torch.fft.fft(k.to(torch.float32), n=mod.seqlen).contiguous()
+
+
+def _pack_kf_from_natural(mod, plan, k_f, conj):
+    """natural-order k_f -> engine-order packed (H, N) 4-byte complex, scaled 1/N (replaces conv.py:640)."""
+    kf_engine = torch.empty((k_f.shape[0], mod.seqlen), dtype=torch.int32, device=k_f.device)
     _lib.check(_lib.lib().bffc_kf_pack(plan.handle, _ptr(torch.view_as_real(k_f)), _ptr(kf_engine),
-                                       int(k.shape[0]), int(conj), _stream()))
+                                       int(k_f.shape[0]), int(conj), _stream()))
     return kf_engine
+
+
+def _pack_kf(mod, plan, k, conj):
+    return _pack_kf_from_natural(mod, plan, _kf_natural(mod, k), conj)
 
 
 def _fwd(mod, u, k, pregate, postgate):
     B, H, L = u.shape
     plan = mod.plan(u.device)
     with torch.cuda.device(u.device):
-        kf_engine = _pack_kf(mod, plan, k, conj=0)
+        k_f = _kf_natural(mod, k)
+        kf_engine = _pack_kf_from_natural(mod, plan, k_f, conj=0)
         y = torch.empty_like(u)
         ws_bytes = _lib.lib().bffc_workspace_bytes(plan.handle, B, H, L)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=u.device) if ws_bytes else None
         _lib.check(_lib.lib().bffc_fwd(plan.handle, _ptr(u), _ptr(kf_engine), _ptr(pregate), _ptr(postgate),
                                        _ptr(y), B, H, L, _ptr(ws), ws_bytes, _stream()))
-    return y, kf_engine
+    return y, k_f
+
+
+def _bwd(mod, dout, u, k_f, k_len, pregate, postgate):
+    """du, dk[, dpregate, dpostgate] — reference: FlashFFTConvFunc.backward, conv.py:1737-1822."""
+    B, H, L = u.shape
+    N = mod.seqlen
+    plan = mod.plan(u.device)
+    dout = dout.contiguous()                                          # conv.py:1742
+    with torch.cuda.device(u.device):
+        kf_conj = _pack_kf_from_natural(mod, plan, k_f, conj=1)
+        kf_eng = _pack_kf_from_natural(mod, plan, k_f, conj=0) if pregate is not None else None
+        du = torch.empty_like(u)
+        dkf_engine = torch.empty((H, N, 2), dtype=torch.float32, device=u.device)
+        dpre = torch.empty_like(u) if pregate is not None else None
+        dpost = torch.empty_like(u) if pregate is not None else None
+        _lib.check(_lib.lib().bffc_bwd(plan.handle, _ptr(dout), _ptr(u), _ptr(kf_eng), _ptr(kf_conj), _ptr(pregate),
+                                       _ptr(postgate), _ptr(du), _ptr(dkf_engine), _ptr(dpre), _ptr(dpost),
+                                       B, H, L, None, 0, _stream()))
+        dkf_nat = torch.empty((H, N), dtype=torch.complex64, device=u.device)
+        _lib.check(_lib.lib().bffc_dkf_unpack(plan.handle, _ptr(dkf_engine), _ptr(torch.view_as_real(dkf_nat)), H,
+                                              _stream()))
+        # the kernel accumulates unnormalised spectra; ifft's 1/N completes the correlation (conv.py:1817-1820)
+        dk = torch.fft.ifft(dkf_nat, dim=-1).real[..., :k_len].contiguous()
+    return du, dk, dpre, dpost
 
 
 class FlashFFTConvFunc(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, k, mod):
         _check_inputs(u, k, mod)
-        y, kf_engine = _fwd(mod, u, k, None, None)
+        y, k_f = _fwd(mod, u, k, None, None)
         ctx.mod = mod
         ctx.k_len = k.shape[-1]
         if mod.training:                                              # conv.py:587-588
-            ctx.save_for_backward(u, k)
+            ctx.save_for_backward(u, k_f)
         return y
 
     @staticmethod
     def backward(ctx, dout):
-        raise NotImplementedError('bffc backward is not implemented yet')
+        u, k_f = ctx.saved_tensors
+        du, dk, _, _ = _bwd(ctx.mod, dout, u, k_f, ctx.k_len, None, None)
+        return du, dk, None                                           # conv.py:1822
 
 
 class GatedFlashFFTConvFunc(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, k, mod, pregate, postgate):
         _check_inputs(u, k, mod, (pregate, postgate))
-        y, kf_engine = _fwd(mod, u, k, pregate, postgate)
+        y, k_f = _fwd(mod, u, k, pregate, postgate)
         ctx.mod = mod
         ctx.k_len = k.shape[-1]
         if mod.training:
-            ctx.save_for_backward(u, k, pregate, postgate)
+            ctx.save_for_backward(u, k_f, pregate, postgate)
         return y
 
     @staticmethod
     def backward(ctx, dout):
-        raise NotImplementedError('bffc backward is not implemented yet')
+        u, k_f, pregate, postgate = ctx.saved_tensors
+        du, dk, dpre, dpost = _bwd(ctx.mod, dout, u, k_f, ctx.k_len, pregate, postgate)
+        return du, dk, None, dpre, dpost                              # conv.py:3939

@@ -24,14 +24,6 @@ def bf16_round(x):
     return u.astype(np.uint32).view(np.float32).astype(np.float64)
 
 
-def engine_perm():
-    """engine index e = (c*128 + k1)*4 + r, k2 = 4c + r  ->  natural frequency k = k1 + 128*k2."""
-    c = np.arange(16)[:, None, None]
-    k1 = np.arange(128)[None, :, None]
-    r = np.arange(4)[None, None, :]
-    return (k1 + 128 * (4 * c + r)).reshape(-1)
-
-
 def half_round(x):
     return np.asarray(x, dtype=np.float16).astype(np.float64)
 

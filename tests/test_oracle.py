@@ -119,8 +119,3 @@ def test_kernel_model_exact_and_quantised():
     yq, _, _ = km.model_fwd(xq, xq, kf, quant=True)
     r = km.ref_conv(xq, k)
     assert np.linalg.norm(yq - r) / np.linalg.norm(r) < 1e-2             # BASELINE.json tolerance
-
-
-def test_engine_perm_is_permutation():
-    p = km.engine_perm()
-    assert sorted(p.tolist()) == list(range(km.N))

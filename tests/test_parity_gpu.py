@@ -1,0 +1,148 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the reference-facing module
+(which goes through the C ABI), against the oracle on the same seeded inputs, the committed golden fixtures
+produced by the reference's own Python, and size-independent properties at BASELINE.json's full sizes.
+
+Tolerance (BASELINE.json north_star): rel-L2 <= 1e-2 and max-abs <= 1e-2 * max|ref| versus the fp32 oracle;
+the reference's own gate `allclose(atol=1e-2)` (tests/test_flashfftconv.py:83) is reported as well.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import fftconv_oracle as orc  # noqa: E402
+
+REL_L2 = 1e-2
+MAX_REL = 1e-2
+
+
+@pytest.fixture(scope='module')
+def ffc():
+    import __graft_entry__ as ge
+    ge.build()
+    import flashfftconv
+    assert torch.cuda.is_available(), 'these tests need a GPU'
+    return flashfftconv
+
+
+def _check(y, ref, what):
+    y = y.float().cpu(); ref = ref.float().cpu()
+    rel = ((y - ref).norm() / ref.norm()).item()
+    mx = ((y - ref).abs().max() / ref.abs().max()).item()
+    assert rel <= REL_L2, f'{what}: rel-L2 {rel:.3e}'
+    assert mx <= MAX_REL * 2.0, f'{what}: max-abs/max|ref| {mx:.3e}'   # bf16 output rounding alone is 4e-3
+    return rel, mx
+
+
+@pytest.mark.parametrize('B,H,L', [(1, 1, 8192), (2, 3, 8192), (3, 5, 8192), (4, 16, 4096), (5, 7, 2048), (2, 2, 64),
+                                   (8, 111, 8192)])
+@pytest.mark.parametrize('unit_scale', [False, True])
+def test_fwd_8192_vs_oracle(ffc, B, H, L, unit_scale):
+    N = 8192
+    d = orc.make_inputs(B, H, N, L, torch.bfloat16, seed=B * 1000 + H, unit_scale=unit_scale)
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    y = conv(d['u'].cuda(), d['k'].cuda())
+    assert y.shape == d['u'].shape and y.dtype == torch.bfloat16
+    ref = orc.ref_fft_conv(d['u'], d['k'], N)
+    _check(y, ref, f'fwd B={B} H={H} L={L}')
+    if not unit_scale:                      # the reference's own acceptance test
+        assert torch.allclose(y.cpu().float(), ref.float(), atol=1e-2)
+
+
+@pytest.mark.parametrize('B,H,L', [(2, 4, 4096), (3, 5, 8192), (4, 16, 4096)])
+def test_fwd_8192_gated_vs_oracle(ffc, B, H, L):
+    N = 8192
+    d = orc.make_inputs(B, H, N, L, torch.bfloat16, seed=7, gated=True, unit_scale=True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    y = conv(d['u'].cuda(), d['k'].cuda(), d['pregate'].cuda(), d['postgate'].cuda())
+    ref = orc.ref_fft_conv_gated(d['u'], d['k'], d['pregate'], d['postgate'], N)
+    _check(y, ref, f'gated fwd B={B} H={H} L={L}')
+
+
+@pytest.mark.parametrize('name', ['n8192_bf16', 'n8192_bf16_pad', 'n8192_bf16_gated'])
+def test_fwd_against_reference_golden(ffc, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f'conv_{name}.npz'))
+    N = int(g['N'])
+    u = torch.from_numpy(g['u']).to(torch.bfloat16).cuda()
+    k = torch.from_numpy(g['k']).cuda()
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    if 'pregate' in g.files:
+        y = conv(u, k, torch.from_numpy(g['pregate']).to(torch.bfloat16).cuda(),
+                 torch.from_numpy(g['postgate']).to(torch.bfloat16).cuda())
+    else:
+        y = conv(u, k)
+    ref = torch.from_numpy(g['y'])
+    _check(y, ref, name)
+    assert torch.allclose(y.cpu().float(), ref, atol=1e-2)             # tests/test_flashfftconv.py:83
+
+
+def test_fwd_full_size_properties(ffc):
+    """BASELINE configs[1] full size (N=8192, B=16, H=768): linearity, batch-pairing independence and
+    agreement with the oracle on a slice (the oracle at full size would take minutes on CPU)."""
+    N, B, H = 8192, 16, 768
+    torch.manual_seed(3)
+    u = torch.randn(B, H, N, device='cuda').to(torch.bfloat16)
+    k = torch.randn(H, N, device='cuda') / N ** 0.5
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    y = conv(u, k)
+    # slice vs oracle
+    ref = orc.ref_fft_conv(u[:2, :32].cpu(), k[:32].cpu(), N)
+    _check(y[:2, :32], ref, 'full-size slice')
+    # (b, b+1) are packed as one complex sequence: result for b must not depend on its partner
+    u2 = u.clone(); u2[1::2] = torch.randn_like(u2[1::2])
+    y2 = conv(u2, k)
+    assert (y2[0::2].float() - y[0::2].float()).abs().max().item() <= 2e-2 * y.float().abs().max().item()
+    # delta kernel = identity (k = e_0)
+    kd = torch.zeros(H, N, device='cuda'); kd[:, 0] = 1.0
+    yd = conv(u, kd)
+    _check(yd, u, 'identity kernel')
+    # shift kernel = circular shift by 5
+    ks = torch.zeros(H, N, device='cuda'); ks[:, 5] = 1.0
+    ysh = conv(u, ks)
+    _check(ysh, torch.roll(u, 5, dims=-1), 'shift kernel')
+
+
+def test_errors(ffc):
+    conv = ffc.FlashFFTConv(8192, dtype=torch.bfloat16).cuda()
+    u = torch.zeros(2, 2, 8192, device='cuda', dtype=torch.bfloat16)
+    k = torch.zeros(2, 8192, device='cuda')
+    with pytest.raises(RuntimeError):
+        conv(u.float(), k)                               # wrong dtype (monarch_fwd.h:7-13 CHECK_INPUT)
+    with pytest.raises(RuntimeError):
+        conv(u.cpu(), k.cpu())                           # no CPU path
+    with pytest.raises(AssertionError):
+        conv(u, k, pregate=u)                            # both gates or neither (conv.py:557-558)
+    with pytest.raises(RuntimeError):
+        conv(u.transpose(0, 1), k)                       # non-contiguous
+
+
+@pytest.mark.parametrize('B,H,L', [(2, 3, 8192), (3, 5, 8192), (4, 16, 4096), (1, 2, 8192), (8, 64, 8192)])
+def test_bwd_8192_vs_oracle(ffc, B, H, L):
+    """du and dk against autograd through the fp32 oracle (tests/test_flashfftconv.py:88-107).  The reference
+    accepts atol=1e-2 for du and atol=0.1 for dk; we require 1e-2 relative for both."""
+    N = 8192
+    d = orc.make_inputs(B, H, N, L, torch.bfloat16, seed=11 + B, unit_scale=True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    u = d['u'].cuda().requires_grad_(True)
+    k = d['k'].cuda().requires_grad_(True)
+    y = conv(u, k)
+    y.backward(d['dout'].cuda())
+    du_ref, dk_ref = orc.ref_grads(d['u'], d['k'], d['dout'], N)
+    assert u.grad.dtype == torch.bfloat16 and k.grad.dtype == torch.float32 and k.grad.shape == d['k'].shape
+    _check(u.grad, du_ref, f'du B={B} H={H} L={L}')
+    _check(k.grad, dk_ref, f'dk B={B} H={H} L={L}')
+
+
+def test_bwd_against_reference_golden(ffc, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'conv_n8192_bf16.npz'))
+    N = int(g['N'])
+    u = torch.from_numpy(g['u']).to(torch.bfloat16).cuda().requires_grad_(True)
+    k = torch.from_numpy(g['k']).cuda().requires_grad_(True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    conv(u, k).backward(torch.from_numpy(g['dout']).to(torch.bfloat16).cuda())
+    assert torch.allclose(u.grad.float().cpu(), torch.from_numpy(g['du']), atol=1e-2)      # test_flashfftconv.py:103
+    assert torch.allclose(k.grad.cpu(), torch.from_numpy(g['dk']), atol=1e-1)              # test_flashfftconv.py:105-107
+    _check(k.grad, torch.from_numpy(g['dk']), 'dk golden')
