@@ -6,10 +6,12 @@
 //   pybind entry + C++ dispatch + launcher  (csrc/flashfftconv/monarch.cpp:16-56,
 //                                            monarch_cuda/monarch_fwd.h:296-376,
 //                                            monarch_cuda_interface_fwd_bf16.cu:656-760)
+//   the three-kernel orchestration of the long sizes (conv.py:1420-1524: butterfly -> complex Monarch -> ibutterfly)
 // No torch types cross this boundary; there is no CPU fallback.
 #include "bffc.h"
 #include "fwd_r128.cuh"
 #include "dkf_r128.cuh"
+#include "outer_cuda.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -90,16 +92,19 @@ __global__ void kf_pack_kernel(const float* __restrict__ kf_nat, uint32_t* __res
   }
 }
 
+constexpr int kInner = 8192;   // the fused tcgen05 kernel's size
+
 }  // namespace
 
 struct bffc_plan {
   int N;
+  int R;         // N = R * 8192; R > 1: outer radix-R stage on CUDA cores around the fused kernel
   int dtype;
   int device;
   __nv_bfloat16* dftC = nullptr;
   __nv_bfloat16* dftS = nullptr;
   uint8_t* gtiles = nullptr;
-  int* perm = nullptr;  // engine index -> natural frequency index
+  int* perm = nullptr;  // engine word index -> 2 * natural frequency index + part
   int num_sms = 0;
 };
 
@@ -109,7 +114,10 @@ int bffc_abi_version(void) { return BFFC_ABI_VERSION; }
 const char* bffc_last_error(void) { return g_err; }
 int bffc_last_launch_count(void) { return g_launches; }
 
-int bffc_supported(int seqlen, int dtype) { return (seqlen == 8192 && dtype == BFFC_DTYPE_BF16) ? 1 : 0; }
+int bffc_supported(int seqlen, int dtype) {
+  if (dtype != BFFC_DTYPE_BF16) return 0;
+  return (seqlen == 8192 || seqlen == 16384 || seqlen == 32768 || seqlen == 65536) ? 1 : 0;
+}
 
 int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   if (!out) return fail(BFFC_ERR_INVALID, "plan output pointer is null");
@@ -122,12 +130,13 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
 
   bffc_plan* p = new bffc_plan();
   p->N = seqlen;
+  p->R = seqlen / kInner;
   p->dtype = dtype;
   CUDA_TRY(cudaGetDevice(&p->device));
   CUDA_TRY(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
 
   const double PI = 3.14159265358979323846;
-  // outer radix-128 DFT, cos / sin planes (symmetric, K-major rows)
+  // outer radix-128 DFT of the fused kernel, cos / sin planes (symmetric, K-major rows)
   std::vector<uint16_t> c(128 * 128), s(128 * 128);
   for (int m = 0; m < 128; ++m)
     for (int k = 0; k < 128; ++k) {
@@ -142,7 +151,7 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
 
   // DFT-64 planes for the row-local stage: G = exp(-2 pi i k n / 64) = Gr + i Gi.  Stored as the MN-major
   // B operand image: row k (K index) = 64 bf16 = 128 B, 16-byte chunk c of row k at chunk position c ^ (k & 7)
-  // (the 128B swizzle TMA / UMMA use), planes Gr then Gi.
+  // (the 128B swizzle TMA / UMMA use).
   std::vector<uint8_t> gt(4 * bffc::r128::kGTileBytes, 0);   // tiles: Gr, Gi, -Gi, Gr
   for (int k = 0; k < 64; ++k)
     for (int n = 0; n < 64; ++n) {
@@ -158,26 +167,30 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   CUDA_TRY(cudaMalloc(&p->gtiles, gt.size()));
   CUDA_TRY(cudaMemcpy(p->gtiles, gt.data(), gt.size(), cudaMemcpyHostToDevice));
 
-  // engine order (32-bit words): w = (c*128 + k1)*4 + 2*pp + part holds the bf16 pair
-  //   (part ? imag : real) of k_f at k2 = 4c + 2pp and k2 + 1, natural frequency k = k1 + 128*k2.
-  // perm[w] = natural index of the first element * 2 + part; the second element is 128 further.
+  // engine order (32-bit words), per channel h: R rows (c = 0..R-1) of 8192 words; inside a row
+  //   w = (cc*128 + k1)*4 + 2*pp + part  holds the bf16 pair (part ? imag : real) of k_f at inner frequencies
+  //   k' = k1 + 128*k2 with k2 = 4cc + 2pp and k2 + 1; natural frequency k = c + R*k'.
+  // perm[c*8192 + w] = 2 * (natural index of the first element) + part; the second element is 128*R further.
+  const int R = p->R;
   std::vector<int> perm(seqlen);
-  for (int c = 0; c < 16; ++c)
-    for (int k1 = 0; k1 < 128; ++k1)
-      for (int pp = 0; pp < 2; ++pp)
-        for (int part = 0; part < 2; ++part)
-          perm[(c * 128 + k1) * 4 + 2 * pp + part] = (k1 + 128 * (4 * c + 2 * pp)) * 2 + part;
+  for (int cr = 0; cr < R; ++cr)
+    for (int cc = 0; cc < 16; ++cc)
+      for (int k1 = 0; k1 < 128; ++k1)
+        for (int pp = 0; pp < 2; ++pp)
+          for (int part = 0; part < 2; ++part)
+            perm[cr * kInner + (cc * 128 + k1) * 4 + 2 * pp + part] =
+                (cr + R * (k1 + 128 * (4 * cc + 2 * pp))) * 2 + part;
   CUDA_TRY(cudaMalloc(&p->perm, perm.size() * sizeof(int)));
   CUDA_TRY(cudaMemcpy(p->perm, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice));
 
-  CUDA_TRY(cudaFuncSetAttribute(bffc::r128::fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                bffc::r128::kSmemTotal));
-  CUDA_TRY(cudaFuncSetAttribute(bffc::r128::fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                bffc::r128::kSmemTotal));
-  CUDA_TRY(cudaFuncSetAttribute(bffc::r128::fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                bffc::r128::kSmemTotalGated));
-  CUDA_TRY(cudaFuncSetAttribute(bffc::r128::dkf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                bffc::r128::kSmemTotalDkf));
+  using namespace bffc::r128;
+  CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+  CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+  CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kSmemTotalGated));
+  CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+  CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf));
+  CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf));
   *out = p;
   return BFFC_OK;
 }
@@ -194,29 +207,38 @@ int bffc_plan_destroy(bffc_plan* p) {
 
 int bffc_kf_pack(const bffc_plan* p, const void* kf_natural, void* kf_engine, int H, int conj, void* stream) {
   if (!p || !kf_natural || !kf_engine || H <= 0) return fail(BFFC_ERR_INVALID, "bffc_kf_pack: bad argument");
-  dim3 grid((p->N + 255) / 256 > 64 ? 64 : (p->N + 255) / 256, H);
+  dim3 grid(64, H);
   kf_pack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float*>(kf_natural), static_cast<uint32_t*>(kf_engine), p->perm, p->N, 128, 1.0f / float(p->N),
-      conj);
+      static_cast<const float*>(kf_natural), static_cast<uint32_t*>(kf_engine), p->perm, p->N, 128 * p->R,
+      1.0f / float(p->N), conj);
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
 
 int bffc_dkf_unpack(const bffc_plan* p, const void* dkf_engine, void* dkf_natural, int H, void* stream) {
   if (!p || !dkf_engine || !dkf_natural || H <= 0) return fail(BFFC_ERR_INVALID, "bffc_dkf_unpack: bad argument");
-  dim3 grid(32, H);
+  dim3 grid(64, H);
   bffc::r128::dkf_unpack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float2*>(dkf_engine), static_cast<float2*>(dkf_natural), p->N);
+      static_cast<const float2*>(dkf_engine), static_cast<float2*>(dkf_natural), p->N, p->R);
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
 
-size_t bffc_workspace_bytes(const bffc_plan*, int, int, int) { return 0; }
+}  // extern "C"
 
-static int make_map(CUtensorMap* map, const void* base, int BH, int L) {
-  // (B*H, L) bf16 viewed as [seq][row = L/64][col = 64]; box = one (128 x 64) tile, 128B swizzle;
-  // rows >= L/64 are out of bounds: zero-filled on load (implicit padding), dropped on store.
-  cuuint64_t dims[3] = {64, cuuint64_t(L / 64), cuuint64_t(BH)};
+// Composite sizes keep the outer stage's output as two bf16 planes (real, imaginary) of pairs*H*N elements.
+static size_t plane_bytes(const bffc_plan* p, int B, int H) { return size_t((B + 1) / 2) * H * p->N * 2; }
+
+extern "C" size_t bffc_workspace_bytes(const bffc_plan* p, int B, int H, int L) {
+  (void)L;
+  if (!p || p->R == 1) return 0;
+  return 4 * plane_bytes(p, B, H);      // forward uses 2 planes; backward transforms u and dout: 4 planes
+}
+
+static int make_map(CUtensorMap* map, const void* base, int rows, int L) {
+  // (rows, L) bf16 viewed as [row][L/64][64]; box = one (128 x 64) tile, 128B swizzle;
+  // tile rows >= L/64 are out of bounds: zero-filled on load (implicit padding), dropped on store.
+  cuuint64_t dims[3] = {64, cuuint64_t(L / 64), cuuint64_t(rows)};
   cuuint64_t strides[2] = {128, cuuint64_t(L) * 2};
   cuuint32_t box[3] = {64, 128, 1};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -227,29 +249,30 @@ static int make_map(CUtensorMap* map, const void* base, int BH, int L) {
   return 0;
 }
 
-static int launch_fwd(const bffc_plan* p, const void* u, const void* kf, const void* pregate, const void* postgate,
-                      void* y, int B, int H, int L, float* dbg, int dbg_stages, int max_units, void* stream) {
-  if (!p || !u || !kf || !y) return fail(BFFC_ERR_INVALID, "bffc_fwd: null pointer");
-  if (B <= 0 || H <= 0 || L <= 0 || L > p->N) return fail(BFFC_ERR_INVALID, "bffc_fwd: bad shape B=%d H=%d L=%d", B, H, L);
-  if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "bffc_fwd: L=%d must be a multiple of 64 in this build", L);
-  if ((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(kf)) & 15)
-    return fail(BFFC_ERR_INVALID, "bffc_fwd: u, y and kf must be 16-byte aligned");
-  if ((reinterpret_cast<uintptr_t>(pregate) | reinterpret_cast<uintptr_t>(postgate)) & 15)
-    return fail(BFFC_ERR_INVALID, "bffc_fwd: gates must be 16-byte aligned");
+static void fill_params(const bffc_plan* p, bffc::FwdParams& prm, const void* kf) {
+  prm.kf = static_cast<const uint32_t*>(kf);
+  prm.dftC = p->dftC;
+  prm.dftS = p->dftS;
+  prm.gtiles = p->gtiles;
+  prm.pregate = nullptr;
+  prm.postgate = nullptr;
+  prm.dbg = nullptr;
+  prm.dbg_stages = 0;
+}
+
+// fused 8192-point kernel on (B, H, L) real sequences
+static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const void* pregate, const void* postgate,
+                        void* y, int B, int H, int L, float* dbg, int dbg_stages, int max_units, cudaStream_t st) {
+  if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen 8192 in this build", L);
   CUtensorMap tm_u, tm_y, tm_g;
   if (int rc = make_map(&tm_u, u, B * H, L)) return rc;
   if (int rc = make_map(&tm_y, y, B * H, L)) return rc;
   if (int rc = make_map(&tm_g, pregate ? pregate : u, B * H, L)) return rc;
   bffc::FwdParams prm;
-  prm.kf = static_cast<const uint32_t*>(kf);
-  prm.dftC = p->dftC;
-  prm.dftS = p->dftS;
-  prm.gtiles = p->gtiles;
+  fill_params(p, prm, kf);
   prm.pregate = static_cast<const uint32_t*>(pregate);
   prm.postgate = static_cast<const uint32_t*>(postgate);
-  prm.L = L;
-  prm.B = B;
-  prm.H = H;
+  prm.B = B; prm.H = H; prm.L = L;
   prm.pairs = (B + 1) / 2;
   prm.ksteps = (L / 64 + 15) / 16;
   prm.units = H * prm.pairs;
@@ -258,62 +281,182 @@ static int launch_fwd(const bffc_plan* p, const void* u, const void* kf, const v
   prm.dbg_stages = dbg_stages;
   int grid = (prm.units + 1) / 2;
   if (grid > p->num_sms) grid = p->num_sms;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   using namespace bffc::r128;
   if (dbg)
-    fwd_kernel<true, false><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
+    fwd_kernel<true, false, false><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
   else if (pregate)
-    fwd_kernel<false, true><<<grid, kThreads, kSmemTotalGated, st>>>(tm_u, tm_y, tm_g, prm);
+    fwd_kernel<false, true, false><<<grid, kThreads, kSmemTotalGated, st>>>(tm_u, tm_y, tm_g, prm);
   else
-    fwd_kernel<false, false><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
+    fwd_kernel<false, false, false><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
   CUDA_TRY(cudaGetLastError());
-  g_launches = 1;
   return BFFC_OK;
 }
 
+// fused kernel on complex rows held in two planes (in place); rows = pairs * kf_rows
+static int launch_planes(const bffc_plan* p, void* pre, void* pim, const void* kf, int pairs, int kf_rows, cudaStream_t st) {
+  CUtensorMap tm_r, tm_i;
+  if (int rc = make_map(&tm_r, pre, pairs * kf_rows, kInner)) return rc;
+  if (int rc = make_map(&tm_i, pim, pairs * kf_rows, kInner)) return rc;
+  bffc::FwdParams prm;
+  fill_params(p, prm, kf);
+  prm.B = 2 * pairs; prm.H = kf_rows; prm.L = kInner;
+  prm.pairs = pairs;
+  prm.ksteps = 8;
+  prm.units = kf_rows * pairs;
+  int grid = (prm.units + 1) / 2;
+  if (grid > p->num_sms) grid = p->num_sms;
+  using namespace bffc::r128;
+  fwd_kernel<false, false, true><<<grid, kThreads, kSmemTotal, st>>>(tm_r, tm_r, tm_i, prm);
+  CUDA_TRY(cudaGetLastError());
+  return BFFC_OK;
+}
+
+template <int R>
+static void launch_outer(bool inverse, bool gated, const bffc::outer::OuterParams& op, cudaStream_t st) {
+  dim3 grid(bffc::outer::kM / (bffc::outer::kVec * 128), op.H, op.pairs);
+  using namespace bffc::outer;
+  if (!inverse) {
+    if (gated) fwd_kernel<R, true><<<grid, 128, 0, st>>>(op);
+    else fwd_kernel<R, false><<<grid, 128, 0, st>>>(op);
+  } else {
+    if (gated) inv_kernel<R, true><<<grid, 128, 0, st>>>(op);
+    else inv_kernel<R, false><<<grid, 128, 0, st>>>(op);
+  }
+}
+static int outer_stage(const bffc_plan* p, bool inverse, bool gated, const bffc::outer::OuterParams& op, cudaStream_t st) {
+  switch (p->R) {
+    case 2: launch_outer<2>(inverse, gated, op, st); break;
+    case 4: launch_outer<4>(inverse, gated, op, st); break;
+    case 8: launch_outer<8>(inverse, gated, op, st); break;
+    default: return fail(BFFC_ERR_UNSUPPORTED, "outer radix %d not supported", p->R);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return BFFC_OK;
+}
+
+static int check_common(const bffc_plan* p, int B, int H, int L, const void* a, const void* b, const void* c) {
+  if (!p) return fail(BFFC_ERR_INVALID, "null plan");
+  if (B <= 0 || H <= 0 || L <= 0 || L > p->N) return fail(BFFC_ERR_INVALID, "bad shape B=%d H=%d L=%d (seqlen %d)", B, H, L, p->N);
+  if (L % 8 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 8 in this build", L);
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15)
+    return fail(BFFC_ERR_INVALID, "device pointers must be 16-byte aligned");
+  return 0;
+}
+
+// y = postgate * conv(u * pregate, k) for any supported size.  `planes`: workspace for composite sizes.
+static int conv_forward(const bffc_plan* p, const void* u, const void* kf, const void* pregate, const void* postgate,
+                        void* y, int B, int H, int L, void* planes, cudaStream_t st, int* launches) {
+  if (p->R == 1) {
+    *launches += 1;
+    return launch_fused(p, u, kf, pregate, postgate, y, B, H, L, nullptr, 0, 0, st);
+  }
+  const int pairs = (B + 1) / 2;
+  uint8_t* ws = static_cast<uint8_t*>(planes);
+  bffc::outer::OuterParams op;
+  op.u = static_cast<const uint4*>(u);
+  op.pregate = static_cast<const uint4*>(pregate);
+  op.postgate = static_cast<const uint4*>(postgate);
+  op.y = static_cast<uint4*>(y);
+  op.pre = reinterpret_cast<uint4*>(ws);
+  op.pim = reinterpret_cast<uint4*>(ws + plane_bytes(p, B, H));
+  op.B = B; op.H = H; op.L = L; op.pairs = pairs;
+  if (int rc = outer_stage(p, false, pregate != nullptr, op, st)) return rc;
+  if (int rc = launch_planes(p, op.pre, op.pim, kf, pairs, H * p->R, st)) return rc;
+  if (int rc = outer_stage(p, true, postgate != nullptr, op, st)) return rc;
+  *launches += 3;
+  return BFFC_OK;
+}
+
+extern "C" {
+
 int bffc_fwd(const bffc_plan* p, const void* u, const void* kf, const void* pregate, const void* postgate, void* y,
-             int B, int H, int L, void*, size_t, void* stream) {
+             int B, int H, int L, void* workspace, size_t workspace_bytes, void* stream) {
   if ((pregate == nullptr) != (postgate == nullptr))
     return fail(BFFC_ERR_INVALID, "bffc_fwd: pregate and postgate must both be given or both be null");
-  return launch_fwd(p, u, kf, pregate, postgate, y, B, H, L, nullptr, 0, 0, stream);
+  if (!u || !kf || !y) return fail(BFFC_ERR_INVALID, "bffc_fwd: null pointer");
+  if (int rc = check_common(p, B, H, L, u, y, kf)) return rc;
+  if ((reinterpret_cast<uintptr_t>(pregate) | reinterpret_cast<uintptr_t>(postgate) | reinterpret_cast<uintptr_t>(workspace)) & 15)
+    return fail(BFFC_ERR_INVALID, "bffc_fwd: gates / workspace must be 16-byte aligned");
+  if (p->R > 1 && (!workspace || workspace_bytes < 2 * plane_bytes(p, B, H)))
+    return fail(BFFC_ERR_INVALID, "bffc_fwd: workspace of %zu bytes required", 2 * plane_bytes(p, B, H));
+  int launches = 0;
+  int rc = conv_forward(p, u, kf, pregate, postgate, y, B, H, L, workspace, static_cast<cudaStream_t>(stream), &launches);
+  g_launches = launches;
+  return rc;
 }
 
 int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf, const void* kf_conj,
              const void* pregate, const void* postgate, void* du, void* dkf, void* dpregate, void* dpostgate, int B, int H,
-             int L, void*, size_t, void* stream) {
+             int L, void* workspace, size_t workspace_bytes, void* stream) {
   if ((pregate == nullptr) != (postgate == nullptr))
     return fail(BFFC_ERR_INVALID, "bffc_bwd: pregate and postgate must both be given or both be null");
   if (pregate) return fail(BFFC_ERR_UNSUPPORTED, "bffc_bwd: gated backward not implemented yet");
   (void)kf; (void)dpregate; (void)dpostgate;
-  if (!p || !dout || !u || !kf_conj || !du || !dkf) return fail(BFFC_ERR_INVALID, "bffc_bwd: null pointer");
-  // du = corr(dout, k) = circular conv with conj(k_f): the forward kernel on dout (kernels_bf16/..._bwd_kernel_bf16.h:740-815)
-  if (int rc = launch_fwd(p, dout, kf_conj, nullptr, nullptr, du, B, H, L, nullptr, 0, 0, stream)) return rc;
+  if (!dout || !u || !kf_conj || !du || !dkf) return fail(BFFC_ERR_INVALID, "bffc_bwd: null pointer");
+  if (int rc = check_common(p, B, H, L, u, du, dout)) return rc;
+  if ((reinterpret_cast<uintptr_t>(dkf) | reinterpret_cast<uintptr_t>(kf_conj) | reinterpret_cast<uintptr_t>(workspace)) & 15)
+    return fail(BFFC_ERR_INVALID, "bffc_bwd: dkf / kf / workspace must be 16-byte aligned");
+  if (p->R > 1 && (!workspace || workspace_bytes < 4 * plane_bytes(p, B, H)))
+    return fail(BFFC_ERR_INVALID, "bffc_bwd: workspace of %zu bytes required", 4 * plane_bytes(p, B, H));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int launches = 0;
+  // du = corr(dout, k) = circular conv with conj(k_f): the forward path on dout
+  // (reference: kernels_bf16/monarch_cuda_32_16_16_bwd_kernel_bf16.h:740-815)
+  if (int rc = conv_forward(p, dout, kf_conj, nullptr, nullptr, du, B, H, L, workspace, st, &launches)) return rc;
   // dk_f = sum_b FFT(dout) * conj(FFT(u))
-  if ((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(dkf)) & 15)
-    return fail(BFFC_ERR_INVALID, "bffc_bwd: u and dkf must be 16-byte aligned");
-  CUtensorMap tm_u, tm_d;
-  if (int rc = make_map(&tm_u, u, B * H, L)) return rc;
-  if (int rc = make_map(&tm_d, dout, B * H, L)) return rc;
+  const int pairs = (B + 1) / 2;
   bffc::DkfParams prm;
   prm.dftC = p->dftC;
   prm.dftS = p->dftS;
   prm.gtiles = p->gtiles;
   prm.dkf = static_cast<float2*>(dkf);
-  prm.B = B; prm.H = H; prm.L = L;
-  prm.pairs = (B + 1) / 2;
-  prm.ksteps = (L / 64 + 15) / 16;
-  int grid = H < p->num_sms ? H : p->num_sms;
-  bffc::r128::dkf_kernel<<<grid, bffc::r128::kThreads, bffc::r128::kSmemTotalDkf, static_cast<cudaStream_t>(stream)>>>(
-      tm_u, tm_d, prm);
-  CUDA_TRY(cudaGetLastError());
-  g_launches = 2;
+  prm.pairs = pairs;
+  using namespace bffc::r128;
+  if (p->R == 1) {
+    if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen 8192 in this build", L);
+    CUtensorMap tm_u, tm_d;
+    if (int rc = make_map(&tm_u, u, B * H, L)) return rc;
+    if (int rc = make_map(&tm_d, dout, B * H, L)) return rc;
+    prm.B = B; prm.H = H; prm.L = L;
+    prm.ksteps = (L / 64 + 15) / 16;
+    int grid = H < p->num_sms ? H : p->num_sms;
+    dkf_kernel<false><<<grid, kThreads, kSmemTotalDkf, st>>>(tm_u, tm_d, tm_u, tm_d, prm);
+    CUDA_TRY(cudaGetLastError());
+    launches += 1;
+  } else {
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    const size_t pb = plane_bytes(p, B, H);
+    bffc::outer::OuterParams ou, od;
+    ou.u = static_cast<const uint4*>(u); ou.pregate = nullptr; ou.postgate = nullptr; ou.y = nullptr;
+    ou.pre = reinterpret_cast<uint4*>(ws); ou.pim = reinterpret_cast<uint4*>(ws + pb);
+    ou.B = B; ou.H = H; ou.L = L; ou.pairs = pairs;
+    od = ou;
+    od.u = static_cast<const uint4*>(dout);
+    od.pre = reinterpret_cast<uint4*>(ws + 2 * pb); od.pim = reinterpret_cast<uint4*>(ws + 3 * pb);
+    if (int rc = outer_stage(p, false, false, ou, st)) return rc;
+    if (int rc = outer_stage(p, false, false, od, st)) return rc;
+    const int rows = H * p->R;
+    CUtensorMap tur, tui, tdr, tdi;
+    if (int rc = make_map(&tur, ou.pre, pairs * rows, kInner)) return rc;
+    if (int rc = make_map(&tui, ou.pim, pairs * rows, kInner)) return rc;
+    if (int rc = make_map(&tdr, od.pre, pairs * rows, kInner)) return rc;
+    if (int rc = make_map(&tdi, od.pim, pairs * rows, kInner)) return rc;
+    prm.B = 2 * pairs; prm.H = rows; prm.L = kInner;
+    prm.ksteps = 8;
+    int grid = rows < p->num_sms ? rows : p->num_sms;
+    dkf_kernel<true><<<grid, kThreads, kSmemTotalDkf, st>>>(tur, tdr, tui, tdi, prm);
+    CUDA_TRY(cudaGetLastError());
+    launches += 3;
+  }
+  g_launches = launches;
   return BFFC_OK;
 }
 
 int bffc_debug_fwd_stages(const bffc_plan* p, const void* u, const void* kf, void* y, int B, int H, int L, float* dump,
                           int max_stages, void* stream) {
-  if (!dump || max_stages <= 0) return -BFFC_ERR_INVALID;
-  int rc = launch_fwd(p, u, kf, nullptr, nullptr, y, B, H, L, dump, max_stages, 1, stream);
+  if (!dump || max_stages <= 0 || !p || p->R != 1) return -BFFC_ERR_INVALID;
+  if (check_common(p, B, H, L, u, y, kf)) return -BFFC_ERR_INVALID;
+  int rc = launch_fused(p, u, kf, nullptr, nullptr, y, B, H, L, dump, max_stages, 1, static_cast<cudaStream_t>(stream));
   if (rc) return -rc;
   return max_stages < 4 ? max_stages : 4;
 }

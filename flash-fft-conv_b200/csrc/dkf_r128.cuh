@@ -33,8 +33,12 @@ namespace r128 {
 
 constexpr int kSmemTotalDkf = kSmemData + kSmemG + kSmemBars + 1024;
 
+// kPlanes: inputs are complex rows in bf16 planes (composite sizes): (tm_u, tm_ui) = real / imaginary plane of the
+// transformed u rows, (tm_d, tm_di) likewise for dout; p.H = number of k_f rows, row = pr * p.H + channel.
+template <bool kPlanes>
 __global__ void __launch_bounds__(kThreads, 1)
-dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_d, const DkfParams p) {
+dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_d,
+           const __grid_constant__ CUtensorMap tm_ui, const __grid_constant__ CUtensorMap tm_di, const DkfParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_g = sbase + kSmemData;
@@ -55,6 +59,7 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   if (tid == 0) {
     tma_prefetch_desc(&tm_u);
     tma_prefetch_desc(&tm_d);
+    if (kPlanes) { tma_prefetch_desc(&tm_ui); tma_prefetch_desc(&tm_di); }
   }
   if ((tid & 255) == 0) {
     mbar_init(bar_tma0, 1);
@@ -116,6 +121,7 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   const uint32_t bar_id = 1 + pipe;
   const uint32_t sG0 = s_g;
   const CUtensorMap* tm = (pipe == 0) ? &tm_u : &tm_d;
+  const CUtensorMap* tmi = kPlanes ? ((pipe == 0) ? &tm_ui : &tm_di) : tm;
   const int BH = p.B * p.H;
 
   // units of this CTA: (h, pr) for h = blockIdx.x, blockIdx.x + gridDim.x, ...
@@ -128,8 +134,13 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
     const uint32_t bar = bar_tma0 + 8 * slot;
     const uint32_t dst = s_slot0 + slot * kSlotBytes;
     mbar_expect_tx(bar, kSlotBytes);
-    tma_load_3d(dst, tm, bar, 0, 0, b0 * p.H + h);
-    tma_load_3d(dst + kTileBytes, tm, bar, 0, 0, b1 < p.B ? b1 * p.H + h : BH);   // out of bounds -> zeros
+    if (kPlanes) {
+      tma_load_3d(dst, tm, bar, 0, 0, pr * p.H + h);
+      tma_load_3d(dst + kTileBytes, tmi, bar, 0, 0, pr * p.H + h);
+    } else {
+      tma_load_3d(dst, tm, bar, 0, 0, b0 * p.H + h);
+      tma_load_3d(dst + kTileBytes, tm, bar, 0, 0, b1 < p.B ? b1 * p.H + h : BH);   // out of bounds -> zeros
+    }
   };
   uint32_t mma_phase = 0;
   auto wait_mma = [&]() {
@@ -246,12 +257,14 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   if (tid < 32) tmem_dealloc(tmem_base, 512);
 }
 
-// dk_f engine order -> natural order complex64 (reference analogue: the inverse permutation at conv.py:1818)
-__global__ void dkf_unpack_kernel(const float2* __restrict__ eng, float2* __restrict__ nat, int N) {
+// dk_f engine order -> natural order complex64 (reference analogue: the inverse permutation at conv.py:1818).
+// Composite sizes: channel row = h*R + c holds frequencies k = c + R*(k1 + 128*k2).
+__global__ void dkf_unpack_kernel(const float2* __restrict__ eng, float2* __restrict__ nat, int N, int R) {
   const int h = blockIdx.y;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
-    const int k1 = k & 127, k2 = k >> 7;
-    nat[size_t(h) * N + k] = eng[((size_t(h) * 4 + (k2 >> 4)) * 128 + k1) * 16 + (k2 & 15)];
+    const int c = k % R, kk = k / R;
+    const int k1 = kk & 127, k2 = kk >> 7;
+    nat[size_t(h) * N + k] = eng[(((size_t(h) * R + c) * 4 + (k2 >> 4)) * 128 + k1) * 16 + (k2 & 15)];
   }
 }
 

@@ -87,7 +87,10 @@ DEVINL uint4 ld_shared_v4(uint32_t addr) {
 // pregate tiles arrive by TMA next to the input tiles and are multiplied in shared memory (bf16 product, as
 // the reference's __hmul2 on load, monarch_cuda_32_16_16_kernel_bf16.h:550-585); the postgate is read with
 // coalesced 16-byte loads in the output pass and applied to the bf16-rounded result.
-template <bool kDebug, bool kGated>
+// kPlanes: complex rows mode for composite sizes (N = R x 8192, see outer_cuda.cuh / outer_r128.cuh): the unit is one
+// complex length-8192 row whose real / imaginary parts live in two bf16 planes (tm_u = tm_y = real plane,
+// tm_g = imaginary plane), k_f row = unit / pairs (p.H = number of k_f rows), result written back in place.
+template <bool kDebug, bool kGated, bool kPlanes = false>
 __global__ void __launch_bounds__(kThreads, 1)
 fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_y,
            const __grid_constant__ CUtensorMap tm_g, const FwdParams p) {
@@ -113,7 +116,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   if (tid == 0) {
     tma_prefetch_desc(&tm_u);
     tma_prefetch_desc(&tm_y);
-    if (kGated) tma_prefetch_desc(&tm_g);
+    if (kGated || kPlanes) tma_prefetch_desc(&tm_g);
   }
   if ((tid & 255) == 0) {
     mbar_init(bar_tma0, 1);
@@ -189,6 +192,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
 
   auto seq_index = [&](int unit, int which) {   // global sequence index (b*H + h) of the re / im member
     const int h = unit / p.pairs, pr = unit - h * p.pairs;
+    if (kPlanes) return pr * p.H + h;           // row of both planes
     int b = 2 * pr + which;
     if (b >= p.B) b = p.B - 1;                  // odd batch: duplicate, result discarded
     return b * p.H + h;
@@ -198,7 +202,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
     const uint32_t dst = s_slot0 + slot * kSlotBytes;
     mbar_expect_tx(bar, kGated ? 2 * kSlotBytes : kSlotBytes);
     tma_load_3d(dst, &tm_u, bar, 0, 0, seq_index(unit, 0));
-    tma_load_3d(dst + kTileBytes, &tm_u, bar, 0, 0, seq_index(unit, 1));
+    tma_load_3d(dst + kTileBytes, kPlanes ? &tm_g : &tm_u, bar, 0, 0, seq_index(unit, 1));
     if (kGated) {   // single pregate slot per pipeline: free again once pass 0 of the current unit is done
       const uint32_t gd = s_gate0 + pipe * kSlotBytes;
       tma_load_3d(gd, &tm_g, bar, 0, 0, seq_index(unit, 0));
@@ -449,7 +453,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
       if (elect_one()) {
         const int pr = unit - h * p.pairs;
         tma_store_3d(&tm_y, sX, 0, 0, seq_index(unit, 0));
-        if (2 * pr + 1 < p.B) tma_store_3d(&tm_y, sX + kTileBytes, 0, 0, seq_index(unit, 1));
+        if (kPlanes) tma_store_3d(&tm_g, sX + kTileBytes, 0, 0, seq_index(unit, 1));
+        else if (2 * pr + 1 < p.B) tma_store_3d(&tm_y, sX + kTileBytes, 0, 0, seq_index(unit, 1));
         tma_store_commit();
       }
       __syncwarp();

@@ -129,9 +129,11 @@ def _bwd(mod, dout, u, k_f, k_len, pregate, postgate):
         dkf_engine = torch.empty((H, N, 2), dtype=torch.float32, device=u.device)
         dpre = torch.empty_like(u) if pregate is not None else None
         dpost = torch.empty_like(u) if pregate is not None else None
+        ws_bytes = _lib.lib().bffc_workspace_bytes(plan.handle, B, H, L)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=u.device) if ws_bytes else None
         _lib.check(_lib.lib().bffc_bwd(plan.handle, _ptr(dout), _ptr(u), _ptr(kf_eng), _ptr(kf_conj), _ptr(pregate),
                                        _ptr(postgate), _ptr(du), _ptr(dkf_engine), _ptr(dpre), _ptr(dpost),
-                                       B, H, L, None, 0, _stream()))
+                                       B, H, L, _ptr(ws), ws_bytes, _stream()))
         dkf_nat = torch.empty((H, N), dtype=torch.complex64, device=u.device)
         _lib.check(_lib.lib().bffc_dkf_unpack(plan.handle, _ptr(dkf_engine), _ptr(torch.view_as_real(dkf_nat)), H,
                                               _stream()))

@@ -146,3 +146,45 @@ def test_bwd_against_reference_golden(ffc, golden_dir):
     assert torch.allclose(u.grad.float().cpu(), torch.from_numpy(g['du']), atol=1e-2)      # test_flashfftconv.py:103
     assert torch.allclose(k.grad.cpu(), torch.from_numpy(g['dk']), atol=1e-1)              # test_flashfftconv.py:105-107
     _check(k.grad, torch.from_numpy(g['dk']), 'dk golden')
+
+
+# ----------------------------------------------------------------------------- composite sizes N = R x 8192
+@pytest.mark.parametrize('N,B,H,L', [(16384, 2, 3, 16384), (16384, 3, 4, 8192), (32768, 2, 4, 32768), (32768, 3, 2, 16384),
+                                     (32768, 2, 2, 8200), (65536, 2, 2, 65536), (65536, 1, 3, 32768)])
+def test_fwd_composite_vs_oracle(ffc, N, B, H, L):
+    d = orc.make_inputs(B, H, N, L, torch.bfloat16, seed=N // 1000 + B, unit_scale=True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    y = conv(d['u'].cuda(), d['k'].cuda())
+    _check(y, orc.ref_fft_conv(d['u'], d['k'], N), f'fwd N={N} B={B} H={H} L={L}')
+
+
+@pytest.mark.parametrize('N,B,H,L', [(32768, 2, 4, 16384), (16384, 3, 2, 16384)])
+def test_fwd_composite_gated_vs_oracle(ffc, N, B, H, L):
+    d = orc.make_inputs(B, H, N, L, torch.bfloat16, seed=5, gated=True, unit_scale=True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    y = conv(d['u'].cuda(), d['k'].cuda(), d['pregate'].cuda(), d['postgate'].cuda())
+    _check(y, orc.ref_fft_conv_gated(d['u'], d['k'], d['pregate'], d['postgate'], N), f'gated fwd N={N}')
+
+
+def test_fwd_32768_gated_padded_golden(ffc, golden_dir):
+    """BASELINE configs[2] shape (N=32768, gated, L=N/2) against the reference's own Python output."""
+    g = np.load(os.path.join(golden_dir, 'conv_n32768_bf16_gated_pad.npz'))
+    N = int(g['N'])
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    t = lambda a: torch.from_numpy(a).to(torch.bfloat16).cuda()
+    y = conv(t(g['u']), torch.from_numpy(g['k']).cuda(), t(g['pregate']), t(g['postgate']))
+    ref = torch.from_numpy(g['y'])
+    assert torch.allclose(y.cpu().float(), ref, atol=1e-2)
+    _check(y, ref, 'golden 32768 gated padded')
+
+
+@pytest.mark.parametrize('N,B,H,L', [(16384, 2, 3, 16384), (32768, 3, 2, 16384), (65536, 2, 2, 65536)])
+def test_bwd_composite_vs_oracle(ffc, N, B, H, L):
+    d = orc.make_inputs(B, H, N, L, torch.bfloat16, seed=21 + B, unit_scale=True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    u = d['u'].cuda().requires_grad_(True)
+    k = d['k'].cuda().requires_grad_(True)
+    conv(u, k).backward(d['dout'].cuda())
+    du_ref, dk_ref = orc.ref_grads(d['u'], d['k'], d['dout'], N)
+    _check(u.grad, du_ref, f'du N={N}')
+    _check(k.grad, dk_ref, f'dk N={N}')
