@@ -36,7 +36,9 @@ def algorithmic_bytes(N, B, H, L, gated):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md 'clocks line')."""
+    """nvidia-smi clocks + throttle reasons while the GPU is under the benchmark load
+    (B200_PROFILING.md 'clocks line'): one persistent `nvidia-smi -lms 100`, samples are time-stamped and only
+    those taken inside a marked load window are summarised."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
@@ -44,31 +46,40 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
-        self.stop_flag = False
+        self.samples = []          # (t, fields)
+        self.windows = []          # (t0, t1) under load
+        self.proc = None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                      '-i', str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(',')]
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.strip().split(',')]
                 if len(f) >= 7:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            time.sleep(0.05)
+                    self.samples.append((time.time(), f))
+        except Exception:
+            pass
+
+    def stop(self):
+        try:
+            if self.proc:
+                self.proc.terminate()
+        except Exception:
+            pass
 
     def summary(self):
-        if not self.samples:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        sm = sorted(float(s[0]) for s in self.samples)
+        inside = [f for (t, f) in self.samples if any(a <= t <= b for a, b in self.windows)]
+        if not inside:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no nvidia-smi sample under load']}
+        sm = sorted(float(s[0]) for s in inside)
         reasons = []
         for i, name in [(3, 'hw_slowdown'), (4, 'hw_thermal_slowdown'), (5, 'sw_thermal_slowdown'), (6, 'sw_power_cap')]:
-            if any(s[i].lower().startswith('active') for s in self.samples):
+            if any(s[i].lower().startswith('active') for s in inside):
                 reasons.append(name)
-        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons,
-                'samples': len(self.samples)}
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(inside[0][1]), 'reasons': reasons,
+                'samples_under_load': len(inside),
+                'power_w_max': max(float(s[2]) for s in inside if s[2].replace('.', '', 1).isdigit())}
 
 
 def cpu_baseline(N, L, gated, budget_s=12.0):
@@ -87,7 +98,8 @@ def cpu_baseline(N, L, gated, budget_s=12.0):
         fn = lambda: ref_fft_conv_gated(u, k, pg, qg, N)
     else:
         fn = lambda: ref_fft_conv(u, k, N)
-    fn()
+    for _ in range(5):          # thread pool / FFT plan warm-up (first calls are 10x slower)
+        fn()
     t0 = time.perf_counter(); n = 0
     while True:
         fn(); n += 1
@@ -176,6 +188,8 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+        time.sleep(0.3)
+    t_load0 = time.time()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     launches = 0
     e0.record()
@@ -202,8 +216,33 @@ def run_ours(args):
     k1.record(); torch.cuda.synchronize()
     kern_ms = k0.elapsed_time(k1) / args.steps
     if sampler:
-        sampler.stop_flag = True
-        sampler.join(timeout=2)
+        # the timed regions last milliseconds; keep the identical kernel running ~1.5 s more so that
+        # nvidia-smi (100 ms period) sees clocks and throttle reasons under this load
+        t_end = time.time() + 1.5
+        while time.time() < t_end:
+            for _ in range(50):
+                kern()
+            torch.cuda.synchronize()
+        sampler.windows.append((t_load0, time.time()))
+        time.sleep(0.15)
+        sampler.stop()
+
+    # ---- (2b) forward + backward through autograd (du, dk), device resident
+    ug = u.clone().requires_grad_(True); kg = k.clone().requires_grad_(True)
+    dout = torch.randn_like(u)
+    def fb():
+        ug.grad = None; kg.grad = None
+        conv(ug, kg).backward(dout)
+    for _ in range(3):
+        fb()
+    barrier()
+    f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        fb()
+    f1.record()
+    barrier()
+    fb_ms = max_over_ranks(f0.elapsed_time(f1) / args.steps)
 
     # ---- (3) end to end through the public API with HOST buffers (pinned), copies inside the timed region
     u_h = u.cpu().pin_memory(); k_h = k.cpu().pin_memory()
@@ -256,6 +295,8 @@ def run_ours(args):
         'e2e': {'value': convs_per_step * world / (e2e_ms * 1e-3), 'unit': 'convs/s',
                 'h2d_bytes_per_step': u_h.numel() * 2 + k_h.numel() * 4, 'd2h_bytes_per_step': y_h.numel() * 2,
                 'ms_per_step': e2e_ms},
+        'fwd_bwd': {'value': convs_per_step * world / (fb_ms * 1e-3), 'unit': 'convs/s', 'ms_per_step': fb_ms,
+                    'note': 'autograd fwd+bwd (du, dk) through FlashFFTConv, inputs resident'},
         'gpu_launches': launches,
         'clocks': sampler.summary() if sampler else None,
     }
