@@ -191,6 +191,7 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf));
   CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf));
+  CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkfGated));
   *out = p;
   return BFFC_OK;
 }
@@ -284,7 +285,7 @@ static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const
   using namespace bffc::r128;
   if (dbg)
     fwd_kernel<true, false, false><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
-  else if (pregate)
+  else if (pregate || postgate)
     fwd_kernel<false, true, false><<<grid, kThreads, kSmemTotalGated, st>>>(tm_u, tm_y, tm_g, prm);
   else
     fwd_kernel<false, false, false><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
@@ -390,9 +391,12 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
              int L, void* workspace, size_t workspace_bytes, void* stream) {
   if ((pregate == nullptr) != (postgate == nullptr))
     return fail(BFFC_ERR_INVALID, "bffc_bwd: pregate and postgate must both be given or both be null");
-  if (pregate) return fail(BFFC_ERR_UNSUPPORTED, "bffc_bwd: gated backward not implemented yet");
-  (void)kf; (void)dpregate; (void)dpostgate;
+  const bool gated = pregate != nullptr;
   if (!dout || !u || !kf_conj || !du || !dkf) return fail(BFFC_ERR_INVALID, "bffc_bwd: null pointer");
+  if (gated && (!kf || !dpregate || !dpostgate)) return fail(BFFC_ERR_INVALID, "bffc_bwd: gated backward needs kf, dpregate, dpostgate");
+  if ((reinterpret_cast<uintptr_t>(pregate) | reinterpret_cast<uintptr_t>(postgate) | reinterpret_cast<uintptr_t>(dpregate) |
+       reinterpret_cast<uintptr_t>(dpostgate) | reinterpret_cast<uintptr_t>(kf)) & 15)
+    return fail(BFFC_ERR_INVALID, "bffc_bwd: gate pointers must be 16-byte aligned");
   if (int rc = check_common(p, B, H, L, u, du, dout)) return rc;
   if ((reinterpret_cast<uintptr_t>(dkf) | reinterpret_cast<uintptr_t>(kf_conj) | reinterpret_cast<uintptr_t>(workspace)) & 15)
     return fail(BFFC_ERR_INVALID, "bffc_bwd: dkf / kf / workspace must be 16-byte aligned");
@@ -402,8 +406,17 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
   int launches = 0;
   // du = corr(dout, k) = circular conv with conj(k_f): the forward path on dout
   // (reference: kernels_bf16/monarch_cuda_32_16_16_bwd_kernel_bf16.h:740-815)
-  if (int rc = conv_forward(p, dout, kf_conj, nullptr, nullptr, du, B, H, L, workspace, st, &launches)) return rc;
-  // dk_f = sum_b FFT(dout) * conj(FFT(u))
+  if (!gated) {
+    if (int rc = conv_forward(p, dout, kf_conj, nullptr, nullptr, du, B, H, L, workspace, st, &launches)) return rc;
+  } else {
+    // y = q * conv(u*p, k)  (conv.py:3856-3939; kernels_bf16/..._bwd_kernel_bf16.h:836-906; host recompute
+    // monarch_cuda_interface_bwd_bf16.cu:798-808).  With dx = corr(dout*q, k):
+    //   dpostgate = dout * conv(u*p, k),  du = p * dx,  dpregate = u * dx     — three passes of the forward path
+    if (int rc = conv_forward(p, u, kf, pregate, dout, dpostgate, B, H, L, workspace, st, &launches)) return rc;
+    if (int rc = conv_forward(p, dout, kf_conj, postgate, pregate, du, B, H, L, workspace, st, &launches)) return rc;
+    if (int rc = conv_forward(p, dout, kf_conj, postgate, u, dpregate, B, H, L, workspace, st, &launches)) return rc;
+  }
+  // dk_f = sum_b FFT(dout*q) * conj(FFT(u*p))
   const int pairs = (B + 1) / 2;
   bffc::DkfParams prm;
   prm.dftC = p->dftC;
@@ -414,27 +427,31 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
   using namespace bffc::r128;
   if (p->R == 1) {
     if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen 8192 in this build", L);
-    CUtensorMap tm_u, tm_d;
+    CUtensorMap tm_u, tm_d, tm_p, tm_q;
     if (int rc = make_map(&tm_u, u, B * H, L)) return rc;
     if (int rc = make_map(&tm_d, dout, B * H, L)) return rc;
+    if (int rc = make_map(&tm_p, gated ? pregate : u, B * H, L)) return rc;
+    if (int rc = make_map(&tm_q, gated ? postgate : dout, B * H, L)) return rc;
     prm.B = B; prm.H = H; prm.L = L;
     prm.ksteps = (L / 64 + 15) / 16;
+    prm.gated = gated ? 1 : 0;
     int grid = H < p->num_sms ? H : p->num_sms;
-    dkf_kernel<false><<<grid, kThreads, kSmemTotalDkf, st>>>(tm_u, tm_d, tm_u, tm_d, prm);
+    dkf_kernel<false><<<grid, kThreads, gated ? kSmemTotalDkfGated : kSmemTotalDkf, st>>>(tm_u, tm_d, tm_p, tm_q, prm);
     CUDA_TRY(cudaGetLastError());
     launches += 1;
   } else {
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     const size_t pb = plane_bytes(p, B, H);
     bffc::outer::OuterParams ou, od;
-    ou.u = static_cast<const uint4*>(u); ou.pregate = nullptr; ou.postgate = nullptr; ou.y = nullptr;
+    ou.u = static_cast<const uint4*>(u); ou.pregate = static_cast<const uint4*>(pregate); ou.postgate = nullptr; ou.y = nullptr;
     ou.pre = reinterpret_cast<uint4*>(ws); ou.pim = reinterpret_cast<uint4*>(ws + pb);
     ou.B = B; ou.H = H; ou.L = L; ou.pairs = pairs;
     od = ou;
     od.u = static_cast<const uint4*>(dout);
+    od.pregate = static_cast<const uint4*>(postgate);
     od.pre = reinterpret_cast<uint4*>(ws + 2 * pb); od.pim = reinterpret_cast<uint4*>(ws + 3 * pb);
-    if (int rc = outer_stage(p, false, false, ou, st)) return rc;
-    if (int rc = outer_stage(p, false, false, od, st)) return rc;
+    if (int rc = outer_stage(p, false, gated, ou, st)) return rc;
+    if (int rc = outer_stage(p, false, gated, od, st)) return rc;
     const int rows = H * p->R;
     CUtensorMap tur, tui, tdr, tdi;
     if (int rc = make_map(&tur, ou.pre, pairs * rows, kInner)) return rc;
@@ -443,6 +460,7 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
     if (int rc = make_map(&tdi, od.pim, pairs * rows, kInner)) return rc;
     prm.B = 2 * pairs; prm.H = rows; prm.L = kInner;
     prm.ksteps = 8;
+    prm.gated = 0;
     int grid = rows < p->num_sms ? rows : p->num_sms;
     dkf_kernel<true><<<grid, kThreads, kSmemTotalDkf, st>>>(tur, tdr, tui, tdi, prm);
     CUDA_TRY(cudaGetLastError());

@@ -27,11 +27,13 @@ struct DkfParams {
   const uint8_t* gtiles;
   float2* dkf;               // [H][4][128][16] complex fp32: k2 = 16*q + t, frequency k = k1 + 128*k2
   int B, H, L, pairs, ksteps;
+  int gated;                 // 1: u is multiplied by pregate and dout by postgate on load (tm_ui / tm_di = gate maps)
 };
 
 namespace r128 {
 
 constexpr int kSmemTotalDkf = kSmemData + kSmemG + kSmemBars + 1024;
+constexpr int kSmemTotalDkfGated = kSmemTotalDkf + kSmemGate + 1024;
 
 // kPlanes: inputs are complex rows in bf16 planes (composite sizes): (tm_u, tm_ui) = real / imaginary plane of the
 // transformed u rows, (tm_d, tm_di) likewise for dout; p.H = number of k_f rows, row = pr * p.H + channel.
@@ -43,6 +45,7 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_g = sbase + kSmemData;
   const uint32_t s_bars = s_g + kSmemG;
+  const uint32_t s_gate0 = s_bars + kSmemBars + 960;   // gated only (1024-byte aligned)
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
 
   const int tid = threadIdx.x;
@@ -133,13 +136,18 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
     const int b0 = 2 * pr, b1 = 2 * pr + 1;
     const uint32_t bar = bar_tma0 + 8 * slot;
     const uint32_t dst = s_slot0 + slot * kSlotBytes;
-    mbar_expect_tx(bar, kSlotBytes);
+    mbar_expect_tx(bar, (!kPlanes && p.gated) ? 2 * kSlotBytes : kSlotBytes);
     if (kPlanes) {
       tma_load_3d(dst, tm, bar, 0, 0, pr * p.H + h);
       tma_load_3d(dst + kTileBytes, tmi, bar, 0, 0, pr * p.H + h);
     } else {
       tma_load_3d(dst, tm, bar, 0, 0, b0 * p.H + h);
       tma_load_3d(dst + kTileBytes, tm, bar, 0, 0, b1 < p.B ? b1 * p.H + h : BH);   // out of bounds -> zeros
+      if (p.gated) {       // gate tiles (pregate for u, postgate for dout) into this pipeline's gate slot
+        const uint32_t gd = s_gate0 + pipe * kSlotBytes;
+        tma_load_3d(gd, tmi, bar, 0, 0, b0 * p.H + h);
+        tma_load_3d(gd + kTileBytes, tmi, bar, 0, 0, b1 < p.B ? b1 * p.H + h : BH);
+      }
     }
   };
   uint32_t mma_phase = 0;
@@ -161,9 +169,25 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   for (int n = 0; n < n_units; ++n) {
     const int slot = n & 1;
     const uint32_t sX = s_slot0 + slot * kSlotBytes;
+    if (!kPlanes && p.gated) {
+      // pass 0: X <- bf16(x * gate) in shared memory (reference: gated loads of the bwd kernel,
+      // kernels_bf16/monarch_cuda_32_16_16_bwd_kernel_bf16.h:505-509,571-581)
+      mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
+      const uint32_t sG = s_gate0 + pipe * kSlotBytes;
+#pragma unroll
+      for (int part = 0; part < 2; ++part)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t off = part * kTileBytes + uint32_t(lane) * 128u + uint32_t(4 * half + c) * 16u;
+          const uint4 a = ld_shared_v4(sX + off), g = ld_shared_v4(sG + off);
+          st_shared_v4(sX + off, hmul2_bf16(a.x, g.x), hmul2_bf16(a.y, g.y), hmul2_bf16(a.z, g.z), hmul2_bf16(a.w, g.w));
+        }
+      fence_proxy_async_smem();
+      named_bar_sync(bar_id, kPipeThreads);
+    }
     // ---------------- stage 1
     if (lead_warp) {
-      mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
+      if (!(!kPlanes && p.gated)) mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
         for (int s = 0; s < p.ksteps; ++s) mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, s > 0);

@@ -200,10 +200,11 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   auto issue_load = [&](int unit, int slot) {
     const uint32_t bar = bar_tma0 + 8 * slot;
     const uint32_t dst = s_slot0 + slot * kSlotBytes;
-    mbar_expect_tx(bar, kGated ? 2 * kSlotBytes : kSlotBytes);
+    const bool has_pre = kGated && p.pregate != nullptr;
+    mbar_expect_tx(bar, has_pre ? 2 * kSlotBytes : kSlotBytes);
     tma_load_3d(dst, &tm_u, bar, 0, 0, seq_index(unit, 0));
     tma_load_3d(dst + kTileBytes, kPlanes ? &tm_g : &tm_u, bar, 0, 0, seq_index(unit, 1));
-    if (kGated) {   // single pregate slot per pipeline: free again once pass 0 of the current unit is done
+    if (has_pre) {   // single pregate slot per pipeline: free again once pass 0 of the current unit is done
       const uint32_t gd = s_gate0 + pipe * kSlotBytes;
       tma_load_3d(gd, &tm_g, bar, 0, 0, seq_index(unit, 0));
       tma_load_3d(gd + kTileBytes, &tm_g, bar, 0, 0, seq_index(unit, 1));
@@ -252,7 +253,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
     const bool first = kDebug && (unit == 0);
     const int h = unit / p.pairs;
 
-    if (kGated) {
+    if (kGated && p.pregate != nullptr) {
       // ---------------- pass 0: X <- bf16(u * pregate), in place in shared memory (same swizzled positions)
       mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
       const uint32_t sG = s_gate0 + pipe * kSlotBytes;
@@ -269,7 +270,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
     }
     // ---------------- stage 1: D1 = F128 * X   (lane = k1, cols [0,64) re, [64,128) im)
     if (lead_warp) {
-      if (!kGated) mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
+      if (!(kGated && p.pregate != nullptr)) mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
       // D[:,0:128]  = C * [Xr | Xi]
@@ -409,7 +410,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
       __syncwarp();
     }
     uint4 pg[2][4];
-    if (kGated) {
+    const bool has_post = kGated && p.postgate != nullptr;
+    if (has_post) {
       const bool row_ok = lane * 64 < p.L;
 #pragma unroll
       for (int part = 0; part < 2; ++part) {
@@ -438,7 +440,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
           uint32_t o1 = pack_bf16x2(__uint_as_float(v[8 * cc + 2]), __uint_as_float(v[8 * cc + 3]));
           uint32_t o2 = pack_bf16x2(__uint_as_float(v[8 * cc + 4]), __uint_as_float(v[8 * cc + 5]));
           uint32_t o3 = pack_bf16x2(__uint_as_float(v[8 * cc + 6]), __uint_as_float(v[8 * cc + 7]));
-          if (kGated) {
+          if (has_post) {
             const uint4 g = pg[part][2 * sub + cc];
             o0 = hmul2_bf16(o0, g.x); o1 = hmul2_bf16(o1, g.y); o2 = hmul2_bf16(o2, g.z); o3 = hmul2_bf16(o3, g.w);
           }

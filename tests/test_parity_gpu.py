@@ -188,3 +188,33 @@ def test_bwd_composite_vs_oracle(ffc, N, B, H, L):
     du_ref, dk_ref = orc.ref_grads(d['u'], d['k'], d['dout'], N)
     _check(u.grad, du_ref, f'du N={N}')
     _check(k.grad, dk_ref, f'dk N={N}')
+
+
+@pytest.mark.parametrize('N,B,H,L', [(8192, 2, 3, 8192), (8192, 3, 4, 4096), (32768, 2, 2, 16384)])
+def test_bwd_gated_vs_oracle(ffc, N, B, H, L):
+    """du, dk, dpregate, dpostgate of the gated operator (tests/test_flashfftconv.py:226-243)."""
+    d = orc.make_inputs(B, H, N, L, torch.bfloat16, seed=31 + B, gated=True, unit_scale=True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    u = d['u'].cuda().requires_grad_(True)
+    k = d['k'].cuda().requires_grad_(True)
+    pre = d['pregate'].cuda().requires_grad_(True)
+    post = d['postgate'].cuda().requires_grad_(True)
+    conv(u, k, pre, post).backward(d['dout'].cuda())
+    du, dk, dpre, dpost = orc.ref_grads(d['u'], d['k'], d['dout'], N, d['pregate'], d['postgate'])
+    _check(u.grad, du, 'gated du')
+    _check(k.grad, dk, 'gated dk')
+    _check(pre.grad, dpre, 'dpregate')
+    _check(post.grad, dpost, 'dpostgate')
+
+
+def test_bwd_gated_golden(ffc, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'conv_n8192_bf16_gated.npz'))
+    N = int(g['N'])
+    t = lambda a: torch.from_numpy(a).to(torch.bfloat16).cuda().requires_grad_(True)
+    u, pre, post = t(g['u']), t(g['pregate']), t(g['postgate'])
+    k = torch.from_numpy(g['k']).cuda().requires_grad_(True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    conv(u, k, pre, post).backward(torch.from_numpy(g['dout']).to(torch.bfloat16).cuda())
+    for got, key in [(u.grad, 'du'), (pre.grad, 'dpregate'), (post.grad, 'dpostgate')]:
+        assert torch.allclose(got.float().cpu(), torch.from_numpy(g[key]), atol=1e-2), key   # test_flashfftconv.py:241-243
+    assert torch.allclose(k.grad.cpu(), torch.from_numpy(g['dk']), atol=1e-1)
