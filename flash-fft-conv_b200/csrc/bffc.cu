@@ -12,6 +12,7 @@
 #include "fwd_r128.cuh"
 #include "dkf_r128.cuh"
 #include "outer_cuda.cuh"
+#include "outer_r128.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -96,9 +97,13 @@ constexpr int kInner = 8192;   // the fused tcgen05 kernel's size
 
 }  // namespace
 
+struct bffc_level { int tc; int R; };   // tc = 1: tcgen05 radix-128 stage (outer_r128.cuh); 0: CUDA-core radix 2/4/8
+
 struct bffc_plan {
   int N;
-  int R;         // N = R * 8192; R > 1: outer radix-R stage on CUDA cores around the fused kernel
+  int R;         // N = R * 8192: product of the outer radices around the fused 8192-point kernel
+  int nlev;      // number of outer levels (0, 1 or 2), outermost first
+  bffc_level lev[2];
   int dtype;
   int device;
   __nv_bfloat16* dftC = nullptr;
@@ -114,9 +119,26 @@ int bffc_abi_version(void) { return BFFC_ABI_VERSION; }
 const char* bffc_last_error(void) { return g_err; }
 int bffc_last_launch_count(void) { return g_launches; }
 
+static int levels_for(int N, bffc_level* lev) {
+  switch (N) {
+    case 8192: return 0;
+    case 16384: lev[0] = {0, 2}; return 1;
+    case 32768: lev[0] = {0, 4}; return 1;
+    case 65536: lev[0] = {0, 8}; return 1;
+    case 131072: lev[0] = {0, 8}; lev[1] = {0, 2}; return 2;
+    case 262144: lev[0] = {0, 8}; lev[1] = {0, 4}; return 2;
+    case 524288: lev[0] = {0, 8}; lev[1] = {0, 8}; return 2;
+    case 1048576: lev[0] = {1, 128}; return 1;
+    case 2097152: lev[0] = {1, 128}; lev[1] = {0, 2}; return 2;
+    case 4194304: lev[0] = {1, 128}; lev[1] = {0, 4}; return 2;
+    default: return -1;
+  }
+}
+
 int bffc_supported(int seqlen, int dtype) {
   if (dtype != BFFC_DTYPE_BF16) return 0;
-  return (seqlen == 8192 || seqlen == 16384 || seqlen == 32768 || seqlen == 65536) ? 1 : 0;
+  bffc_level lev[2];
+  return levels_for(seqlen, lev) >= 0 ? 1 : 0;
 }
 
 int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
@@ -131,6 +153,7 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   bffc_plan* p = new bffc_plan();
   p->N = seqlen;
   p->R = seqlen / kInner;
+  p->nlev = levels_for(seqlen, p->lev);
   p->dtype = dtype;
   CUDA_TRY(cudaGetDevice(&p->device));
   CUDA_TRY(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
@@ -167,19 +190,20 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   CUDA_TRY(cudaMalloc(&p->gtiles, gt.size()));
   CUDA_TRY(cudaMemcpy(p->gtiles, gt.data(), gt.size(), cudaMemcpyHostToDevice));
 
-  // engine order (32-bit words), per channel h: R rows (c = 0..R-1) of 8192 words; inside a row
+  // engine order (32-bit words), per channel h: R rows of 8192 words, row = c0*R1 + c1 (outer digits); inside a row
   //   w = (cc*128 + k1)*4 + 2*pp + part  holds the bf16 pair (part ? imag : real) of k_f at inner frequencies
-  //   k' = k1 + 128*k2 with k2 = 4cc + 2pp and k2 + 1; natural frequency k = c + R*k'.
-  // perm[c*8192 + w] = 2 * (natural index of the first element) + part; the second element is 128*R further.
-  const int R = p->R;
+  //   k'' = k1 + 128*k2 with k2 = 4cc + 2pp and k2 + 1; natural frequency k = c0 + R0*(c1 + R1*k'').
+  // perm[row*8192 + w] = 2 * (natural index of the first element) + part; the second element is 128*R further.
+  const int R0 = p->nlev >= 1 ? p->lev[0].R : 1, R1 = p->nlev >= 2 ? p->lev[1].R : 1;
   std::vector<int> perm(seqlen);
-  for (int cr = 0; cr < R; ++cr)
-    for (int cc = 0; cc < 16; ++cc)
-      for (int k1 = 0; k1 < 128; ++k1)
-        for (int pp = 0; pp < 2; ++pp)
-          for (int part = 0; part < 2; ++part)
-            perm[cr * kInner + (cc * 128 + k1) * 4 + 2 * pp + part] =
-                (cr + R * (k1 + 128 * (4 * cc + 2 * pp))) * 2 + part;
+  for (int c0 = 0; c0 < R0; ++c0)
+    for (int c1 = 0; c1 < R1; ++c1)
+      for (int cc = 0; cc < 16; ++cc)
+        for (int k1 = 0; k1 < 128; ++k1)
+          for (int pp = 0; pp < 2; ++pp)
+            for (int part = 0; part < 2; ++part)
+              perm[(c0 * R1 + c1) * kInner + (cc * 128 + k1) * 4 + 2 * pp + part] =
+                  (c0 + R0 * (c1 + R1 * (k1 + 128 * (4 * cc + 2 * pp)))) * 2 + part;
   CUDA_TRY(cudaMalloc(&p->perm, perm.size() * sizeof(int)));
   CUDA_TRY(cudaMemcpy(p->perm, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice));
 
@@ -192,6 +216,8 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf));
   CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf));
   CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkfGated));
+  CUDA_TRY(cudaFuncSetAttribute(outer_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOuterGated));
+  CUDA_TRY(cudaFuncSetAttribute(outer_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOuter));
   *out = p;
   return BFFC_OK;
 }
@@ -220,7 +246,8 @@ int bffc_dkf_unpack(const bffc_plan* p, const void* dkf_engine, void* dkf_natura
   if (!p || !dkf_engine || !dkf_natural || H <= 0) return fail(BFFC_ERR_INVALID, "bffc_dkf_unpack: bad argument");
   dim3 grid(64, H);
   bffc::r128::dkf_unpack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float2*>(dkf_engine), static_cast<float2*>(dkf_natural), p->N, p->R);
+      static_cast<const float2*>(dkf_engine), static_cast<float2*>(dkf_natural), p->N,
+      p->nlev >= 1 ? p->lev[0].R : 1, p->nlev >= 2 ? p->lev[1].R : 1);
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -232,8 +259,9 @@ static size_t plane_bytes(const bffc_plan* p, int B, int H) { return size_t((B +
 
 extern "C" size_t bffc_workspace_bytes(const bffc_plan* p, int B, int H, int L) {
   (void)L;
-  if (!p || p->R == 1) return 0;
-  return 4 * plane_bytes(p, B, H);      // forward uses 2 planes; backward transforms u and dout: 4 planes
+  if (!p || p->nlev == 0) return 0;
+  // plane sets (real + imaginary plane each): forward nlev sets; backward nlev + 1 (transformed u and dout)
+  return size_t(2 * (p->nlev + 1)) * plane_bytes(p, B, H);
 }
 
 static int make_map(CUtensorMap* map, const void* base, int rows, int L) {
@@ -312,26 +340,143 @@ static int launch_planes(const bffc_plan* p, void* pre, void* pim, const void* k
   return BFFC_OK;
 }
 
+static int make_map4(CUtensorMap* map, const void* base, int chunks, int rows, int seqs, size_t row_stride_bytes,
+                     size_t seq_stride_bytes) {
+  // [seq][row][chunk][64] bf16 view of a strided matrix; box = 128 rows x 64 columns of one chunk, 128B swizzle.
+  cuuint64_t dims[4] = {64, cuuint64_t(chunks), cuuint64_t(rows), cuuint64_t(seqs)};
+  cuuint64_t strides[3] = {128, cuuint64_t(row_stride_bytes), cuuint64_t(seq_stride_bytes)};
+  cuuint32_t box[4] = {64, 1, 128, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(BFFC_ERR_CUDA, "cuTensorMapEncodeTiled (4d) failed (%d)", int(r));
+  return 0;
+}
+
+struct PlaneSet { uint8_t* re; uint8_t* im; };
+
 template <int R>
-static void launch_outer(bool inverse, bool gated, const bffc::outer::OuterParams& op, cudaStream_t st) {
-  dim3 grid(bffc::outer::kM / (bffc::outer::kVec * 128), op.H, op.pairs);
+static void launch_cc(bool inverse, bool gated, bool planes, const bffc::outer::OuterParams& op, int rows, cudaStream_t st) {
   using namespace bffc::outer;
-  if (!inverse) {
-    if (gated) fwd_kernel<R, true><<<grid, 128, 0, st>>>(op);
-    else fwd_kernel<R, false><<<grid, 128, 0, st>>>(op);
+  const int cb = op.M / (kVec * 128);
+  if (planes) {
+    dim3 grid(rows, cb, 1);
+    if (!inverse) fwd_kernel<R, false, true><<<grid, 128, 0, st>>>(op);
+    else inv_kernel<R, false, true><<<grid, 128, 0, st>>>(op);
   } else {
-    if (gated) inv_kernel<R, true><<<grid, 128, 0, st>>>(op);
-    else inv_kernel<R, false><<<grid, 128, 0, st>>>(op);
+    dim3 grid(cb, op.H, op.pairs);
+    if (!inverse) {
+      if (gated) fwd_kernel<R, true, false><<<grid, 128, 0, st>>>(op);
+      else fwd_kernel<R, false, false><<<grid, 128, 0, st>>>(op);
+    } else {
+      if (gated) inv_kernel<R, true, false><<<grid, 128, 0, st>>>(op);
+      else inv_kernel<R, false, false><<<grid, 128, 0, st>>>(op);
+    }
   }
 }
-static int outer_stage(const bffc_plan* p, bool inverse, bool gated, const bffc::outer::OuterParams& op, cudaStream_t st) {
-  switch (p->R) {
-    case 2: launch_outer<2>(inverse, gated, op, st); break;
-    case 4: launch_outer<4>(inverse, gated, op, st); break;
-    case 8: launch_outer<8>(inverse, gated, op, st); break;
-    default: return fail(BFFC_ERR_UNSUPPORTED, "outer radix %d not supported", p->R);
+static int cc_stage(int R, bool inverse, bool gated, bool planes, const bffc::outer::OuterParams& op, int rows,
+                    cudaStream_t st) {
+  switch (R) {
+    case 2: launch_cc<2>(inverse, gated, planes, op, rows, st); break;
+    case 4: launch_cc<4>(inverse, gated, planes, op, rows, st); break;
+    case 8: launch_cc<8>(inverse, gated, planes, op, rows, st); break;
+    default: return fail(BFFC_ERR_UNSUPPORTED, "outer radix %d not supported", R);
   }
   CUDA_TRY(cudaGetLastError());
+  return BFFC_OK;
+}
+
+// tcgen05 radix-128 level 0: real endpoint x (u or y), gate g (pregate fwd / postgate inv), planes set A
+static int tc_stage(const bffc_plan* p, bool inverse, const void* x, const void* gate, PlaneSet A, int B, int H, int L,
+                    cudaStream_t st) {
+  const int M = p->N / 128, chunks = M / 64, pairs = (B + 1) / 2;
+  if (L % M != 0) return fail(BFFC_ERR_UNSUPPORTED, "seqlen %d needs L to be a multiple of %d in this build (L=%d)", p->N, M, L);
+  CUtensorMap tm_x, tm_pr, tm_pi, tm_g;
+  if (int rc = make_map4(&tm_x, x, chunks, L / M, B * H, size_t(M) * 2, size_t(L) * 2)) return rc;
+  if (int rc = make_map4(&tm_pr, A.re, chunks, 128, pairs * H, size_t(M) * 2, size_t(p->N) * 2)) return rc;
+  if (int rc = make_map4(&tm_pi, A.im, chunks, 128, pairs * H, size_t(M) * 2, size_t(p->N) * 2)) return rc;
+  if (int rc = make_map4(&tm_g, (!inverse && gate) ? gate : x, chunks, L / M, B * H, size_t(M) * 2, size_t(L) * 2)) return rc;
+  bffc::OuterTcParams prm;
+  prm.dftC = p->dftC; prm.dftS = p->dftS;
+  prm.postgate = inverse ? static_cast<const uint32_t*>(gate) : nullptr;
+  prm.has_pregate = (!inverse && gate) ? 1 : 0;
+  prm.B = B; prm.H = H; prm.L = L; prm.pairs = pairs;
+  prm.N = p->N; prm.M = M; prm.chunks = chunks;
+  prm.ksteps = (L / M + 15) / 16;
+  prm.units = pairs * H * chunks;
+  int grid = (prm.units + 1) / 2;
+  if (grid > p->num_sms) grid = p->num_sms;
+  using namespace bffc::r128;
+  if (!inverse)
+    outer_tc_kernel<false><<<grid, kThreads, prm.has_pregate ? kSmemOuterGated : kSmemOuter, st>>>(tm_x, tm_pr, tm_pi, tm_g, prm);
+  else
+    outer_tc_kernel<true><<<grid, kThreads, kSmemOuter, st>>>(tm_x, tm_pr, tm_pi, tm_g, prm);
+  CUDA_TRY(cudaGetLastError());
+  return BFFC_OK;
+}
+
+static PlaneSet plane_set(const bffc_plan* p, void* ws, int idx, int B, int H) {
+  uint8_t* b = static_cast<uint8_t*>(ws) + size_t(2 * idx) * plane_bytes(p, B, H);
+  return PlaneSet{b, b + plane_bytes(p, B, H)};
+}
+
+// all outer levels, forward: real (B,H,L) x (* pregate) -> complex 8192-point rows.  Level 0 writes set `s0`,
+// level 1 (if any) reads `s0` and writes `s1`; returns the set holding the rows.
+static int transform_fwd(const bffc_plan* p, const void* x, const void* pregate, int B, int H, int L, PlaneSet s0,
+                         PlaneSet s1, PlaneSet* out, cudaStream_t st, int* launches) {
+  const int pairs = (B + 1) / 2;
+  const bffc_level l0 = p->lev[0];
+  if (l0.tc) {
+    if (int rc = tc_stage(p, false, x, pregate, s0, B, H, L, st)) return rc;
+  } else {
+    bffc::outer::OuterParams op{};
+    op.u = static_cast<const uint4*>(x);
+    op.pregate = static_cast<const uint4*>(pregate);
+    op.pre = reinterpret_cast<uint4*>(s0.re); op.pim = reinterpret_cast<uint4*>(s0.im);
+    op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / l0.R;
+    if (int rc = cc_stage(l0.R, false, pregate != nullptr, false, op, 0, st)) return rc;
+  }
+  *launches += 1;
+  *out = s0;
+  if (p->nlev == 2) {
+    const bffc_level l1 = p->lev[1];
+    bffc::outer::OuterParams op{};
+    op.xre = reinterpret_cast<uint4*>(s0.re); op.xim = reinterpret_cast<uint4*>(s0.im);
+    op.pre = reinterpret_cast<uint4*>(s1.re); op.pim = reinterpret_cast<uint4*>(s1.im);
+    op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / (l0.R * l1.R);
+    if (int rc = cc_stage(l1.R, false, false, true, op, pairs * H * l0.R, st)) return rc;
+    *launches += 1;
+    *out = s1;
+  }
+  return BFFC_OK;
+}
+
+// all outer levels, inverse: rows in `rows` (set s1 if two levels, else s0) -> real y (* postgate)
+static int transform_inv(const bffc_plan* p, void* y, const void* postgate, int B, int H, int L, PlaneSet s0, PlaneSet s1,
+                         cudaStream_t st, int* launches) {
+  const int pairs = (B + 1) / 2;
+  const bffc_level l0 = p->lev[0];
+  if (p->nlev == 2) {
+    const bffc_level l1 = p->lev[1];
+    bffc::outer::OuterParams op{};
+    op.xre = reinterpret_cast<uint4*>(s0.re); op.xim = reinterpret_cast<uint4*>(s0.im);
+    op.pre = reinterpret_cast<uint4*>(s1.re); op.pim = reinterpret_cast<uint4*>(s1.im);
+    op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / (l0.R * l1.R);
+    if (int rc = cc_stage(l1.R, true, false, true, op, pairs * H * l0.R, st)) return rc;
+    *launches += 1;
+  }
+  if (l0.tc) {
+    if (int rc = tc_stage(p, true, y, postgate, s0, B, H, L, st)) return rc;
+  } else {
+    bffc::outer::OuterParams op{};
+    op.y = static_cast<uint4*>(y);
+    op.postgate = static_cast<const uint4*>(postgate);
+    op.pre = reinterpret_cast<uint4*>(s0.re); op.pim = reinterpret_cast<uint4*>(s0.im);
+    op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / l0.R;
+    if (int rc = cc_stage(l0.R, true, postgate != nullptr, false, op, 0, st)) return rc;
+  }
+  *launches += 1;
   return BFFC_OK;
 }
 
@@ -344,28 +489,19 @@ static int check_common(const bffc_plan* p, int B, int H, int L, const void* a, 
   return 0;
 }
 
-// y = postgate * conv(u * pregate, k) for any supported size.  `planes`: workspace for composite sizes.
+// y = postgate * conv(u * pregate, k) for any supported size.  `ws`: workspace (plane sets 0 and 1) for composite sizes.
 static int conv_forward(const bffc_plan* p, const void* u, const void* kf, const void* pregate, const void* postgate,
-                        void* y, int B, int H, int L, void* planes, cudaStream_t st, int* launches) {
-  if (p->R == 1) {
+                        void* y, int B, int H, int L, void* ws, cudaStream_t st, int* launches) {
+  if (p->nlev == 0) {
     *launches += 1;
     return launch_fused(p, u, kf, pregate, postgate, y, B, H, L, nullptr, 0, 0, st);
   }
   const int pairs = (B + 1) / 2;
-  uint8_t* ws = static_cast<uint8_t*>(planes);
-  bffc::outer::OuterParams op;
-  op.u = static_cast<const uint4*>(u);
-  op.pregate = static_cast<const uint4*>(pregate);
-  op.postgate = static_cast<const uint4*>(postgate);
-  op.y = static_cast<uint4*>(y);
-  op.pre = reinterpret_cast<uint4*>(ws);
-  op.pim = reinterpret_cast<uint4*>(ws + plane_bytes(p, B, H));
-  op.B = B; op.H = H; op.L = L; op.pairs = pairs;
-  if (int rc = outer_stage(p, false, pregate != nullptr, op, st)) return rc;
-  if (int rc = launch_planes(p, op.pre, op.pim, kf, pairs, H * p->R, st)) return rc;
-  if (int rc = outer_stage(p, true, postgate != nullptr, op, st)) return rc;
-  *launches += 3;
-  return BFFC_OK;
+  PlaneSet s0 = plane_set(p, ws, 0, B, H), s1 = plane_set(p, ws, p->nlev == 2 ? 1 : 0, B, H), rows;
+  if (int rc = transform_fwd(p, u, pregate, B, H, L, s0, s1, &rows, st, launches)) return rc;
+  if (int rc = launch_planes(p, rows.re, rows.im, kf, pairs, H * p->R, st)) return rc;
+  *launches += 1;
+  return transform_inv(p, y, postgate, B, H, L, s0, s1, st, launches);
 }
 
 extern "C" {
@@ -378,8 +514,8 @@ int bffc_fwd(const bffc_plan* p, const void* u, const void* kf, const void* preg
   if (int rc = check_common(p, B, H, L, u, y, kf)) return rc;
   if ((reinterpret_cast<uintptr_t>(pregate) | reinterpret_cast<uintptr_t>(postgate) | reinterpret_cast<uintptr_t>(workspace)) & 15)
     return fail(BFFC_ERR_INVALID, "bffc_fwd: gates / workspace must be 16-byte aligned");
-  if (p->R > 1 && (!workspace || workspace_bytes < 2 * plane_bytes(p, B, H)))
-    return fail(BFFC_ERR_INVALID, "bffc_fwd: workspace of %zu bytes required", 2 * plane_bytes(p, B, H));
+  if (p->nlev > 0 && (!workspace || workspace_bytes < size_t(2 * p->nlev) * plane_bytes(p, B, H)))
+    return fail(BFFC_ERR_INVALID, "bffc_fwd: workspace of %zu bytes required", size_t(2 * p->nlev) * plane_bytes(p, B, H));
   int launches = 0;
   int rc = conv_forward(p, u, kf, pregate, postgate, y, B, H, L, workspace, static_cast<cudaStream_t>(stream), &launches);
   g_launches = launches;
@@ -400,8 +536,8 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
   if (int rc = check_common(p, B, H, L, u, du, dout)) return rc;
   if ((reinterpret_cast<uintptr_t>(dkf) | reinterpret_cast<uintptr_t>(kf_conj) | reinterpret_cast<uintptr_t>(workspace)) & 15)
     return fail(BFFC_ERR_INVALID, "bffc_bwd: dkf / kf / workspace must be 16-byte aligned");
-  if (p->R > 1 && (!workspace || workspace_bytes < 4 * plane_bytes(p, B, H)))
-    return fail(BFFC_ERR_INVALID, "bffc_bwd: workspace of %zu bytes required", 4 * plane_bytes(p, B, H));
+  if (p->nlev > 0 && (!workspace || workspace_bytes < bffc_workspace_bytes(p, B, H, L)))
+    return fail(BFFC_ERR_INVALID, "bffc_bwd: workspace of %zu bytes required", bffc_workspace_bytes(p, B, H, L));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int launches = 0;
   // du = corr(dout, k) = circular conv with conj(k_f): the forward path on dout
@@ -425,7 +561,7 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
   prm.dkf = static_cast<float2*>(dkf);
   prm.pairs = pairs;
   using namespace bffc::r128;
-  if (p->R == 1) {
+  if (p->nlev == 0) {
     if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen 8192 in this build", L);
     CUtensorMap tm_u, tm_d, tm_p, tm_q;
     if (int rc = make_map(&tm_u, u, B * H, L)) return rc;
@@ -440,31 +576,30 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
     CUDA_TRY(cudaGetLastError());
     launches += 1;
   } else {
-    uint8_t* ws = static_cast<uint8_t*>(workspace);
-    const size_t pb = plane_bytes(p, B, H);
-    bffc::outer::OuterParams ou, od;
-    ou.u = static_cast<const uint4*>(u); ou.pregate = static_cast<const uint4*>(pregate); ou.postgate = nullptr; ou.y = nullptr;
-    ou.pre = reinterpret_cast<uint4*>(ws); ou.pim = reinterpret_cast<uint4*>(ws + pb);
-    ou.B = B; ou.H = H; ou.L = L; ou.pairs = pairs;
-    od = ou;
-    od.u = static_cast<const uint4*>(dout);
-    od.pregate = static_cast<const uint4*>(postgate);
-    od.pre = reinterpret_cast<uint4*>(ws + 2 * pb); od.pim = reinterpret_cast<uint4*>(ws + 3 * pb);
-    if (int rc = outer_stage(p, false, gated, ou, st)) return rc;
-    if (int rc = outer_stage(p, false, gated, od, st)) return rc;
+    // transformed u rows -> set U, transformed dout rows -> set D (set 0 is the level-0 intermediate when nlev == 2)
+    PlaneSet s0 = plane_set(p, workspace, 0, B, H);
+    PlaneSet sU = p->nlev == 2 ? plane_set(p, workspace, 1, B, H) : s0;
+    PlaneSet sD = plane_set(p, workspace, p->nlev == 2 ? 2 : 1, B, H);
+    PlaneSet ru, rd;
+    if (int rc = transform_fwd(p, u, pregate, B, H, L, s0, sU, &ru, st, &launches)) return rc;
+    if (p->nlev == 2) {
+      if (int rc = transform_fwd(p, dout, postgate, B, H, L, s0, sD, &rd, st, &launches)) return rc;
+    } else {
+      if (int rc = transform_fwd(p, dout, postgate, B, H, L, sD, sD, &rd, st, &launches)) return rc;
+    }
     const int rows = H * p->R;
     CUtensorMap tur, tui, tdr, tdi;
-    if (int rc = make_map(&tur, ou.pre, pairs * rows, kInner)) return rc;
-    if (int rc = make_map(&tui, ou.pim, pairs * rows, kInner)) return rc;
-    if (int rc = make_map(&tdr, od.pre, pairs * rows, kInner)) return rc;
-    if (int rc = make_map(&tdi, od.pim, pairs * rows, kInner)) return rc;
+    if (int rc = make_map(&tur, ru.re, pairs * rows, kInner)) return rc;
+    if (int rc = make_map(&tui, ru.im, pairs * rows, kInner)) return rc;
+    if (int rc = make_map(&tdr, rd.re, pairs * rows, kInner)) return rc;
+    if (int rc = make_map(&tdi, rd.im, pairs * rows, kInner)) return rc;
     prm.B = 2 * pairs; prm.H = rows; prm.L = kInner;
     prm.ksteps = 8;
     prm.gated = 0;
     int grid = rows < p->num_sms ? rows : p->num_sms;
     dkf_kernel<true><<<grid, kThreads, kSmemTotalDkf, st>>>(tur, tdr, tui, tdi, prm);
     CUDA_TRY(cudaGetLastError());
-    launches += 3;
+    launches += 1;
   }
   g_launches = launches;
   return BFFC_OK;

@@ -124,7 +124,7 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   const uint32_t bar_id = 1 + pipe;
   const uint32_t sG0 = s_g;
   const CUtensorMap* tm = (pipe == 0) ? &tm_u : &tm_d;
-  const CUtensorMap* tmi = kPlanes ? ((pipe == 0) ? &tm_ui : &tm_di) : tm;
+  const CUtensorMap* tmi = (kPlanes || p.gated) ? ((pipe == 0) ? &tm_ui : &tm_di) : tm;   // imaginary plane / gate
   const int BH = p.B * p.H;
 
   // units of this CTA: (h, pr) for h = blockIdx.x, blockIdx.x + gridDim.x, ...
@@ -282,13 +282,15 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
 }
 
 // dk_f engine order -> natural order complex64 (reference analogue: the inverse permutation at conv.py:1818).
-// Composite sizes: channel row = h*R + c holds frequencies k = c + R*(k1 + 128*k2).
-__global__ void dkf_unpack_kernel(const float2* __restrict__ eng, float2* __restrict__ nat, int N, int R) {
+// Composite sizes: channel row (h*R0 + c0)*R1 + c1 holds frequencies k = c0 + R0*(c1 + R1*(k1 + 128*k2)).
+__global__ void dkf_unpack_kernel(const float2* __restrict__ eng, float2* __restrict__ nat, int N, int R0, int R1) {
   const int h = blockIdx.y;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
-    const int c = k % R, kk = k / R;
+    const int c0 = k % R0, r0 = k / R0;
+    const int c1 = r0 % R1, kk = r0 / R1;
     const int k1 = kk & 127, k2 = kk >> 7;
-    nat[size_t(h) * N + k] = eng[(((size_t(h) * R + c) * 4 + (k2 >> 4)) * 128 + k1) * 16 + (k2 & 15)];
+    const size_t row = (size_t(h) * R0 + c0) * R1 + c1;
+    nat[size_t(h) * N + k] = eng[((row * 4 + (k2 >> 4)) * 128 + k1) * 16 + (k2 & 15)];
   }
 }
 

@@ -16,7 +16,6 @@
 namespace bffc {
 namespace outer {
 
-constexpr int kM = 8192;
 constexpr int kVec = 8;
 
 DEVINL void unpack8(const uint4& v, float (&f)[8]) {
@@ -39,13 +38,16 @@ DEVINL uint4 hmul8(const uint4& a, const uint4& b) {
 }
 
 struct OuterParams {
-  const uint4* u;        // (B, H, L) bf16
+  const uint4* u;        // (B, H, L) bf16                                  (real endpoint, level 0)
   const uint4* pregate;  // optional
   const uint4* postgate; // optional
   uint4* y;              // (B, H, L) bf16 (inverse only)
-  uint4* pre;            // planes: real parts,  rows = pairs*H*R, each row M bf16
-  uint4* pim;            // planes: imaginary parts
+  uint4* xre;            // kPlanes: outer-side complex rows (rows x R*M), read by fwd / written by inv
+  uint4* xim;
+  uint4* pre;            // inner-side planes: real parts,  rows*R rows of M bf16 each
+  uint4* pim;            // inner-side planes: imaginary parts
   int B, H, L, pairs;
+  int M;                 // inner row length
 };
 
 // W_R^{a c} for R <= 8 as exact constants
@@ -57,10 +59,11 @@ DEVINL void wr(int R, int e, float& c, float& s) {   // exp(-2 pi i e / R)
   c = cs[t]; s = sn[t];
 }
 
-// forward: grid (M / (kVec*blockDim.x), H, pairs)
-template <int R, bool kGated>
+// forward: grid (M / (kVec*blockDim.x), H, pairs)   [kPlanes: (rows, M / (kVec*blockDim.x), 1)]
+template <int R, bool kGated, bool kPlanes>
 __global__ void __launch_bounds__(128) fwd_kernel(const OuterParams p) {
-  const int np = (blockIdx.x * blockDim.x + threadIdx.x) * kVec;   // n'
+  const int kM = p.M;
+  const int np = ((kPlanes ? blockIdx.y : blockIdx.x) * blockDim.x + threadIdx.x) * kVec;   // n'
   const int h = blockIdx.y, pr = blockIdx.z;
   const int b0 = 2 * pr, b1 = 2 * pr + 1;
   const size_t L8 = size_t(p.L) / kVec;
@@ -69,7 +72,12 @@ __global__ void __launch_bounds__(128) fwd_kernel(const OuterParams p) {
 #pragma unroll
   for (int a = 0; a < R; ++a) {
     const int n = a * kM + np;
-    if (n < p.L) {
+    if (kPlanes) {
+      rows = R;
+      const size_t o = (size_t(blockIdx.x) * R * kM + n) / kVec;
+      unpack8(__ldg(p.xre + o), zr[a]);
+      unpack8(__ldg(p.xim + o), zi[a]);
+    } else if (n < p.L) {
       rows = a + 1;
       const size_t o0 = (size_t(b0) * p.H + h) * L8 + n / kVec;
       uint4 v0 = __ldg(p.u + o0);
@@ -122,16 +130,17 @@ __global__ void __launch_bounds__(128) fwd_kernel(const OuterParams p) {
       ws[t] = wc[t] * w1s[t] + ws[t] * w1c[t];
       wc[t] = nc;
     }
-    const size_t row = (size_t(pr) * p.H + h) * R + c;
+    const size_t row = (kPlanes ? size_t(blockIdx.x) : (size_t(pr) * p.H + h)) * R + c;
     p.pre[row * (kM / kVec) + np / kVec] = pack8(or_);
     p.pim[row * (kM / kVec) + np / kVec] = pack8(oi_);
   }
 }
 
 // inverse: same grid
-template <int R, bool kGated>
+template <int R, bool kGated, bool kPlanes>
 __global__ void __launch_bounds__(128) inv_kernel(const OuterParams p) {
-  const int np = (blockIdx.x * blockDim.x + threadIdx.x) * kVec;
+  const int kM = p.M;
+  const int np = ((kPlanes ? blockIdx.y : blockIdx.x) * blockDim.x + threadIdx.x) * kVec;
   const int h = blockIdx.y, pr = blockIdx.z;
   const int b0 = 2 * pr, b1 = 2 * pr + 1;
   const size_t L8 = size_t(p.L) / kVec;
@@ -144,7 +153,7 @@ __global__ void __launch_bounds__(128) inv_kernel(const OuterParams p) {
   float tr[R][8], ti[R][8];
 #pragma unroll
   for (int c = 0; c < R; ++c) {
-    const size_t row = (size_t(pr) * p.H + h) * R + c;
+    const size_t row = (kPlanes ? size_t(blockIdx.x) : (size_t(pr) * p.H + h)) * R + c;
     float xr[8], xi[8];
     unpack8(__ldg(p.pre + row * (kM / kVec) + np / kVec), xr);
     unpack8(__ldg(p.pim + row * (kM / kVec) + np / kVec), xi);
@@ -160,7 +169,7 @@ __global__ void __launch_bounds__(128) inv_kernel(const OuterParams p) {
 #pragma unroll
   for (int a = 0; a < R; ++a) {
     const int n = a * kM + np;
-    if (n < p.L) {
+    if (kPlanes || n < p.L) {
       float yr[8], yi[8];
 #pragma unroll
       for (int t = 0; t < 8; ++t) { yr[t] = 0.f; yi[t] = 0.f; }
@@ -173,6 +182,12 @@ __global__ void __launch_bounds__(128) inv_kernel(const OuterParams p) {
           yr[t] += tr[c][t] * fc - ti[c][t] * fs;
           yi[t] += tr[c][t] * fs + ti[c][t] * fc;
         }
+      }
+      if (kPlanes) {
+        const size_t o = (size_t(blockIdx.x) * R * kM + n) / kVec;
+        p.xre[o] = pack8(yr);
+        p.xim[o] = pack8(yi);
+        continue;
       }
       const size_t o0 = (size_t(b0) * p.H + h) * L8 + n / kVec;
       uint4 v0 = pack8(yr);

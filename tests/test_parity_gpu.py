@@ -218,3 +218,36 @@ def test_bwd_gated_golden(ffc, golden_dir):
     for got, key in [(u.grad, 'du'), (pre.grad, 'dpregate'), (post.grad, 'dpostgate')]:
         assert torch.allclose(got.float().cpu(), torch.from_numpy(g[key]), atol=1e-2), key   # test_flashfftconv.py:241-243
     assert torch.allclose(k.grad.cpu(), torch.from_numpy(g['dk']), atol=1e-1)
+
+
+# ----------------------------------------------------------------------------- long sizes (two outer levels / tcgen05 outer stage)
+LONG = [(131072, 2, 2, 131072), (262144, 1, 2, 131072), (524288, 2, 1, 524288), (1048576, 2, 2, 1048576),
+        (1048576, 3, 2, 524288), (2097152, 2, 1, 2097152), (4194304, 2, 1, 4194304), (4194304, 1, 2, 2097152)]
+
+
+@pytest.mark.parametrize('N,B,H,L', LONG)
+def test_fwd_long_vs_oracle(ffc, N, B, H, L):
+    d = orc.make_inputs(B, H, N, L, torch.bfloat16, seed=N // 100000 + B, unit_scale=True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    y = conv(d['u'].cuda(), d['k'].cuda())
+    _check(y, orc.ref_fft_conv(d['u'], d['k'], N), f'fwd N={N} B={B} H={H} L={L}')
+
+
+@pytest.mark.parametrize('N,B,H,L', [(1048576, 2, 2, 524288), (4194304, 2, 1, 2097152), (262144, 2, 2, 262144)])
+def test_fwd_long_gated_vs_oracle(ffc, N, B, H, L):
+    d = orc.make_inputs(B, H, N, L, torch.bfloat16, seed=9, gated=True, unit_scale=True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    y = conv(d['u'].cuda(), d['k'].cuda(), d['pregate'].cuda(), d['postgate'].cuda())
+    _check(y, orc.ref_fft_conv_gated(d['u'], d['k'], d['pregate'], d['postgate'], N), f'gated fwd N={N}')
+
+
+@pytest.mark.parametrize('N,B,H,L', [(1048576, 2, 2, 1048576), (4194304, 2, 1, 2097152), (524288, 3, 1, 524288)])
+def test_bwd_long_vs_oracle(ffc, N, B, H, L):
+    d = orc.make_inputs(B, H, N, L, torch.bfloat16, seed=41 + B, unit_scale=True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    u = d['u'].cuda().requires_grad_(True)
+    k = d['k'].cuda().requires_grad_(True)
+    conv(u, k).backward(d['dout'].cuda())
+    du_ref, dk_ref = orc.ref_grads(d['u'], d['k'], d['dout'], N)
+    _check(u.grad, du_ref, f'du N={N}')
+    _check(k.grad, dk_ref, f'dk N={N}')
