@@ -78,17 +78,24 @@ uint16_t f2bf(double x) {  // round-to-nearest-even float -> bf16 bits
   return static_cast<uint16_t>((u + r) >> 16);
 }
 
+// kHalf: the source holds only frequencies 0..N/2 of a real filter (torch.fft.rfft); k > N/2 is conj(src[N-k]).
+template <bool kHalf>
 __global__ void kf_pack_kernel(const float* __restrict__ kf_nat, uint32_t* __restrict__ kf_eng,
                                const int* __restrict__ perm, int N, int pair_stride, float scale, int conj) {
   const int h = blockIdx.y;
-  const float* src = kf_nat + size_t(h) * N * 2;      // interleaved (re, im) fp32
+  const float* src = kf_nat + size_t(h) * (kHalf ? (N / 2 + 1) : N) * 2;      // interleaved (re, im) fp32
   for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < N; w += gridDim.x * blockDim.x) {
     const int pw = perm[w];
     const int part = pw & 1;
-    const float sc = (part && conj) ? -scale : scale;
-    const float a = src[pw] * sc;                      // element k      (re or im)
-    const float b = src[pw + 2 * pair_stride] * sc;    // element k + pair_stride
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    float v2[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      int k = (pw >> 1) + e * pair_stride;               // natural frequency of this element
+      float sc = (part && conj) ? -scale : scale;
+      if (kHalf && k > N / 2) { k = N - k; if (part) sc = -sc; }
+      v2[e] = src[2 * k + part] * sc;
+    }
+    __nv_bfloat162 v = __floats2bfloat162_rn(v2[0], v2[1]);
     kf_eng[size_t(h) * N + w] = *reinterpret_cast<uint32_t*>(&v);
   }
 }
@@ -235,8 +242,18 @@ int bffc_plan_destroy(bffc_plan* p) {
 int bffc_kf_pack(const bffc_plan* p, const void* kf_natural, void* kf_engine, int H, int conj, void* stream) {
   if (!p || !kf_natural || !kf_engine || H <= 0) return fail(BFFC_ERR_INVALID, "bffc_kf_pack: bad argument");
   dim3 grid(64, H);
-  kf_pack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  kf_pack_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float*>(kf_natural), static_cast<uint32_t*>(kf_engine), p->perm, p->N, 128 * p->R,
+      1.0f / float(p->N), conj);
+  CUDA_TRY(cudaGetLastError());
+  return BFFC_OK;
+}
+
+int bffc_kf_pack_rfft(const bffc_plan* p, const void* kf_half, void* kf_engine, int H, int conj, void* stream) {
+  if (!p || !kf_half || !kf_engine || H <= 0) return fail(BFFC_ERR_INVALID, "bffc_kf_pack_rfft: bad argument");
+  dim3 grid(64, H);
+  kf_pack_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(kf_half), static_cast<uint32_t*>(kf_engine), p->perm, p->N, 128 * p->R,
       1.0f / float(p->N), conj);
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;

@@ -86,15 +86,16 @@ def _check_inputs(u, k, mod, gates=()):
 
 
 def _kf_natural(mod, k):
-    """k (H, Lk) fp32 -> FFT_N(k) complex64, natural order (reference: conv.py:575)."""
-    return torch.fft.fft(k.to(torch.float32), n=mod.seqlen).contiguous()
+    """k (H, Lk) fp32 -> the N/2+1 non-redundant frequencies of FFT_N(k), complex64 (reference: conv.py:575 computes
+    the full complex FFT of the real filter; the second half is its Hermitian mirror and is rebuilt by the pack kernel)."""
+    return torch.fft.rfft(k.to(torch.float32), n=mod.seqlen).contiguous()
 
 
 def _pack_kf_from_natural(mod, plan, k_f, conj):
-    """natural-order k_f -> engine-order packed (H, N) 4-byte complex, scaled 1/N (replaces conv.py:640)."""
+    """rfft k_f -> engine-order packed (H, N) 4-byte complex, scaled 1/N (replaces conv.py:640)."""
     kf_engine = torch.empty((k_f.shape[0], mod.seqlen), dtype=torch.int32, device=k_f.device)
-    _lib.check(_lib.lib().bffc_kf_pack(plan.handle, _ptr(torch.view_as_real(k_f)), _ptr(kf_engine),
-                                       int(k_f.shape[0]), int(conj), _stream()))
+    _lib.check(_lib.lib().bffc_kf_pack_rfft(plan.handle, _ptr(torch.view_as_real(k_f)), _ptr(kf_engine),
+                                            int(k_f.shape[0]), int(conj), _stream()))
     return kf_engine
 
 

@@ -75,6 +75,10 @@ int bffc_plan_destroy(bffc_plan* plan);
  */
 int bffc_kf_pack(const bffc_plan* plan, const void* kf_natural, void* kf_engine, int H, int conj,
                  void* stream);
+/* Same as bffc_kf_pack, but kf_half holds only the N/2+1 non-redundant frequencies of the real filter
+ * (torch.fft.rfft(k, n=N), complex64); the other half is filled in by Hermitian symmetry. */
+int bffc_kf_pack_rfft(const bffc_plan* plan, const void* kf_half, void* kf_engine, int H, int conj,
+                      void* stream);
 int bffc_dkf_unpack(const bffc_plan* plan, const void* dkf_engine, void* dkf_natural, int H,
                     void* stream);
 
