@@ -27,6 +27,9 @@ import torch  # noqa: E402
 WORKLOADS = {
     # name: (N, B, H, L, gated)
     'c2': (8192, 16, 768, 8192, False),       # BASELINE.json configs[1]: M2-BERT dims, the metric's config
+    'c3': (32768, 8, 1024, 16384, True),      # configs[2]: Hyena-style, gated, implicit 2x causal padding
+    'c4': (1048576, 2, 128, 1048576, False),  # configs[3]: HyenaDNA long range (per GPU here; see config.sharding)
+    'c5': (4194304, 8, 8, 4194304, False),    # configs[4] per-GPU shard: B=8, H=64/8
 }
 
 
@@ -82,13 +85,18 @@ class ClockSampler(threading.Thread):
                 'power_w_max': max(float(s[2]) for s in inside if s[2].replace('.', '', 1).isdigit())}
 
 
+def sample_shape(N):
+    n = max(2, (1 << 21) // N)
+    return (4, n // 4) if n >= 8 else (2, n // 2)
+
+
 def cpu_baseline(N, L, gated, budget_s=12.0):
     """The reference's CPU path (oracle port of tests/test_flashfftconv.py:5-13) on the host cores,
     on a bounded sample of the same workload: S convolutions of the true N / L, all threads."""
     from oracle.fftconv_oracle import ref_fft_conv, ref_fft_conv_gated
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Bs, Hs = 4, 64                                    # 256 convolutions per call
+    Bs, Hs = sample_shape(N)                          # bounded sample: ~2M points per call
     g = torch.Generator().manual_seed(0)
     u = torch.randn(Bs, Hs, L, generator=g).to(torch.bfloat16)
     k = torch.randn(Hs, L, generator=g) / L ** 0.5
@@ -129,7 +137,7 @@ def run_reference(args):
     from oracle.fftconv_oracle import ref_fft_conv
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Bs, Hs = 4, 64
+    Bs, Hs = sample_shape(N)
     g = torch.Generator().manual_seed(0)
     u = torch.randn(Bs, Hs, L, generator=g).to(torch.bfloat16)
     k = torch.randn(Hs, L, generator=g) / L ** 0.5
@@ -165,6 +173,7 @@ def run_ours(args):
     plan = conv.plan(dev)
     u = torch.randn(B, H, L, device=dev).to(torch.bfloat16)
     k = torch.randn(H, L, device=dev) / L ** 0.5
+    gates = [torch.randn(B, H, L, device=dev).to(torch.bfloat16) for _ in range(2)] if gated else []
     convs_per_step = B * H
 
     def barrier():
@@ -183,7 +192,7 @@ def run_ours(args):
 
     # ---- (1) device-resident whole step through the public forward (k -> k_f -> fused conv)
     for _ in range(args.warmup):
-        y = conv(u, k)
+        y = conv(u, k, *gates)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -194,8 +203,8 @@ def run_ours(args):
     launches = 0
     e0.record()
     for _ in range(args.steps):
-        y = conv(u, k)
-        launches += 1 + _lib.lib().bffc_last_launch_count()          # kf_pack + fused conv (our kernels only)
+        y = conv(u, k, *gates)
+        launches += 1 + _lib.lib().bffc_last_launch_count()          # kf_pack + conv kernels (our kernels only)
     e1.record()
     barrier()
     step_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
@@ -203,9 +212,14 @@ def run_ours(args):
     # ---- (2) dominant kernel alone (k_f pre-packed), CUDA events on the launching stream -> roofline
     kf = _pack_kf(conv, plan, k, 0)
     yk = torch.empty_like(u)
+    ws_bytes = _lib.lib().bffc_workspace_bytes(plan.handle, B, H, L)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+    g0 = _ptr(gates[0]) if gated else None
+    g1 = _ptr(gates[1]) if gated else None
 
     def kern():
-        _lib.check(_lib.lib().bffc_fwd(plan.handle, _ptr(u), _ptr(kf), None, None, _ptr(yk), B, H, L, None, 0, _stream()))
+        _lib.check(_lib.lib().bffc_fwd(plan.handle, _ptr(u), _ptr(kf), g0, g1, _ptr(yk), B, H, L, _ptr(ws), ws_bytes,
+                                       _stream()))
     for _ in range(max(3, args.warmup)):
         kern()
     torch.cuda.synchronize()
@@ -229,10 +243,13 @@ def run_ours(args):
 
     # ---- (2b) forward + backward through autograd (du, dk), device resident
     ug = u.clone().requires_grad_(True); kg = k.clone().requires_grad_(True)
+    gg = [g.clone().requires_grad_(True) for g in gates]
     dout = torch.randn_like(u)
     def fb():
         ug.grad = None; kg.grad = None
-        conv(ug, kg).backward(dout)
+        for g in gg:
+            g.grad = None
+        conv(ug, kg, *gg).backward(dout)
     for _ in range(3):
         fb()
     barrier()
@@ -246,13 +263,17 @@ def run_ours(args):
 
     # ---- (3) end to end through the public API with HOST buffers (pinned), copies inside the timed region
     u_h = u.cpu().pin_memory(); k_h = k.cpu().pin_memory()
+    g_h = [g.cpu().pin_memory() for g in gates]
     y_h = torch.empty_like(u_h).pin_memory()
     u_d = torch.empty_like(u); k_d = torch.empty_like(k)
+    g_d = [torch.empty_like(g) for g in gates]
     e2e_steps = max(2, min(args.steps, 5))
 
     def e2e_step():
         u_d.copy_(u_h, non_blocking=True); k_d.copy_(k_h, non_blocking=True)
-        yy = conv(u_d, k_d)
+        for a, b in zip(g_d, g_h):
+            a.copy_(b, non_blocking=True)
+        yy = conv(u_d, k_d, *g_d)
         y_h.copy_(yy, non_blocking=True)
     e2e_step()
     barrier()
@@ -284,16 +305,20 @@ def run_ours(args):
         'metric': 'fftconv_fwd_convs_per_sec', 'value': convs_per_step * world / (step_ms * 1e-3), 'unit': 'convs/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_ms,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-        'config': {'workload': f'{args.workload}: FlashFFTConv({N}, bf16) fwd, B={B} H={H} L={L} ungated per GPU '
-                               f'(BASELINE.json configs[1]); step = k->k_f (torch.fft + bffc_kf_pack) + fused conv',
-                   'l2': 'inputs+outputs 403 MB per step exceed the 126 MB L2 (no flush needed)',
+        'config': {'workload': f'{args.workload}: FlashFFTConv({N}, bf16) fwd, B={B} H={H} L={L} '
+                               f'{"gated" if gated else "ungated"} per GPU (BASELINE.json configs); '
+                               f'step = k->k_f (torch.fft.rfft + bffc_kf_pack_rfft) + conv kernels',
+                   'l2': f'inputs+outputs {abytes / 1e6:.0f} MB per step exceed the 126 MB L2 (no flush needed)',
                    'sharding': 'B x H sharded over ranks, no data-path collective'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
-                     'traffic': traffic, 'kernel': 'bffc::r128::fwd_kernel', 'kernel_ms': kern_ms,
+                     'traffic': traffic,
+                     'kernel': 'bffc::r128::fwd_kernel' if N == 8192 else 'bffc_fwd native path (outer stages + bffc::r128::fwd_kernel)',
+                     'kernel_ms': kern_ms,
                      'algorithmic_bytes': abytes, 'peak_source': peak_src,
                      'kernel_convs_per_sec': convs_per_step / (kern_ms * 1e-3)},
         'e2e': {'value': convs_per_step * world / (e2e_ms * 1e-3), 'unit': 'convs/s',
-                'h2d_bytes_per_step': u_h.numel() * 2 + k_h.numel() * 4, 'd2h_bytes_per_step': y_h.numel() * 2,
+                'h2d_bytes_per_step': u_h.numel() * 2 * (3 if gated else 1) + k_h.numel() * 4,
+                'd2h_bytes_per_step': y_h.numel() * 2,
                 'ms_per_step': e2e_ms},
         'fwd_bwd': {'value': convs_per_step * world / (fb_ms * 1e-3), 'unit': 'convs/s', 'ms_per_step': fb_ms,
                     'note': 'autograd fwd+bwd (du, dk) through FlashFFTConv, inputs resident'},
