@@ -100,6 +100,46 @@ __global__ void kf_pack_kernel(const float* __restrict__ kf_nat, uint32_t* __res
   }
 }
 
+// Tiled variant for a large outermost radix R0 (tcgen05 outer stage, R0 = 128): consecutive c0 are adjacent in the
+// natural order, consecutive words are adjacent in the engine rows, so a (32 c0) x (32 word pairs) tile goes
+// through shared memory and both sides are accessed in 256-byte runs.
+// grid: (8192/2/32 word-pair tiles, R0/32 * R1, H)
+constexpr int kInnerWords = 8192;
+
+template <bool kHalf>
+__global__ void kf_pack_tiled_kernel(const float2* __restrict__ kf_nat, uint2* __restrict__ kf_eng, int N, int R0, int R1,
+                                     float scale, int conj) {
+  __shared__ uint2 tile[32][33];
+  const int h = blockIdx.z;
+  const int c0b = (blockIdx.y % (R0 / 32)) * 32, c1 = blockIdx.y / (R0 / 32);
+  const int wp0 = blockIdx.x * 32;
+  const int R = R0 * R1;
+  const float2* src = kf_nat + size_t(h) * (kHalf ? (N / 2 + 1) : N);
+  const int tx = threadIdx.x, ty = threadIdx.y;      // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int wp = wp0 + j;                            // word pair index inside the row: (cc*128 + k1)*2 + pp
+    const int pp = wp & 1, k1 = (wp >> 1) & 127, cc = wp >> 8;
+    const int kin = k1 + 128 * (4 * cc + 2 * pp);      // inner frequency of the first element
+    float2 v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      int k = (c0b + tx) + R0 * (c1 + R1 * (kin + 128 * e));
+      float sg = conj ? -1.f : 1.f;
+      if (kHalf && k > N / 2) { k = N - k; sg = -sg; }
+      float2 t = src[k];
+      v[e] = make_float2(t.x * scale, t.y * scale * sg);
+    }
+    __nv_bfloat162 re = __floats2bfloat162_rn(v[0].x, v[1].x), im = __floats2bfloat162_rn(v[0].y, v[1].y);
+    tile[tx][j] = make_uint2(*reinterpret_cast<uint32_t*>(&re), *reinterpret_cast<uint32_t*>(&im));
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {                   // j = c0 offset, tx = word pair
+    const size_t row = (size_t(h) * R0 + (c0b + j)) * R1 + c1;
+    kf_eng[row * (kInnerWords / 2) + wp0 + tx] = tile[j][tx];
+  }
+  (void)R;
+}
+
 constexpr int kInner = 8192;   // the fused tcgen05 kernel's size
 
 }  // namespace
@@ -241,6 +281,14 @@ int bffc_plan_destroy(bffc_plan* p) {
 
 int bffc_kf_pack(const bffc_plan* p, const void* kf_natural, void* kf_engine, int H, int conj, void* stream) {
   if (!p || !kf_natural || !kf_engine || H <= 0) return fail(BFFC_ERR_INVALID, "bffc_kf_pack: bad argument");
+  if (p->nlev >= 1 && p->lev[0].R >= 32) {
+    dim3 grid(kInner / 2 / 32, (p->lev[0].R / 32) * (p->nlev == 2 ? p->lev[1].R : 1), H);
+    kf_pack_tiled_kernel<false><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float2*>(kf_natural), static_cast<uint2*>(kf_engine), p->N, p->lev[0].R,
+        p->nlev == 2 ? p->lev[1].R : 1, 1.0f / float(p->N), conj);
+    CUDA_TRY(cudaGetLastError());
+    return BFFC_OK;
+  }
   dim3 grid(64, H);
   kf_pack_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float*>(kf_natural), static_cast<uint32_t*>(kf_engine), p->perm, p->N, 128 * p->R,
@@ -251,6 +299,14 @@ int bffc_kf_pack(const bffc_plan* p, const void* kf_natural, void* kf_engine, in
 
 int bffc_kf_pack_rfft(const bffc_plan* p, const void* kf_half, void* kf_engine, int H, int conj, void* stream) {
   if (!p || !kf_half || !kf_engine || H <= 0) return fail(BFFC_ERR_INVALID, "bffc_kf_pack_rfft: bad argument");
+  if (p->nlev >= 1 && p->lev[0].R >= 32) {
+    dim3 grid(kInner / 2 / 32, (p->lev[0].R / 32) * (p->nlev == 2 ? p->lev[1].R : 1), H);
+    kf_pack_tiled_kernel<true><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float2*>(kf_half), static_cast<uint2*>(kf_engine), p->N, p->lev[0].R,
+        p->nlev == 2 ? p->lev[1].R : 1, 1.0f / float(p->N), conj);
+    CUDA_TRY(cudaGetLastError());
+    return BFFC_OK;
+  }
   dim3 grid(64, H);
   kf_pack_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float*>(kf_half), static_cast<uint32_t*>(kf_engine), p->perm, p->N, 128 * p->R,

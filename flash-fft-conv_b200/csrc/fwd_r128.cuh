@@ -280,10 +280,6 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
         mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN, 1);
       for (int s = 0; s < p.ksteps; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN_NEG, 1);
       mma_commit(bar_mma);
-      if (unit + 1 < u_end) {      // prefetch next unit into the other slot (its last reader: TMA store)
-        tma_store_wait_read0();
-        issue_load(unit + 1, slot ^ 1);
-      }
       }
       __syncwarp();
     }
@@ -326,6 +322,13 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
         for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 8 * s, pair_desc(sG0 + s * 2048, 8192), ID_N128_MN, s > 0);
         for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 32 + 8 * s, pair_desc(sG0 + 16384 + s * 2048, 8192), ID_N128_MN, 1);
         mma_commit(bar_mma);
+        // prefetch the next unit into the other slot.  Its last reader was the previous unit's TMA store, issued
+        // a full stage-1 + pass-1 ago: waiting for it here (not before stage 1) keeps the issuing warp from
+        // arriving late at the pass-1 barrier (15 % barrier stall in profiles/r1_v21).
+        if (unit + 1 < u_end) {
+          tma_store_wait_read0();
+          issue_load(unit + 1, slot ^ 1);
+        }
       }
       __syncwarp();
     }

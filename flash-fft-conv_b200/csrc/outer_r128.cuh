@@ -31,8 +31,12 @@ struct OuterTcParams {
 
 namespace r128 {
 
-constexpr int kSmemOuter = kSmemData + kSmemBars + 1024;
-constexpr int kSmemOuterGated = kSmemOuter + kSmemGate + 1024;
+// ungated: a ring of three (re, im) tile slots per pipeline so the next unit's TMA load never waits for the
+// previous unit's TMA store; gated forward keeps two slots + one gate slot (shared-memory budget)
+constexpr int kOuterSlots = 3;
+constexpr int kSmemOuterData = 2 * kOuterSlots * kSlotBytes;
+constexpr int kSmemOuter = kSmemOuterData + kSmemBars + 1024;
+constexpr int kSmemOuterGated = kSmemOuterData + kSmemBars + 1024;   // gate slot = third ring slot
 
 template <bool kInverse>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -43,8 +47,7 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
                 const OuterTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t s_bars = sbase + kSmemData;
-  const uint32_t s_gate0 = s_bars + kSmemBars + 960;
+  const uint32_t s_bars = sbase + kSmemOuterData;
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
 
   const int tid = threadIdx.x;
@@ -54,9 +57,9 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
   const int warp_q = (tid >> 5) & 3;
   const bool lead_warp = ((tid & 255) < 32);
 
-  const uint32_t bar_tma0 = s_bars + pipe * 24;
-  const uint32_t bar_mma = s_bars + pipe * 24 + 16;
-  const uint32_t s_tmemptr = s_bars + 48;
+  const uint32_t bar_tma0 = s_bars + pipe * 32;       // three TMA barriers
+  const uint32_t bar_mma = s_bars + pipe * 32 + 24;   // one MMA barrier
+  const uint32_t s_tmemptr = s_bars + 64;
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_x);
@@ -66,6 +69,7 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
   if ((tid & 255) == 0) {
     mbar_init(bar_tma0, 1);
     mbar_init(bar_tma0 + 8, 1);
+    mbar_init(bar_tma0 + 16, 1);
     mbar_init(bar_mma, 1);
     fence_barrier_init();
   }
@@ -76,7 +80,7 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + kSmemData + 48);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + kSmemOuterData + 64);
   const uint32_t tlane = tmem_base + (uint32_t(warp_q * 32) << 16);
   {
     const uint4* row = reinterpret_cast<const uint4*>((pipe == 0 ? p.dftC : p.dftS) + lane * 128) + half * 8;
@@ -114,7 +118,7 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
   const int u_begin = int((long long)p.units * gp / GP);
   const int u_end = int((long long)p.units * (gp + 1) / GP);
 
-  const uint32_t s_slot0 = sbase + pipe * 2 * kSlotBytes;
+  const uint32_t s_slot0 = sbase + pipe * kOuterSlots * kSlotBytes;
   const uint32_t tD = tlane + colD(pipe);
   const uint32_t tD0 = tmem_base + colD(pipe);
   const uint32_t tC0 = tmem_base + kColC;
@@ -122,6 +126,8 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
   const uint32_t bar_id = 1 + pipe;
   const int BH = p.B * p.H;
   const bool gated_in = (!kInverse) && p.has_pregate;
+  const int nslots = gated_in ? 2 : kOuterSlots;
+  const uint32_t s_gate0 = s_slot0 + 2 * kSlotBytes;     // gated: the third ring slot holds the pregate tiles
 
   struct UnitIdx { int cj, h, pr; };
   auto decode = [&](int unit) {
@@ -143,7 +149,7 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
       tma_load_4d(dst, &tm_x, bar, 0, x.cj, 0, s0);
       tma_load_4d(dst + kTileBytes, &tm_x, bar, 0, x.cj, 0, s1);
       if (gated_in) {
-        const uint32_t gd = s_gate0 + pipe * kSlotBytes;
+        const uint32_t gd = s_gate0;
         tma_load_4d(gd, &tm_g, bar, 0, x.cj, 0, s0);
         tma_load_4d(gd + kTileBytes, &tm_g, bar, 0, x.cj, 0, s1);
       }
@@ -166,7 +172,8 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
   }
 
   for (int unit = u_begin, n = 0; unit < u_end; ++unit, ++n) {
-    const int slot = n & 1;
+    const int slot = n % nslots;
+    const uint32_t tma_par = uint32_t(n / nslots) & 1u;
     const uint32_t sX = s_slot0 + slot * kSlotBytes;
     const UnitIdx x = decode(unit);
     // chunk base twiddle W_N^{k0 * 64 * cj}
@@ -174,9 +181,9 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
     sincospif(-float((lane * 64 * x.cj) & (p.N - 1)) * invN2, &bs, &bc);
     const f32x2 bc2 = pk2(bc, bc), bs2 = pk2(bs, bs);
 
-    if (kInverse || gated_in) mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
+    if (kInverse || gated_in) mbar_wait(bar_tma0 + 8 * slot, tma_par);
     if (gated_in) {
-      const uint32_t sG = s_gate0 + pipe * kSlotBytes;
+      const uint32_t sG = s_gate0;
 #pragma unroll
       for (int part = 0; part < 2; ++part)
 #pragma unroll
@@ -215,7 +222,7 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
     }
     // ---------------- radix-128 MMA
     if (lead_warp) {
-      if (!(kInverse || gated_in)) mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
+      if (!(kInverse || gated_in)) mbar_wait(bar_tma0 + 8 * slot, tma_par);
       tc_fence_after();
       if (elect_one()) {
         const int ks = kInverse ? 8 : p.ksteps;
@@ -226,9 +233,10 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
         for (int s = 0; s < ks; ++s)
           mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), kInverse ? ID_N64_MN : ID_N64_MN_NEG, 1);
         mma_commit(bar_mma);
+        // next unit -> next ring slot (ungated: its last reader, a TMA store, was issued two units ago)
         if (unit + 1 < u_end) {
-          tma_store_wait_read0();
-          issue_load(unit + 1, slot ^ 1);
+          if (nslots == 3) tma_store_wait_read1(); else tma_store_wait_read0();
+          issue_load(unit + 1, (n + 1) % nslots);
         }
       }
       __syncwarp();
