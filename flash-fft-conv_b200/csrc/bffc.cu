@@ -106,6 +106,36 @@ __global__ void kf_pack_kernel(const float* __restrict__ kf_nat, uint32_t* __res
 // grid: (8192/2/32 word-pair tiles, R0/32 * R1, H)
 constexpr int kInnerWords = 8192;
 
+// small sizes: y[n] = t[n] + t[n + off] (* postgate), n < L; t rows have Lt elements.  8 elements per thread.
+__global__ void fold_kernel(const uint4* __restrict__ t, const uint4* __restrict__ postgate, uint4* __restrict__ y,
+                            int L, int Lt, int off, size_t rows) {
+  const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int per = L / 8;
+  if (idx >= rows * per) return;
+  const size_t r = idx / per;
+  const int v = int(idx - r * per);
+  const uint4 a = t[r * (Lt / 8) + v], b = t[r * (Lt / 8) + v + off / 8];
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float lo = __uint_as_float(aw[i] << 16) + __uint_as_float(bw[i] << 16);
+    const float hi = __uint_as_float(aw[i] & 0xffff0000u) + __uint_as_float(bw[i] & 0xffff0000u);
+    __nv_bfloat162 v2 = __floats2bfloat162_rn(lo, hi);
+    o[i] = *reinterpret_cast<uint32_t*>(&v2);
+  }
+  if (postgate) {
+    const uint4 g = postgate[r * per + v];
+    const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 r2 = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&o[i]), *reinterpret_cast<const __nv_bfloat162*>(&gw[i]));
+      o[i] = *reinterpret_cast<uint32_t*>(&r2);
+    }
+  }
+  y[r * per + v] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 template <bool kHalf>
 __global__ void kf_pack_tiled_kernel(const float2* __restrict__ kf_nat, uint2* __restrict__ kf_eng, int N, int R0, int R1,
                                      float scale, int conj) {
@@ -147,6 +177,8 @@ constexpr int kInner = 8192;   // the fused tcgen05 kernel's size
 struct bffc_level { int tc; int R; };   // tc = 1: tcgen05 radix-128 stage (outer_r128.cuh); 0: CUDA-core radix 2/4/8
 
 struct bffc_plan {
+  int NE;        // engine FFT size: N for N >= 8192; 8192 for the small sizes (256..4096), which run as a linear
+                 // convolution inside the 8192-point kernel followed by a fold  y[n] = t[n] + t[n + N]
   int N;
   int R;         // N = R * 8192: product of the outer radices around the fused 8192-point kernel
   int nlev;      // number of outer levels (0, 1 or 2), outermost first
@@ -168,6 +200,7 @@ int bffc_last_launch_count(void) { return g_launches; }
 
 static int levels_for(int N, bffc_level* lev) {
   switch (N) {
+    case 256: case 512: case 1024: case 2048: case 4096: return 0;
     case 8192: return 0;
     case 16384: lev[0] = {0, 2}; return 1;
     case 32768: lev[0] = {0, 4}; return 1;
@@ -199,7 +232,8 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
 
   bffc_plan* p = new bffc_plan();
   p->N = seqlen;
-  p->R = seqlen / kInner;
+  p->NE = seqlen < kInner ? kInner : seqlen;
+  p->R = p->NE / kInner;
   p->nlev = levels_for(seqlen, p->lev);
   p->dtype = dtype;
   CUDA_TRY(cudaGetDevice(&p->device));
@@ -242,7 +276,7 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   //   k'' = k1 + 128*k2 with k2 = 4cc + 2pp and k2 + 1; natural frequency k = c0 + R0*(c1 + R1*k'').
   // perm[row*8192 + w] = 2 * (natural index of the first element) + part; the second element is 128*R further.
   const int R0 = p->nlev >= 1 ? p->lev[0].R : 1, R1 = p->nlev >= 2 ? p->lev[1].R : 1;
-  std::vector<int> perm(seqlen);
+  std::vector<int> perm(p->NE);
   for (int c0 = 0; c0 < R0; ++c0)
     for (int c1 = 0; c1 < R1; ++c1)
       for (int cc = 0; cc < 16; ++cc)
@@ -269,6 +303,8 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   return BFFC_OK;
 }
 
+int bffc_fft_size(const bffc_plan* p) { return p ? p->NE : 0; }
+
 int bffc_plan_destroy(bffc_plan* p) {
   if (!p) return BFFC_OK;
   cudaFree(p->dftC);
@@ -284,15 +320,15 @@ int bffc_kf_pack(const bffc_plan* p, const void* kf_natural, void* kf_engine, in
   if (p->nlev >= 1 && p->lev[0].R >= 32) {
     dim3 grid(kInner / 2 / 32, (p->lev[0].R / 32) * (p->nlev == 2 ? p->lev[1].R : 1), H);
     kf_pack_tiled_kernel<false><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const float2*>(kf_natural), static_cast<uint2*>(kf_engine), p->N, p->lev[0].R,
-        p->nlev == 2 ? p->lev[1].R : 1, 1.0f / float(p->N), conj);
+        static_cast<const float2*>(kf_natural), static_cast<uint2*>(kf_engine), p->NE, p->lev[0].R,
+        p->nlev == 2 ? p->lev[1].R : 1, 1.0f / float(p->NE), conj);
     CUDA_TRY(cudaGetLastError());
     return BFFC_OK;
   }
   dim3 grid(64, H);
   kf_pack_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float*>(kf_natural), static_cast<uint32_t*>(kf_engine), p->perm, p->N, 128 * p->R,
-      1.0f / float(p->N), conj);
+      static_cast<const float*>(kf_natural), static_cast<uint32_t*>(kf_engine), p->perm, p->NE, 128 * p->R,
+      1.0f / float(p->NE), conj);
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -302,15 +338,15 @@ int bffc_kf_pack_rfft(const bffc_plan* p, const void* kf_half, void* kf_engine, 
   if (p->nlev >= 1 && p->lev[0].R >= 32) {
     dim3 grid(kInner / 2 / 32, (p->lev[0].R / 32) * (p->nlev == 2 ? p->lev[1].R : 1), H);
     kf_pack_tiled_kernel<true><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const float2*>(kf_half), static_cast<uint2*>(kf_engine), p->N, p->lev[0].R,
-        p->nlev == 2 ? p->lev[1].R : 1, 1.0f / float(p->N), conj);
+        static_cast<const float2*>(kf_half), static_cast<uint2*>(kf_engine), p->NE, p->lev[0].R,
+        p->nlev == 2 ? p->lev[1].R : 1, 1.0f / float(p->NE), conj);
     CUDA_TRY(cudaGetLastError());
     return BFFC_OK;
   }
   dim3 grid(64, H);
   kf_pack_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float*>(kf_half), static_cast<uint32_t*>(kf_engine), p->perm, p->N, 128 * p->R,
-      1.0f / float(p->N), conj);
+      static_cast<const float*>(kf_half), static_cast<uint32_t*>(kf_engine), p->perm, p->NE, 128 * p->R,
+      1.0f / float(p->NE), conj);
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -319,7 +355,7 @@ int bffc_dkf_unpack(const bffc_plan* p, const void* dkf_engine, void* dkf_natura
   if (!p || !dkf_engine || !dkf_natural || H <= 0) return fail(BFFC_ERR_INVALID, "bffc_dkf_unpack: bad argument");
   dim3 grid(64, H);
   bffc::r128::dkf_unpack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float2*>(dkf_engine), static_cast<float2*>(dkf_natural), p->N,
+      static_cast<const float2*>(dkf_engine), static_cast<float2*>(dkf_natural), p->NE,
       p->nlev >= 1 ? p->lev[0].R : 1, p->nlev >= 2 ? p->lev[1].R : 1);
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
@@ -332,7 +368,9 @@ static size_t plane_bytes(const bffc_plan* p, int B, int H) { return size_t((B +
 
 extern "C" size_t bffc_workspace_bytes(const bffc_plan* p, int B, int H, int L) {
   (void)L;
-  if (!p || p->nlev == 0) return 0;
+  if (!p) return 0;
+  if (p->N < kInner) return size_t(B) * H * kInner * 2;     // small sizes: one (B, H, 8192) bf16 scratch
+  if (p->nlev == 0) return 0;
   // plane sets (real + imaginary plane each): forward nlev sets; backward nlev + 1 (transformed u and dout)
   return size_t(2 * (p->nlev + 1)) * plane_bytes(p, B, H);
 }
@@ -364,11 +402,13 @@ static void fill_params(const bffc_plan* p, bffc::FwdParams& prm, const void* kf
 
 // fused 8192-point kernel on (B, H, L) real sequences
 static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const void* pregate, const void* postgate,
-                        void* y, int B, int H, int L, float* dbg, int dbg_stages, int max_units, cudaStream_t st) {
-  if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen 8192 in this build", L);
+                        void* y, int B, int H, int L, float* dbg, int dbg_stages, int max_units, cudaStream_t st,
+                        int L_out = 0) {
+  if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen <= 8192 in this build", L);
+  if (L_out == 0) L_out = L;
   CUtensorMap tm_u, tm_y, tm_g;
   if (int rc = make_map(&tm_u, u, B * H, L)) return rc;
-  if (int rc = make_map(&tm_y, y, B * H, L)) return rc;
+  if (int rc = make_map(&tm_y, y, B * H, L_out)) return rc;
   if (int rc = make_map(&tm_g, pregate ? pregate : u, B * H, L)) return rc;
   bffc::FwdParams prm;
   fill_params(p, prm, kf);
@@ -564,7 +604,21 @@ static int check_common(const bffc_plan* p, int B, int H, int L, const void* a, 
 
 // y = postgate * conv(u * pregate, k) for any supported size.  `ws`: workspace (plane sets 0 and 1) for composite sizes.
 static int conv_forward(const bffc_plan* p, const void* u, const void* kf, const void* pregate, const void* postgate,
-                        void* y, int B, int H, int L, void* ws, cudaStream_t st, int* launches) {
+                        void* y, int B, int H, int L, void* ws, cudaStream_t st, int* launches, int corr = 0) {
+  if (p->N < kInner) {
+    // small sizes (reference: the 2-stage / r2r kernels for 256..2048 and 16_16_16 for 4096, conv.py:78-131): zero-padded
+    // operands make the 8192-point circular result a LINEAR (corr = 0) convolution or correlation (corr = 1, du path)
+    // of support < 2N; folding it modulo N gives the N-point circular result.
+    const int Lt = corr ? kInner : 2 * p->N;
+    const int off = corr ? kInner - p->N : p->N;
+    if (int rc = launch_fused(p, u, kf, pregate, nullptr, ws, B, H, L, nullptr, 0, 0, st, Lt)) return rc;
+    const size_t rows = size_t(B) * H, total = rows * (L / 8);
+    fold_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(ws), static_cast<const uint4*>(postgate),
+                                                               static_cast<uint4*>(y), L, Lt, off, rows);
+    CUDA_TRY(cudaGetLastError());
+    *launches += 2;
+    return BFFC_OK;
+  }
   if (p->nlev == 0) {
     *launches += 1;
     return launch_fused(p, u, kf, pregate, postgate, y, B, H, L, nullptr, 0, 0, st);
@@ -587,7 +641,10 @@ int bffc_fwd(const bffc_plan* p, const void* u, const void* kf, const void* preg
   if (int rc = check_common(p, B, H, L, u, y, kf)) return rc;
   if ((reinterpret_cast<uintptr_t>(pregate) | reinterpret_cast<uintptr_t>(postgate) | reinterpret_cast<uintptr_t>(workspace)) & 15)
     return fail(BFFC_ERR_INVALID, "bffc_fwd: gates / workspace must be 16-byte aligned");
-  if (p->nlev > 0 && (!workspace || workspace_bytes < size_t(2 * p->nlev) * plane_bytes(p, B, H)))
+  if (p->N < kInner) {
+    if (!workspace || workspace_bytes < bffc_workspace_bytes(p, B, H, L))
+      return fail(BFFC_ERR_INVALID, "bffc_fwd: workspace of %zu bytes required", bffc_workspace_bytes(p, B, H, L));
+  } else if (p->nlev > 0 && (!workspace || workspace_bytes < size_t(2 * p->nlev) * plane_bytes(p, B, H)))
     return fail(BFFC_ERR_INVALID, "bffc_fwd: workspace of %zu bytes required", size_t(2 * p->nlev) * plane_bytes(p, B, H));
   int launches = 0;
   int rc = conv_forward(p, u, kf, pregate, postgate, y, B, H, L, workspace, static_cast<cudaStream_t>(stream), &launches);
@@ -609,21 +666,21 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
   if (int rc = check_common(p, B, H, L, u, du, dout)) return rc;
   if ((reinterpret_cast<uintptr_t>(dkf) | reinterpret_cast<uintptr_t>(kf_conj) | reinterpret_cast<uintptr_t>(workspace)) & 15)
     return fail(BFFC_ERR_INVALID, "bffc_bwd: dkf / kf / workspace must be 16-byte aligned");
-  if (p->nlev > 0 && (!workspace || workspace_bytes < bffc_workspace_bytes(p, B, H, L)))
+  if ((p->nlev > 0 || p->N < kInner) && (!workspace || workspace_bytes < bffc_workspace_bytes(p, B, H, L)))
     return fail(BFFC_ERR_INVALID, "bffc_bwd: workspace of %zu bytes required", bffc_workspace_bytes(p, B, H, L));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int launches = 0;
   // du = corr(dout, k) = circular conv with conj(k_f): the forward path on dout
   // (reference: kernels_bf16/monarch_cuda_32_16_16_bwd_kernel_bf16.h:740-815)
   if (!gated) {
-    if (int rc = conv_forward(p, dout, kf_conj, nullptr, nullptr, du, B, H, L, workspace, st, &launches)) return rc;
+    if (int rc = conv_forward(p, dout, kf_conj, nullptr, nullptr, du, B, H, L, workspace, st, &launches, 1)) return rc;
   } else {
     // y = q * conv(u*p, k)  (conv.py:3856-3939; kernels_bf16/..._bwd_kernel_bf16.h:836-906; host recompute
     // monarch_cuda_interface_bwd_bf16.cu:798-808).  With dx = corr(dout*q, k):
     //   dpostgate = dout * conv(u*p, k),  du = p * dx,  dpregate = u * dx     — three passes of the forward path
     if (int rc = conv_forward(p, u, kf, pregate, dout, dpostgate, B, H, L, workspace, st, &launches)) return rc;
-    if (int rc = conv_forward(p, dout, kf_conj, postgate, pregate, du, B, H, L, workspace, st, &launches)) return rc;
-    if (int rc = conv_forward(p, dout, kf_conj, postgate, u, dpregate, B, H, L, workspace, st, &launches)) return rc;
+    if (int rc = conv_forward(p, dout, kf_conj, postgate, pregate, du, B, H, L, workspace, st, &launches, 1)) return rc;
+    if (int rc = conv_forward(p, dout, kf_conj, postgate, u, dpregate, B, H, L, workspace, st, &launches, 1)) return rc;
   }
   // dk_f = sum_b FFT(dout*q) * conj(FFT(u*p))
   const int pairs = (B + 1) / 2;

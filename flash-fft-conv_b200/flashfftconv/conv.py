@@ -60,6 +60,10 @@ class FlashFFTConv(torch.nn.Module):
             self._plans[key] = _Plan(self.seqlen, self.dtype, device)
         return self._plans[key]
 
+    def fft_size(self, device):
+        """FFT size of the engine: seqlen, or 8192 for the small sizes (computed as a folded linear convolution)."""
+        return _lib.lib().bffc_fft_size(self.plan(device).handle)
+
     def forward(self, u, k, pregate=None, postgate=None):
         if pregate is not None or postgate is not None:
             assert pregate is not None and postgate is not None       # conv.py:557-558
@@ -88,12 +92,12 @@ def _check_inputs(u, k, mod, gates=()):
 def _kf_natural(mod, k):
     """k (H, Lk) fp32 -> the N/2+1 non-redundant frequencies of FFT_N(k), complex64 (reference: conv.py:575 computes
     the full complex FFT of the real filter; the second half is its Hermitian mirror and is rebuilt by the pack kernel)."""
-    return torch.fft.rfft(k.to(torch.float32), n=mod.seqlen).contiguous()
+    return torch.fft.rfft(k.to(torch.float32), n=mod.fft_size(k.device)).contiguous()
 
 
 def _pack_kf_from_natural(mod, plan, k_f, conj):
     """rfft k_f -> engine-order packed (H, N) 4-byte complex, scaled 1/N (replaces conv.py:640)."""
-    kf_engine = torch.empty((k_f.shape[0], mod.seqlen), dtype=torch.int32, device=k_f.device)
+    kf_engine = torch.empty((k_f.shape[0], mod.fft_size(k_f.device)), dtype=torch.int32, device=k_f.device)
     _lib.check(_lib.lib().bffc_kf_pack_rfft(plan.handle, _ptr(torch.view_as_real(k_f)), _ptr(kf_engine),
                                             int(k_f.shape[0]), int(conj), _stream()))
     return kf_engine
@@ -120,7 +124,7 @@ def _fwd(mod, u, k, pregate, postgate):
 def _bwd(mod, dout, u, k_f, k_len, pregate, postgate):
     """du, dk[, dpregate, dpostgate] — reference: FlashFFTConvFunc.backward, conv.py:1737-1822."""
     B, H, L = u.shape
-    N = mod.seqlen
+    N = mod.fft_size(u.device)
     plan = mod.plan(u.device)
     dout = dout.contiguous()                                          # conv.py:1742
     with torch.cuda.device(u.device):
@@ -139,7 +143,10 @@ def _bwd(mod, dout, u, k_f, k_len, pregate, postgate):
         _lib.check(_lib.lib().bffc_dkf_unpack(plan.handle, _ptr(dkf_engine), _ptr(torch.view_as_real(dkf_nat)), H,
                                               _stream()))
         # the kernel accumulates unnormalised spectra; ifft's 1/N completes the correlation (conv.py:1817-1820)
-        dk = torch.fft.ifft(dkf_nat, dim=-1).real[..., :k_len].contiguous()
+        c = torch.fft.ifft(dkf_nat, dim=-1).real
+        if N != mod.seqlen:        # small sizes: fold the linear correlation (lags -seqlen..seqlen) modulo seqlen
+            c = c[..., : mod.seqlen] + c[..., N - mod.seqlen:]
+        dk = c[..., :k_len].contiguous()
     return du, dk, dpre, dpost
 
 

@@ -61,6 +61,9 @@ int bffc_supported(int seqlen, int dtype);
  */
 int bffc_plan_create(bffc_plan** plan, int seqlen, int dtype);
 int bffc_plan_destroy(bffc_plan* plan);
+/* FFT size n the caller must use for k_f = rfft(k, n) / for the inverse FFT of dk_f: seqlen for seqlen >= 8192;
+ * 8192 for the small sizes (256..4096), whose dk then is dk[i] = c[i] + c[8192 - seqlen + i], c = ifft(dk_f).real */
+int bffc_fft_size(const bffc_plan* plan);
 
 /*
  * Frequency-domain filter layout.  The engine consumes k_f = FFT_N(k)/N as packed complex

@@ -251,3 +251,39 @@ def test_bwd_long_vs_oracle(ffc, N, B, H, L):
     du_ref, dk_ref = orc.ref_grads(d['u'], d['k'], d['dout'], N)
     _check(u.grad, du_ref, f'du N={N}')
     _check(k.grad, dk_ref, f'dk N={N}')
+
+
+# ----------------------------------------------------------------------------- small sizes (folded linear convolution in the 8192 kernel)
+@pytest.mark.parametrize('N,B,H,L', [(256, 2, 3, 256), (256, 3, 2, 128), (512, 2, 2, 512), (1024, 2, 16, 1024),
+                                     (2048, 1, 3, 1024), (4096, 4, 5, 4096), (4096, 2, 2, 2048)])
+def test_fwd_small_vs_oracle(ffc, N, B, H, L):
+    d = orc.make_inputs(B, H, N, L, torch.bfloat16, seed=N + B, unit_scale=True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    y = conv(d['u'].cuda(), d['k'].cuda())
+    _check(y, orc.ref_fft_conv(d['u'], d['k'], N), f'fwd N={N} B={B} H={H} L={L}')
+
+
+@pytest.mark.parametrize('name', ['n256_bf16', 'n4096_bf16_pad'])
+def test_fwd_small_golden(ffc, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f'conv_{name}.npz'))
+    N = int(g['N'])
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    y = conv(torch.from_numpy(g['u']).to(torch.bfloat16).cuda(), torch.from_numpy(g['k']).cuda())
+    assert torch.allclose(y.cpu().float(), torch.from_numpy(g['y']), atol=1e-2)
+    _check(y, torch.from_numpy(g['y']), name)
+
+
+@pytest.mark.parametrize('N,B,H,L,gated', [(1024, 2, 4, 1024, False), (4096, 3, 2, 2048, False), (512, 2, 2, 512, True)])
+def test_bwd_small_vs_oracle(ffc, N, B, H, L, gated):
+    d = orc.make_inputs(B, H, N, L, torch.bfloat16, seed=51 + B, gated=gated, unit_scale=True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    u = d['u'].cuda().requires_grad_(True)
+    k = d['k'].cuda().requires_grad_(True)
+    gl = [d[n].cuda().requires_grad_(True) for n in ('pregate', 'postgate')] if gated else []
+    conv(u, k, *gl).backward(d['dout'].cuda())
+    refs = orc.ref_grads(d['u'], d['k'], d['dout'], N, *([d['pregate'], d['postgate']] if gated else []))
+    _check(u.grad, refs[0], f'du N={N}')
+    _check(k.grad, refs[1], f'dk N={N}')
+    if gated:
+        _check(gl[0].grad, refs[2], 'dpregate')
+        _check(gl[1].grad, refs[3], 'dpostgate')
