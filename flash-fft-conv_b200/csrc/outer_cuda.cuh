@@ -61,7 +61,7 @@ DEVINL void wr(int R, int e, float& c, float& s) {   // exp(-2 pi i e / R)
 
 // forward: grid (M / (kVec*blockDim.x), H, pairs)   [kPlanes: (rows, M / (kVec*blockDim.x), 1)]
 template <int R, bool kGated, bool kPlanes>
-__global__ void __launch_bounds__(128) fwd_kernel(const OuterParams p) {
+__global__ void __launch_bounds__(128, (R <= 4) ? 4 : 2) fwd_kernel(const OuterParams p) {
   const int kM = p.M;
   const int np = ((kPlanes ? blockIdx.y : blockIdx.x) * blockDim.x + threadIdx.x) * kVec;   // n'
   const int h = blockIdx.y, pr = blockIdx.z;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(128) fwd_kernel(const OuterParams p) {
 
 // inverse: same grid
 template <int R, bool kGated, bool kPlanes>
-__global__ void __launch_bounds__(128) inv_kernel(const OuterParams p) {
+__global__ void __launch_bounds__(128, (R <= 4) ? 4 : 2) inv_kernel(const OuterParams p) {
   const int kM = p.M;
   const int np = ((kPlanes ? blockIdx.y : blockIdx.x) * blockDim.x + threadIdx.x) * kVec;
   const int h = blockIdx.y, pr = blockIdx.z;
