@@ -70,6 +70,21 @@ int check_device() {
   return 0;
 }
 
+#define FMT_SWITCH(dtype_, ...)                         \
+  do {                                                   \
+    if ((dtype_) == BFFC_DTYPE_BF16) { constexpr int F = 1; __VA_ARGS__ } \
+    else { constexpr int F = 0; __VA_ARGS__ }            \
+  } while (0)
+
+uint16_t f2bf(double x);
+uint16_t f2h16(double x, int dtype) {   // table entry in the plan's element type
+  if (dtype == BFFC_DTYPE_BF16) return f2bf(x);
+  __half h = __float2half_rn(static_cast<float>(x));
+  uint16_t b;
+  memcpy(&b, &h, 2);
+  return b;
+}
+
 uint16_t f2bf(double x) {  // round-to-nearest-even float -> bf16 bits
   float f = static_cast<float>(x);
   uint32_t u;
@@ -79,7 +94,7 @@ uint16_t f2bf(double x) {  // round-to-nearest-even float -> bf16 bits
 }
 
 // kHalf: the source holds only frequencies 0..N/2 of a real filter (torch.fft.rfft); k > N/2 is conj(src[N-k]).
-template <bool kHalf>
+template <bool kHalf, int kFmt>
 __global__ void kf_pack_kernel(const float* __restrict__ kf_nat, uint32_t* __restrict__ kf_eng,
                                const int* __restrict__ perm, int N, int pair_stride, float scale, int conj) {
   const int h = blockIdx.y;
@@ -95,8 +110,7 @@ __global__ void kf_pack_kernel(const float* __restrict__ kf_nat, uint32_t* __res
       if (kHalf && k > N / 2) { k = N - k; if (part) sc = -sc; }
       v2[e] = src[2 * k + part] * sc;
     }
-    __nv_bfloat162 v = __floats2bfloat162_rn(v2[0], v2[1]);
-    kf_eng[size_t(h) * N + w] = *reinterpret_cast<uint32_t*>(&v);
+    kf_eng[size_t(h) * N + w] = bffc::Num<kFmt>::pack(v2[0], v2[1]);
   }
 }
 
@@ -107,6 +121,7 @@ __global__ void kf_pack_kernel(const float* __restrict__ kf_nat, uint32_t* __res
 constexpr int kInnerWords = 8192;
 
 // small sizes: y[n] = t[n] + t[n + off] (* postgate), n < L; t rows have Lt elements.  8 elements per thread.
+template <int kFmt>
 __global__ void fold_kernel(const uint4* __restrict__ t, const uint4* __restrict__ postgate, uint4* __restrict__ y,
                             int L, int Lt, int off, size_t rows) {
   const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -119,24 +134,21 @@ __global__ void fold_kernel(const uint4* __restrict__ t, const uint4* __restrict
   uint32_t o[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float lo = __uint_as_float(aw[i] << 16) + __uint_as_float(bw[i] << 16);
-    const float hi = __uint_as_float(aw[i] & 0xffff0000u) + __uint_as_float(bw[i] & 0xffff0000u);
-    __nv_bfloat162 v2 = __floats2bfloat162_rn(lo, hi);
-    o[i] = *reinterpret_cast<uint32_t*>(&v2);
+    float a0, a1, b0, b1;
+    bffc::upk2(bffc::Num<kFmt>::unpack(aw[i]), a0, a1);
+    bffc::upk2(bffc::Num<kFmt>::unpack(bw[i]), b0, b1);
+    o[i] = bffc::Num<kFmt>::pack(a0 + b0, a1 + b1);
   }
   if (postgate) {
     const uint4 g = postgate[r * per + v];
     const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __nv_bfloat162 r2 = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&o[i]), *reinterpret_cast<const __nv_bfloat162*>(&gw[i]));
-      o[i] = *reinterpret_cast<uint32_t*>(&r2);
-    }
+    for (int i = 0; i < 4; ++i) o[i] = bffc::Num<kFmt>::hmul2(o[i], gw[i]);
   }
   y[r * per + v] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-template <bool kHalf>
+template <bool kHalf, int kFmt>
 __global__ void kf_pack_tiled_kernel(const float2* __restrict__ kf_nat, uint2* __restrict__ kf_eng, int N, int R0, int R1,
                                      float scale, int conj) {
   __shared__ uint2 tile[32][33];
@@ -159,8 +171,7 @@ __global__ void kf_pack_tiled_kernel(const float2* __restrict__ kf_nat, uint2* _
       float2 t = src[k];
       v[e] = make_float2(t.x * scale, t.y * scale * sg);
     }
-    __nv_bfloat162 re = __floats2bfloat162_rn(v[0].x, v[1].x), im = __floats2bfloat162_rn(v[0].y, v[1].y);
-    tile[tx][j] = make_uint2(*reinterpret_cast<uint32_t*>(&re), *reinterpret_cast<uint32_t*>(&im));
+    tile[tx][j] = make_uint2(bffc::Num<kFmt>::pack(v[0].x, v[1].x), bffc::Num<kFmt>::pack(v[0].y, v[1].y));
   }
   __syncthreads();
   for (int j = ty; j < 32; j += 8) {                   // j = c0 offset, tx = word pair
@@ -216,7 +227,7 @@ static int levels_for(int N, bffc_level* lev) {
 }
 
 int bffc_supported(int seqlen, int dtype) {
-  if (dtype != BFFC_DTYPE_BF16) return 0;
+  if (dtype != BFFC_DTYPE_BF16 && dtype != BFFC_DTYPE_FP16) return 0;
   bffc_level lev[2];
   return levels_for(seqlen, lev) >= 0 ? 1 : 0;
 }
@@ -245,8 +256,8 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   for (int m = 0; m < 128; ++m)
     for (int k = 0; k < 128; ++k) {
       const double ang = 2.0 * PI * double((m * k) & 127) / 128.0;
-      c[m * 128 + k] = f2bf(cos(ang));
-      s[m * 128 + k] = f2bf(sin(ang));
+      c[m * 128 + k] = f2h16(cos(ang), dtype);
+      s[m * 128 + k] = f2h16(sin(ang), dtype);
     }
   CUDA_TRY(cudaMalloc(&p->dftC, c.size() * 2));
   CUDA_TRY(cudaMalloc(&p->dftS, s.size() * 2));
@@ -260,7 +271,7 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   for (int k = 0; k < 64; ++k)
     for (int n = 0; n < 64; ++n) {
       const double ang = -2.0 * PI * double((k * n) & 63) / 64.0;
-      const uint16_t gr = f2bf(cos(ang)), gi = f2bf(sin(ang)), ngi = f2bf(-sin(ang));
+      const uint16_t gr = f2h16(cos(ang), dtype), gi = f2h16(sin(ang), dtype), ngi = f2h16(-sin(ang), dtype);
       const size_t off = size_t(k) * 128 + (size_t((n >> 3) ^ (k & 7)) << 4) + size_t(n & 7) * 2;
       const size_t T = bffc::r128::kGTileBytes;
       memcpy(gt.data() + off, &gr, 2);
@@ -289,21 +300,28 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   CUDA_TRY(cudaMemcpy(p->perm, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice));
 
   using namespace bffc::r128;
-  CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-  CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-  CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                kSmemTotalGated));
-  CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-  CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf));
-  CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf));
-  CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkfGated));
-  CUDA_TRY(cudaFuncSetAttribute(outer_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOuterGated));
-  CUDA_TRY(cudaFuncSetAttribute(outer_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOuter));
+  FMT_SWITCH(dtype,
+    CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<false, false, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<true, false, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<false, true, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalGated));
+    CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<false, false, true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf));
+    CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkfGated));
+    CUDA_TRY(cudaFuncSetAttribute(outer_tc_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOuterGated));
+    CUDA_TRY(cudaFuncSetAttribute(outer_tc_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOuter));
+  );
   *out = p;
   return BFFC_OK;
 }
 
 int bffc_fft_size(const bffc_plan* p) { return p ? p->NE : 0; }
+
+int bffc_length_multiple(const bffc_plan* p) {
+  if (!p) return 0;
+  if (p->nlev == 0) return 64;                       // fused kernel: TMA tiles of 64 columns
+  if (p->lev[0].tc) return p->N / 128;               // tcgen05 outer stage: whole rows of the [128][N/128] view
+  return 8;                                          // CUDA-core outer stage: 16-byte vectors
+}
 
 int bffc_plan_destroy(bffc_plan* p) {
   if (!p) return BFFC_OK;
@@ -319,16 +337,16 @@ int bffc_kf_pack(const bffc_plan* p, const void* kf_natural, void* kf_engine, in
   if (!p || !kf_natural || !kf_engine || H <= 0) return fail(BFFC_ERR_INVALID, "bffc_kf_pack: bad argument");
   if (p->nlev >= 1 && p->lev[0].R >= 32) {
     dim3 grid(kInner / 2 / 32, (p->lev[0].R / 32) * (p->nlev == 2 ? p->lev[1].R : 1), H);
-    kf_pack_tiled_kernel<false><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+    FMT_SWITCH(p->dtype, (kf_pack_tiled_kernel<false, F><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const float2*>(kf_natural), static_cast<uint2*>(kf_engine), p->NE, p->lev[0].R,
-        p->nlev == 2 ? p->lev[1].R : 1, 1.0f / float(p->NE), conj);
+        p->nlev == 2 ? p->lev[1].R : 1, 1.0f / float(p->NE), conj)););
     CUDA_TRY(cudaGetLastError());
     return BFFC_OK;
   }
   dim3 grid(64, H);
-  kf_pack_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FMT_SWITCH(p->dtype, (kf_pack_kernel<false, F><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float*>(kf_natural), static_cast<uint32_t*>(kf_engine), p->perm, p->NE, 128 * p->R,
-      1.0f / float(p->NE), conj);
+      1.0f / float(p->NE), conj)););
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -337,16 +355,16 @@ int bffc_kf_pack_rfft(const bffc_plan* p, const void* kf_half, void* kf_engine, 
   if (!p || !kf_half || !kf_engine || H <= 0) return fail(BFFC_ERR_INVALID, "bffc_kf_pack_rfft: bad argument");
   if (p->nlev >= 1 && p->lev[0].R >= 32) {
     dim3 grid(kInner / 2 / 32, (p->lev[0].R / 32) * (p->nlev == 2 ? p->lev[1].R : 1), H);
-    kf_pack_tiled_kernel<true><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+    FMT_SWITCH(p->dtype, (kf_pack_tiled_kernel<true, F><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const float2*>(kf_half), static_cast<uint2*>(kf_engine), p->NE, p->lev[0].R,
-        p->nlev == 2 ? p->lev[1].R : 1, 1.0f / float(p->NE), conj);
+        p->nlev == 2 ? p->lev[1].R : 1, 1.0f / float(p->NE), conj)););
     CUDA_TRY(cudaGetLastError());
     return BFFC_OK;
   }
   dim3 grid(64, H);
-  kf_pack_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FMT_SWITCH(p->dtype, (kf_pack_kernel<true, F><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float*>(kf_half), static_cast<uint32_t*>(kf_engine), p->perm, p->NE, 128 * p->R,
-      1.0f / float(p->NE), conj);
+      1.0f / float(p->NE), conj)););
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -375,6 +393,11 @@ extern "C" size_t bffc_workspace_bytes(const bffc_plan* p, int B, int H, int L) 
   return size_t(2 * (p->nlev + 1)) * plane_bytes(p, B, H);
 }
 
+static thread_local CUtensorMapDataType g_tm_dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+static void set_map_dtype(const bffc_plan* p) {
+  g_tm_dtype = p->dtype == BFFC_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+}
+
 static int make_map(CUtensorMap* map, const void* base, int rows, int L) {
   // (rows, L) bf16 viewed as [row][L/64][64]; box = one (128 x 64) tile, 128B swizzle;
   // tile rows >= L/64 are out of bounds: zero-filled on load (implicit padding), dropped on store.
@@ -382,7 +405,7 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int L) {
   cuuint64_t strides[2] = {128, cuuint64_t(L) * 2};
   cuuint32_t box[3] = {64, 128, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = g_encode(map, g_tm_dtype, 3, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(BFFC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
@@ -424,12 +447,14 @@ static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const
   int grid = (prm.units + 1) / 2;
   if (grid > p->num_sms) grid = p->num_sms;
   using namespace bffc::r128;
-  if (dbg)
-    fwd_kernel<true, false, false><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
-  else if (pregate || postgate)
-    fwd_kernel<false, true, false><<<grid, kThreads, kSmemTotalGated, st>>>(tm_u, tm_y, tm_g, prm);
-  else
-    fwd_kernel<false, false, false><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
+  FMT_SWITCH(p->dtype,
+    if (dbg)
+      fwd_kernel<true, false, false, F><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
+    else if (pregate || postgate)
+      fwd_kernel<false, true, false, F><<<grid, kThreads, kSmemTotalGated, st>>>(tm_u, tm_y, tm_g, prm);
+    else
+      fwd_kernel<false, false, false, F><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
+  );
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -448,7 +473,7 @@ static int launch_planes(const bffc_plan* p, void* pre, void* pim, const void* k
   int grid = (prm.units + 1) / 2;
   if (grid > p->num_sms) grid = p->num_sms;
   using namespace bffc::r128;
-  fwd_kernel<false, false, true><<<grid, kThreads, kSmemTotal, st>>>(tm_r, tm_r, tm_i, prm);
+  FMT_SWITCH(p->dtype, (fwd_kernel<false, false, true, F><<<grid, kThreads, kSmemTotal, st>>>(tm_r, tm_r, tm_i, prm)););
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -460,7 +485,7 @@ static int make_map4(CUtensorMap* map, const void* base, int chunks, int rows, i
   cuuint64_t strides[3] = {128, cuuint64_t(row_stride_bytes), cuuint64_t(seq_stride_bytes)};
   cuuint32_t box[4] = {64, 1, 128, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = g_encode(map, g_tm_dtype, 4, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(BFFC_ERR_CUDA, "cuTensorMapEncodeTiled (4d) failed (%d)", int(r));
@@ -469,31 +494,32 @@ static int make_map4(CUtensorMap* map, const void* base, int chunks, int rows, i
 
 struct PlaneSet { uint8_t* re; uint8_t* im; };
 
-template <int R>
+template <int R, int F>
 static void launch_cc(bool inverse, bool gated, bool planes, const bffc::outer::OuterParams& op, int rows, cudaStream_t st) {
   using namespace bffc::outer;
   const int cb = op.M / (kVec * 128);
   if (planes) {
     dim3 grid(rows, cb, 1);
-    if (!inverse) fwd_kernel<R, false, true><<<grid, 128, 0, st>>>(op);
-    else inv_kernel<R, false, true><<<grid, 128, 0, st>>>(op);
+    if (!inverse) fwd_kernel<R, false, true, F><<<grid, 128, 0, st>>>(op);
+    else inv_kernel<R, false, true, F><<<grid, 128, 0, st>>>(op);
   } else {
     dim3 grid(cb, op.H, op.pairs);
     if (!inverse) {
-      if (gated) fwd_kernel<R, true, false><<<grid, 128, 0, st>>>(op);
-      else fwd_kernel<R, false, false><<<grid, 128, 0, st>>>(op);
+      if (gated) fwd_kernel<R, true, false, F><<<grid, 128, 0, st>>>(op);
+      else fwd_kernel<R, false, false, F><<<grid, 128, 0, st>>>(op);
     } else {
-      if (gated) inv_kernel<R, true, false><<<grid, 128, 0, st>>>(op);
-      else inv_kernel<R, false, false><<<grid, 128, 0, st>>>(op);
+      if (gated) inv_kernel<R, true, false, F><<<grid, 128, 0, st>>>(op);
+      else inv_kernel<R, false, false, F><<<grid, 128, 0, st>>>(op);
     }
   }
 }
+static thread_local int g_cur_dtype = BFFC_DTYPE_BF16;
 static int cc_stage(int R, bool inverse, bool gated, bool planes, const bffc::outer::OuterParams& op, int rows,
                     cudaStream_t st) {
   switch (R) {
-    case 2: launch_cc<2>(inverse, gated, planes, op, rows, st); break;
-    case 4: launch_cc<4>(inverse, gated, planes, op, rows, st); break;
-    case 8: launch_cc<8>(inverse, gated, planes, op, rows, st); break;
+    case 2: FMT_SWITCH(g_cur_dtype, (launch_cc<2, F>(inverse, gated, planes, op, rows, st));); break;
+    case 4: FMT_SWITCH(g_cur_dtype, (launch_cc<4, F>(inverse, gated, planes, op, rows, st));); break;
+    case 8: FMT_SWITCH(g_cur_dtype, (launch_cc<8, F>(inverse, gated, planes, op, rows, st));); break;
     default: return fail(BFFC_ERR_UNSUPPORTED, "outer radix %d not supported", R);
   }
   CUDA_TRY(cudaGetLastError());
@@ -521,10 +547,12 @@ static int tc_stage(const bffc_plan* p, bool inverse, const void* x, const void*
   int grid = (prm.units + 1) / 2;
   if (grid > p->num_sms) grid = p->num_sms;
   using namespace bffc::r128;
-  if (!inverse)
-    outer_tc_kernel<false><<<grid, kThreads, prm.has_pregate ? kSmemOuterGated : kSmemOuter, st>>>(tm_x, tm_pr, tm_pi, tm_g, prm);
-  else
-    outer_tc_kernel<true><<<grid, kThreads, kSmemOuter, st>>>(tm_x, tm_pr, tm_pi, tm_g, prm);
+  FMT_SWITCH(p->dtype,
+    if (!inverse)
+      outer_tc_kernel<false, F><<<grid, kThreads, prm.has_pregate ? kSmemOuterGated : kSmemOuter, st>>>(tm_x, tm_pr, tm_pi, tm_g, prm);
+    else
+      outer_tc_kernel<true, F><<<grid, kThreads, kSmemOuter, st>>>(tm_x, tm_pr, tm_pi, tm_g, prm);
+  );
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -613,8 +641,8 @@ static int conv_forward(const bffc_plan* p, const void* u, const void* kf, const
     const int off = corr ? kInner - p->N : p->N;
     if (int rc = launch_fused(p, u, kf, pregate, nullptr, ws, B, H, L, nullptr, 0, 0, st, Lt)) return rc;
     const size_t rows = size_t(B) * H, total = rows * (L / 8);
-    fold_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(ws), static_cast<const uint4*>(postgate),
-                                                               static_cast<uint4*>(y), L, Lt, off, rows);
+    FMT_SWITCH(p->dtype, (fold_kernel<F><<<unsigned((total + 255) / 256), 256, 0, st>>>(
+        static_cast<const uint4*>(ws), static_cast<const uint4*>(postgate), static_cast<uint4*>(y), L, Lt, off, rows)););
     CUDA_TRY(cudaGetLastError());
     *launches += 2;
     return BFFC_OK;
@@ -639,6 +667,7 @@ int bffc_fwd(const bffc_plan* p, const void* u, const void* kf, const void* preg
     return fail(BFFC_ERR_INVALID, "bffc_fwd: pregate and postgate must both be given or both be null");
   if (!u || !kf || !y) return fail(BFFC_ERR_INVALID, "bffc_fwd: null pointer");
   if (int rc = check_common(p, B, H, L, u, y, kf)) return rc;
+  set_map_dtype(p); g_cur_dtype = p->dtype;
   if ((reinterpret_cast<uintptr_t>(pregate) | reinterpret_cast<uintptr_t>(postgate) | reinterpret_cast<uintptr_t>(workspace)) & 15)
     return fail(BFFC_ERR_INVALID, "bffc_fwd: gates / workspace must be 16-byte aligned");
   if (p->N < kInner) {
@@ -664,6 +693,7 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
        reinterpret_cast<uintptr_t>(dpostgate) | reinterpret_cast<uintptr_t>(kf)) & 15)
     return fail(BFFC_ERR_INVALID, "bffc_bwd: gate pointers must be 16-byte aligned");
   if (int rc = check_common(p, B, H, L, u, du, dout)) return rc;
+  set_map_dtype(p); g_cur_dtype = p->dtype;
   if ((reinterpret_cast<uintptr_t>(dkf) | reinterpret_cast<uintptr_t>(kf_conj) | reinterpret_cast<uintptr_t>(workspace)) & 15)
     return fail(BFFC_ERR_INVALID, "bffc_bwd: dkf / kf / workspace must be 16-byte aligned");
   if ((p->nlev > 0 || p->N < kInner) && (!workspace || workspace_bytes < bffc_workspace_bytes(p, B, H, L)))
@@ -702,7 +732,7 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
     prm.ksteps = (L / 64 + 15) / 16;
     prm.gated = gated ? 1 : 0;
     int grid = H < p->num_sms ? H : p->num_sms;
-    dkf_kernel<false><<<grid, kThreads, gated ? kSmemTotalDkfGated : kSmemTotalDkf, st>>>(tm_u, tm_d, tm_p, tm_q, prm);
+    FMT_SWITCH(p->dtype, (dkf_kernel<false, F><<<grid, kThreads, gated ? kSmemTotalDkfGated : kSmemTotalDkf, st>>>(tm_u, tm_d, tm_p, tm_q, prm)););
     CUDA_TRY(cudaGetLastError());
     launches += 1;
   } else {
@@ -727,7 +757,7 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
     prm.ksteps = 8;
     prm.gated = 0;
     int grid = rows < p->num_sms ? rows : p->num_sms;
-    dkf_kernel<true><<<grid, kThreads, kSmemTotalDkf, st>>>(tur, tdr, tui, tdi, prm);
+    FMT_SWITCH(p->dtype, (dkf_kernel<true, F><<<grid, kThreads, kSmemTotalDkf, st>>>(tur, tdr, tui, tdi, prm)););
     CUDA_TRY(cudaGetLastError());
     launches += 1;
   }
@@ -739,6 +769,7 @@ int bffc_debug_fwd_stages(const bffc_plan* p, const void* u, const void* kf, voi
                           int max_stages, void* stream) {
   if (!dump || max_stages <= 0 || !p || p->R != 1) return -BFFC_ERR_INVALID;
   if (check_common(p, B, H, L, u, y, kf)) return -BFFC_ERR_INVALID;
+  set_map_dtype(p); g_cur_dtype = p->dtype;
   int rc = launch_fused(p, u, kf, nullptr, nullptr, y, B, H, L, dump, max_stages, 1, static_cast<cudaStream_t>(stream));
   if (rc) return -rc;
   return max_stages < 4 ? max_stages : 4;

@@ -37,10 +37,12 @@ constexpr int kSmemTotalDkfGated = kSmemTotalDkf + kSmemGate + 1024;
 
 // kPlanes: inputs are complex rows in bf16 planes (composite sizes): (tm_u, tm_ui) = real / imaginary plane of the
 // transformed u rows, (tm_d, tm_di) likewise for dout; p.H = number of k_f rows, row = pr * p.H + channel.
-template <bool kPlanes>
+template <bool kPlanes, int kFmt = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_d,
            const __grid_constant__ CUtensorMap tm_ui, const __grid_constant__ CUtensorMap tm_di, const DkfParams p) {
+  using NT = Num<kFmt>;
+  constexpr uint32_t ID_N128_MN = Idesc<kFmt>::N128_MN, ID_N64_MN = Idesc<kFmt>::N64_MN, ID_N64_MN_NEG = Idesc<kFmt>::N64_MN_NEG;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_g = sbase + kSmemData;
@@ -180,7 +182,7 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
         for (int c = 0; c < 4; ++c) {
           const uint32_t off = part * kTileBytes + uint32_t(lane) * 128u + uint32_t(4 * half + c) * 16u;
           const uint4 a = ld_shared_v4(sX + off), g = ld_shared_v4(sG + off);
-          st_shared_v4(sX + off, hmul2_bf16(a.x, g.x), hmul2_bf16(a.y, g.y), hmul2_bf16(a.z, g.z), hmul2_bf16(a.w, g.w));
+          st_shared_v4(sX + off, NT::hmul2(a.x, g.x), NT::hmul2(a.y, g.y), NT::hmul2(a.z, g.z), NT::hmul2(a.w, g.w));
         }
       fence_proxy_async_smem();
       named_bar_sync(bar_id, kPipeThreads);
@@ -214,8 +216,8 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
         const float2 c = __half22float2(twc[8 * sub + q]), sn = __half22float2(tws[8 * sub + q]);
         f32x2 vr, vi;
         cmul2(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), pk2(c.x, c.y), pk2(sn.x, sn.y), vr, vi);
-        ore[q] = pack_bf16x2_v(vr);
-        oim[q] = pack_bf16x2_v(vi);
+        ore[q] = NT::pack_v(vr);
+        oim[q] = NT::pack_v(vi);
       }
       tmem_st8(tA + 16 * half + 8 * sub, ore);
       tmem_st8(tA + 32 + 16 * half + 8 * sub, oim);

@@ -61,9 +61,11 @@ constexpr uint32_t kColC = 0, kColS = 64;                 // DFT-128 cos / sin, 
 DEVINL constexpr uint32_t colD(int pipe) { return 128 + 192 * pipe; }        // 128 fp32 cols
 DEVINL constexpr uint32_t colA(int pipe) { return 128 + 192 * pipe + 128; }  // 64 cols (bf16x2)
 
-constexpr uint32_t ID_N128_MN = make_idesc(1, 128, true, false);
-constexpr uint32_t ID_N64_MN = make_idesc(1, 64, true, false);
-constexpr uint32_t ID_N64_MN_NEG = make_idesc(1, 64, true, true);
+template <int kFmt> struct Idesc {
+  static constexpr uint32_t N128_MN = make_idesc(kFmt, 128, true, false);
+  static constexpr uint32_t N64_MN = make_idesc(kFmt, 64, true, false);
+  static constexpr uint32_t N64_MN_NEG = make_idesc(kFmt, 64, true, true);
+};
 
 DEVINL void cmul(float ar, float ai, float br, float bi, float& cr, float& ci) {
   cr = ar * br - ai * bi;
@@ -73,10 +75,6 @@ DEVINL uint64_t tile_desc(uint32_t saddr) { return make_sdesc(saddr, kTileBytes,
 // N=128 B operand made of two 64-column tiles `lbo` bytes apart
 DEVINL uint64_t pair_desc(uint32_t saddr, uint32_t lbo) { return make_sdesc(saddr, lbo, 1024, 2); }
 
-DEVINL uint32_t hmul2_bf16(uint32_t a, uint32_t b) {
-  __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
-  return *reinterpret_cast<uint32_t*>(&r);
-}
 DEVINL uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -90,10 +88,12 @@ DEVINL uint4 ld_shared_v4(uint32_t addr) {
 // kPlanes: complex rows mode for composite sizes (N = R x 8192, see outer_cuda.cuh / outer_r128.cuh): the unit is one
 // complex length-8192 row whose real / imaginary parts live in two bf16 planes (tm_u = tm_y = real plane,
 // tm_g = imaginary plane), k_f row = unit / pairs (p.H = number of k_f rows), result written back in place.
-template <bool kDebug, bool kGated, bool kPlanes = false>
+template <bool kDebug, bool kGated, bool kPlanes = false, int kFmt = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_y,
            const __grid_constant__ CUtensorMap tm_g, const FwdParams p) {
+  using NT = Num<kFmt>;
+  constexpr uint32_t ID_N128_MN = Idesc<kFmt>::N128_MN, ID_N64_MN = Idesc<kFmt>::N64_MN, ID_N64_MN_NEG = Idesc<kFmt>::N64_MN_NEG;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_g = sbase + kSmemData;            // Gr tile, Gi tile
@@ -263,7 +263,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
         for (int c = 0; c < 4; ++c) {
           const uint32_t off = part * kTileBytes + uint32_t(lane) * 128u + uint32_t(4 * half + c) * 16u;
           const uint4 a = ld_shared_v4(sX + off), g = ld_shared_v4(sG + off);
-          st_shared_v4(sX + off, hmul2_bf16(a.x, g.x), hmul2_bf16(a.y, g.y), hmul2_bf16(a.z, g.z), hmul2_bf16(a.w, g.w));
+          st_shared_v4(sX + off, NT::hmul2(a.x, g.x), NT::hmul2(a.y, g.y), NT::hmul2(a.z, g.z), NT::hmul2(a.w, g.w));
         }
       fence_proxy_async_smem();
       named_bar_sync(bar_id, kPipeThreads);
@@ -307,8 +307,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
         const float2 c = __half22float2(twc[8 * sub + q]), sn = __half22float2(tws[8 * sub + q]);
         f32x2 vr, vi;
         cmul2(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), pk2(c.x, c.y), pk2(sn.x, sn.y), vr, vi);
-        ore[q] = pack_bf16x2_v(vr);
-        oim[q] = pack_bf16x2_v(vi);
+        ore[q] = NT::pack_v(vr);
+        oim[q] = NT::pack_v(vi);
       }
       tmem_st8(tA + 16 * half + 8 * sub, ore);
       tmem_st8(tA + 32 + 16 * half + 8 * sub, oim);
@@ -349,10 +349,9 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
         const uint4 kq = kfv[4 * sub + (q >> 1)];
         const uint32_t wr = (q & 1) ? kq.z : kq.x, wi = (q & 1) ? kq.w : kq.y;
         f32x2 vr, vi;
-        cmul2(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), pk2u(wr << 16, wr & 0xffff0000u),
-              pk2u(wi << 16, wi & 0xffff0000u), vr, vi);
-        ore[q] = pack_bf16x2_v(vr);
-        oim[q] = pack_bf16x2_v(vi);
+        cmul2(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), NT::unpack(wr), NT::unpack(wi), vr, vi);
+        ore[q] = NT::pack_v(vr);
+        oim[q] = NT::pack_v(vi);
       }
       tmem_st8(tA + 16 * half + 8 * sub, ore);
       tmem_st8(tA + 32 + 16 * half + 8 * sub, oim);
@@ -386,8 +385,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
         const float2 c = __half22float2(twc[8 * sub + q]), sn = __half22float2(tws[8 * sub + q]);
         f32x2 vr, vi;
         cmul2_conj(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), pk2(c.x, c.y), pk2(sn.x, sn.y), vr, vi);
-        ore[q] = pack_bf16x2_v(vr);
-        oim[q] = pack_bf16x2_v(vi);
+        ore[q] = NT::pack_v(vr);
+        oim[q] = NT::pack_v(vi);
       }
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
@@ -439,13 +438,13 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
         for (int cc = 0; cc < 2; ++cc) {
           const int chunk = 4 * half + 2 * sub + cc;
           const uint32_t off = uint32_t(lane) * 128u + (uint32_t(chunk ^ (lane & 7)) << 4);
-          uint32_t o0 = pack_bf16x2(__uint_as_float(v[8 * cc + 0]), __uint_as_float(v[8 * cc + 1]));
-          uint32_t o1 = pack_bf16x2(__uint_as_float(v[8 * cc + 2]), __uint_as_float(v[8 * cc + 3]));
-          uint32_t o2 = pack_bf16x2(__uint_as_float(v[8 * cc + 4]), __uint_as_float(v[8 * cc + 5]));
-          uint32_t o3 = pack_bf16x2(__uint_as_float(v[8 * cc + 6]), __uint_as_float(v[8 * cc + 7]));
+          uint32_t o0 = NT::pack(__uint_as_float(v[8 * cc + 0]), __uint_as_float(v[8 * cc + 1]));
+          uint32_t o1 = NT::pack(__uint_as_float(v[8 * cc + 2]), __uint_as_float(v[8 * cc + 3]));
+          uint32_t o2 = NT::pack(__uint_as_float(v[8 * cc + 4]), __uint_as_float(v[8 * cc + 5]));
+          uint32_t o3 = NT::pack(__uint_as_float(v[8 * cc + 6]), __uint_as_float(v[8 * cc + 7]));
           if (has_post) {
             const uint4 g = pg[part][2 * sub + cc];
-            o0 = hmul2_bf16(o0, g.x); o1 = hmul2_bf16(o1, g.y); o2 = hmul2_bf16(o2, g.z); o3 = hmul2_bf16(o3, g.w);
+            o0 = NT::hmul2(o0, g.x); o1 = NT::hmul2(o1, g.y); o2 = NT::hmul2(o2, g.z); o3 = NT::hmul2(o3, g.w);
           }
           st_shared_v4(sX + part * kTileBytes + off, o0, o1, o2, o3);
         }

@@ -18,23 +18,21 @@ namespace outer {
 
 constexpr int kVec = 8;
 
+template <int kFmt>
 DEVINL void unpack8(const uint4& v, float (&f)[8]) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    f[2 * i] = __uint_as_float(w[i] << 16);
-    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-  }
+  for (int i = 0; i < 4; ++i) upk2(Num<kFmt>::unpack(w[i]), f[2 * i], f[2 * i + 1]);
 }
+template <int kFmt>
 DEVINL uint4 pack8(const float (&f)[8]) {
-  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  using NT = Num<kFmt>;
+  return make_uint4(NT::pack(f[0], f[1]), NT::pack(f[2], f[3]), NT::pack(f[4], f[5]), NT::pack(f[6], f[7]));
 }
+template <int kFmt>
 DEVINL uint4 hmul8(const uint4& a, const uint4& b) {
-  auto m = [](uint32_t x, uint32_t y) {
-    __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&x), *reinterpret_cast<__nv_bfloat162*>(&y));
-    return *reinterpret_cast<uint32_t*>(&r);
-  };
-  return make_uint4(m(a.x, b.x), m(a.y, b.y), m(a.z, b.z), m(a.w, b.w));
+  using NT = Num<kFmt>;
+  return make_uint4(NT::hmul2(a.x, b.x), NT::hmul2(a.y, b.y), NT::hmul2(a.z, b.z), NT::hmul2(a.w, b.w));
 }
 
 struct OuterParams {
@@ -60,7 +58,7 @@ DEVINL void wr(int R, int e, float& c, float& s) {   // exp(-2 pi i e / R)
 }
 
 // forward: grid (M / (kVec*blockDim.x), H, pairs)   [kPlanes: (rows, M / (kVec*blockDim.x), 1)]
-template <int R, bool kGated, bool kPlanes>
+template <int R, bool kGated, bool kPlanes, int kFmt>
 __global__ void __launch_bounds__(128, (R <= 4) ? 4 : 2) fwd_kernel(const OuterParams p) {
   const int kM = p.M;
   const int np = ((kPlanes ? blockIdx.y : blockIdx.x) * blockDim.x + threadIdx.x) * kVec;   // n'
@@ -75,19 +73,19 @@ __global__ void __launch_bounds__(128, (R <= 4) ? 4 : 2) fwd_kernel(const OuterP
     if (kPlanes) {
       rows = R;
       const size_t o = (size_t(blockIdx.x) * R * kM + n) / kVec;
-      unpack8(__ldg(p.xre + o), zr[a]);
-      unpack8(__ldg(p.xim + o), zi[a]);
+      unpack8<kFmt>(__ldg(p.xre + o), zr[a]);
+      unpack8<kFmt>(__ldg(p.xim + o), zi[a]);
     } else if (n < p.L) {
       rows = a + 1;
       const size_t o0 = (size_t(b0) * p.H + h) * L8 + n / kVec;
       uint4 v0 = __ldg(p.u + o0);
-      if (kGated) v0 = hmul8(v0, __ldg(p.pregate + o0));
-      unpack8(v0, zr[a]);
+      if (kGated) v0 = hmul8<kFmt>(v0, __ldg(p.pregate + o0));
+      unpack8<kFmt>(v0, zr[a]);
       if (b1 < p.B) {
         const size_t o1 = (size_t(b1) * p.H + h) * L8 + n / kVec;
         uint4 v1 = __ldg(p.u + o1);
-        if (kGated) v1 = hmul8(v1, __ldg(p.pregate + o1));
-        unpack8(v1, zi[a]);
+        if (kGated) v1 = hmul8<kFmt>(v1, __ldg(p.pregate + o1));
+        unpack8<kFmt>(v1, zi[a]);
       } else {
 #pragma unroll
         for (int t = 0; t < 8; ++t) zi[a][t] = 0.f;
@@ -131,13 +129,13 @@ __global__ void __launch_bounds__(128, (R <= 4) ? 4 : 2) fwd_kernel(const OuterP
       wc[t] = nc;
     }
     const size_t row = (kPlanes ? size_t(blockIdx.x) : (size_t(pr) * p.H + h)) * R + c;
-    p.pre[row * (kM / kVec) + np / kVec] = pack8(or_);
-    p.pim[row * (kM / kVec) + np / kVec] = pack8(oi_);
+    p.pre[row * (kM / kVec) + np / kVec] = pack8<kFmt>(or_);
+    p.pim[row * (kM / kVec) + np / kVec] = pack8<kFmt>(oi_);
   }
 }
 
 // inverse: same grid
-template <int R, bool kGated, bool kPlanes>
+template <int R, bool kGated, bool kPlanes, int kFmt>
 __global__ void __launch_bounds__(128, (R <= 4) ? 4 : 2) inv_kernel(const OuterParams p) {
   const int kM = p.M;
   const int np = ((kPlanes ? blockIdx.y : blockIdx.x) * blockDim.x + threadIdx.x) * kVec;
@@ -155,8 +153,8 @@ __global__ void __launch_bounds__(128, (R <= 4) ? 4 : 2) inv_kernel(const OuterP
   for (int c = 0; c < R; ++c) {
     const size_t row = (kPlanes ? size_t(blockIdx.x) : (size_t(pr) * p.H + h)) * R + c;
     float xr[8], xi[8];
-    unpack8(__ldg(p.pre + row * (kM / kVec) + np / kVec), xr);
-    unpack8(__ldg(p.pim + row * (kM / kVec) + np / kVec), xi);
+    unpack8<kFmt>(__ldg(p.pre + row * (kM / kVec) + np / kVec), xr);
+    unpack8<kFmt>(__ldg(p.pim + row * (kM / kVec) + np / kVec), xi);
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       tr[c][t] = xr[t] * wc[t] - xi[t] * ws[t];
@@ -185,18 +183,18 @@ __global__ void __launch_bounds__(128, (R <= 4) ? 4 : 2) inv_kernel(const OuterP
       }
       if (kPlanes) {
         const size_t o = (size_t(blockIdx.x) * R * kM + n) / kVec;
-        p.xre[o] = pack8(yr);
-        p.xim[o] = pack8(yi);
+        p.xre[o] = pack8<kFmt>(yr);
+        p.xim[o] = pack8<kFmt>(yi);
         continue;
       }
       const size_t o0 = (size_t(b0) * p.H + h) * L8 + n / kVec;
-      uint4 v0 = pack8(yr);
-      if (kGated) v0 = hmul8(v0, __ldg(p.postgate + o0));
+      uint4 v0 = pack8<kFmt>(yr);
+      if (kGated) v0 = hmul8<kFmt>(v0, __ldg(p.postgate + o0));
       p.y[o0] = v0;
       if (b1 < p.B) {
         const size_t o1 = (size_t(b1) * p.H + h) * L8 + n / kVec;
-        uint4 v1 = pack8(yi);
-        if (kGated) v1 = hmul8(v1, __ldg(p.postgate + o1));
+        uint4 v1 = pack8<kFmt>(yi);
+        if (kGated) v1 = hmul8<kFmt>(v1, __ldg(p.postgate + o1));
         p.y[o1] = v1;
       }
     }

@@ -38,13 +38,15 @@ constexpr int kSmemOuterData = 2 * kOuterSlots * kSlotBytes;
 constexpr int kSmemOuter = kSmemOuterData + kSmemBars + 1024;
 constexpr int kSmemOuterGated = kSmemOuterData + kSmemBars + 1024;   // gate slot = third ring slot
 
-template <bool kInverse>
+template <bool kInverse, int kFmt = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u (fwd) / y (inv), 4-D
                 const __grid_constant__ CUtensorMap tm_pr,   // planes, real part, 4-D
                 const __grid_constant__ CUtensorMap tm_pi,   // planes, imaginary part
                 const __grid_constant__ CUtensorMap tm_g,    // pregate (fwd, optional)
                 const OuterTcParams p) {
+  using NT = Num<kFmt>;
+  constexpr uint32_t ID_N128_MN = Idesc<kFmt>::N128_MN, ID_N64_MN = Idesc<kFmt>::N64_MN, ID_N64_MN_NEG = Idesc<kFmt>::N64_MN_NEG;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_bars = sbase + kSmemOuterData;
@@ -190,7 +192,7 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
         for (int c = 0; c < 4; ++c) {
           const uint32_t off = part * kTileBytes + uint32_t(lane) * 128u + uint32_t(4 * half + c) * 16u;
           const uint4 a = ld_shared_v4(sX + off), g = ld_shared_v4(sG + off);
-          st_shared_v4(sX + off, hmul2_bf16(a.x, g.x), hmul2_bf16(a.y, g.y), hmul2_bf16(a.z, g.z), hmul2_bf16(a.w, g.w));
+          st_shared_v4(sX + off, NT::hmul2(a.x, g.x), NT::hmul2(a.y, g.y), NT::hmul2(a.z, g.z), NT::hmul2(a.w, g.w));
         }
     }
     if (kInverse) {
@@ -208,9 +210,9 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
           f32x2 wcr, wci;   // full twiddle = base * table
           cmul2(bc2, bs2, pk2(tc.x, tc.y), pk2(ts.x, ts.y), wcr, wci);
           f32x2 orr2, oii2;
-          cmul2_conj(pk2u(wr_[e] << 16, wr_[e] & 0xffff0000u), pk2u(wi_[e] << 16, wi_[e] & 0xffff0000u), wcr, wci, orr2, oii2);
-          orr[e] = pack_bf16x2_v(orr2);
-          oii[e] = pack_bf16x2_v(oii2);
+          cmul2_conj(NT::unpack(wr_[e]), NT::unpack(wi_[e]), wcr, wci, orr2, oii2);
+          orr[e] = NT::pack_v(orr2);
+          oii[e] = NT::pack_v(oii2);
         }
         st_shared_v4(sX + off, orr[0], orr[1], orr[2], orr[3]);
         st_shared_v4(sX + kTileBytes + off, oii[0], oii[1], oii[2], oii[3]);
@@ -272,11 +274,11 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
           f32x2 wcr, wci, vr, vi;
           cmul2(bc2, bs2, pk2(tc.x, tc.y), pk2(ts.x, ts.y), wcr, wci);
           cmul2(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), wcr, wci, vr, vi);
-          ore[q] = pack_bf16x2_v(vr);
-          oim[q] = pack_bf16x2_v(vi);
+          ore[q] = NT::pack_v(vr);
+          oim[q] = NT::pack_v(vi);
         } else {
-          ore[q] = pack_bf16x2(__uint_as_float(re[2 * q]), __uint_as_float(re[2 * q + 1]));
-          oim[q] = pack_bf16x2(__uint_as_float(im[2 * q]), __uint_as_float(im[2 * q + 1]));
+          ore[q] = NT::pack(__uint_as_float(re[2 * q]), __uint_as_float(re[2 * q + 1]));
+          oim[q] = NT::pack(__uint_as_float(im[2 * q]), __uint_as_float(im[2 * q + 1]));
         }
       }
 #pragma unroll
@@ -287,8 +289,8 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
         uint32_t b0 = oim[4 * cc], b1 = oim[4 * cc + 1], b2 = oim[4 * cc + 2], b3 = oim[4 * cc + 3];
         if (has_post) {
           const uint4 g0 = pg[0][2 * sub + cc], g1 = pg[1][2 * sub + cc];
-          a0 = hmul2_bf16(a0, g0.x); a1 = hmul2_bf16(a1, g0.y); a2 = hmul2_bf16(a2, g0.z); a3 = hmul2_bf16(a3, g0.w);
-          b0 = hmul2_bf16(b0, g1.x); b1 = hmul2_bf16(b1, g1.y); b2 = hmul2_bf16(b2, g1.z); b3 = hmul2_bf16(b3, g1.w);
+          a0 = NT::hmul2(a0, g0.x); a1 = NT::hmul2(a1, g0.y); a2 = NT::hmul2(a2, g0.z); a3 = NT::hmul2(a3, g0.w);
+          b0 = NT::hmul2(b0, g1.x); b1 = NT::hmul2(b1, g1.y); b2 = NT::hmul2(b2, g1.z); b3 = NT::hmul2(b3, g1.w);
         }
         st_shared_v4(sX + off, a0, a1, a2, a3);
         st_shared_v4(sX + kTileBytes + off, b0, b1, b2, b3);

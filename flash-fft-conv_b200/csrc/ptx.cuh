@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #define DEVINL __device__ __forceinline__
@@ -211,6 +212,34 @@ DEVINL uint32_t pack_bf16x2_v(f32x2 v) {   // (lo, hi) fp32 pair -> bf16x2
   __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&r);
 }
+
+DEVINL uint32_t pack_bf16x2(float lo, float hi);
+// 16-bit element formats.  kFmt follows the UMMA encoding: 1 = bf16, 0 = fp16 (fp32 accumulate either way).
+template <int kFmt> struct Num;
+template <> struct Num<1> {
+  static DEVINL uint32_t pack(float lo, float hi) { return pack_bf16x2(lo, hi); }
+  static DEVINL uint32_t pack_v(f32x2 v) { return pack_bf16x2_v(v); }
+  static DEVINL f32x2 unpack(uint32_t w) { return pk2u(w << 16, w & 0xffff0000u); }
+  static DEVINL uint32_t hmul2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+};
+template <> struct Num<0> {
+  static DEVINL uint32_t pack(float lo, float hi) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  static DEVINL uint32_t pack_v(f32x2 v) { float a, b; upk2(v, a, b); return pack(a, b); }
+  static DEVINL f32x2 unpack(uint32_t w) {
+    const float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
+    return pk2(f.x, f.y);
+  }
+  static DEVINL uint32_t hmul2(uint32_t a, uint32_t b) {
+    __half2 r = __hmul2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+};
 
 // Warp-uniform single-thread election (elect.sync): lets the compiler keep MMA/TMA operands in uniform
 // registers instead of emitting a per-instruction uniformisation loop.

@@ -21,6 +21,7 @@ SYMBOLS = {
     'bffc_plan_create': (_c.c_int, [_c.POINTER(_c.c_void_p), _c.c_int, _c.c_int]),
     'bffc_plan_destroy': (_c.c_int, [_c.c_void_p]),
     'bffc_fft_size': (_c.c_int, [_c.c_void_p]),
+    'bffc_length_multiple': (_c.c_int, [_c.c_void_p]),
     'bffc_kf_pack': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p]),
     'bffc_kf_pack_rfft': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p]),
     'bffc_dkf_unpack': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p]),

@@ -107,7 +107,27 @@ def _pack_kf(mod, plan, k, conj):
     return _pack_kf_from_natural(mod, plan, _kf_natural(mod, k), conj)
 
 
+def _pad_len(mod, device, L):
+    q = _lib.lib().bffc_length_multiple(mod.plan(device).handle)
+    return (L + q - 1) // q * q
+
+
+def _padded(t, Lp):
+    """zero-extend (B,H,L) to (B,H,Lp): identical operator (implicit zero padding), used for lengths the kernels'
+    tiling does not take directly (the reference only requires L even, README.md:270)."""
+    if t is None or t.shape[-1] == Lp:
+        return t
+    out = torch.zeros(t.shape[:-1] + (Lp,), dtype=t.dtype, device=t.device)
+    out[..., : t.shape[-1]] = t
+    return out
+
+
 def _fwd(mod, u, k, pregate, postgate):
+    L0 = u.shape[-1]
+    Lp = _pad_len(mod, u.device, L0)
+    if Lp != L0:
+        y, k_f = _fwd(mod, _padded(u, Lp), k, _padded(pregate, Lp), _padded(postgate, Lp))
+        return y[..., :L0].contiguous(), k_f
     B, H, L = u.shape
     plan = mod.plan(u.device)
     with torch.cuda.device(u.device):
@@ -123,6 +143,12 @@ def _fwd(mod, u, k, pregate, postgate):
 
 def _bwd(mod, dout, u, k_f, k_len, pregate, postgate):
     """du, dk[, dpregate, dpostgate] — reference: FlashFFTConvFunc.backward, conv.py:1737-1822."""
+    L0 = u.shape[-1]
+    Lp = _pad_len(mod, u.device, L0)
+    if Lp != L0:
+        r = _bwd(mod, _padded(dout, Lp), _padded(u, Lp), k_f, k_len, _padded(pregate, Lp), _padded(postgate, Lp))
+        cut = lambda t: None if t is None else t[..., :L0].contiguous()
+        return cut(r[0]), r[1], cut(r[2]), cut(r[3])
     B, H, L = u.shape
     N = mod.fft_size(u.device)
     plan = mod.plan(u.device)

@@ -64,6 +64,8 @@ int bffc_plan_destroy(bffc_plan* plan);
 /* FFT size n the caller must use for k_f = rfft(k, n) / for the inverse FFT of dk_f: seqlen for seqlen >= 8192;
  * 8192 for the small sizes (256..4096), whose dk then is dk[i] = c[i] + c[8192 - seqlen + i], c = ifft(dk_f).real */
 int bffc_fft_size(const bffc_plan* plan);
+/* L passed to bffc_fwd / bffc_bwd must be a multiple of this (the host mirror zero-pads other lengths). */
+int bffc_length_multiple(const bffc_plan* plan);
 
 /*
  * Frequency-domain filter layout.  The engine consumes k_f = FFT_N(k)/N as packed complex

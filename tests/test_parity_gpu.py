@@ -287,3 +287,53 @@ def test_bwd_small_vs_oracle(ffc, N, B, H, L, gated):
     if gated:
         _check(gl[0].grad, refs[2], 'dpregate')
         _check(gl[1].grad, refs[3], 'dpostgate')
+
+
+# ----------------------------------------------------------------------------- fp16 (the reference module's default dtype)
+@pytest.mark.parametrize('N,B,H,L', [(8192, 3, 4, 8192), (8192, 2, 2, 4096), (32768, 2, 2, 16384), (1048576, 2, 1, 1048576),
+                                     (1024, 2, 3, 1024)])
+@pytest.mark.parametrize('unit_scale', [False, True])
+def test_fwd_fp16_vs_oracle(ffc, N, B, H, L, unit_scale):
+    d = orc.make_inputs(B, H, N, L, torch.float16, seed=61 + B, unit_scale=unit_scale)
+    conv = ffc.FlashFFTConv(N, dtype=torch.float16).cuda()
+    y = conv(d['u'].cuda(), d['k'].cuda())
+    assert y.dtype == torch.float16
+    _check(y, orc.ref_fft_conv(d['u'], d['k'], N), f'fp16 fwd N={N}')
+
+
+def test_fp16_golden_and_backward(ffc, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'conv_n8192_fp16.npz'))
+    N = int(g['N'])
+    u = torch.from_numpy(g['u']).to(torch.float16).cuda().requires_grad_(True)
+    k = torch.from_numpy(g['k']).cuda().requires_grad_(True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.float16).cuda()
+    y = conv(u, k)
+    assert torch.allclose(y.detach().cpu().float(), torch.from_numpy(g['y']), atol=1e-2)
+    _check(y.detach(), torch.from_numpy(g['y']), 'fp16 golden fwd')
+    y.backward(torch.from_numpy(g['dout']).to(torch.float16).cuda())
+    _check(u.grad, torch.from_numpy(g['du']), 'fp16 golden du')
+    _check(k.grad, torch.from_numpy(g['dk']), 'fp16 golden dk')
+
+
+def test_fp16_gated(ffc):
+    N, B, H, L = 8192, 2, 3, 4096
+    d = orc.make_inputs(B, H, N, L, torch.float16, seed=71, gated=True, unit_scale=True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.float16).cuda()
+    y = conv(d['u'].cuda(), d['k'].cuda(), d['pregate'].cuda(), d['postgate'].cuda())
+    _check(y, orc.ref_fft_conv_gated(d['u'], d['k'], d['pregate'], d['postgate'], N), 'fp16 gated fwd')
+
+
+@pytest.mark.parametrize('N,B,H,L', [(8192, 2, 3, 8190), (8192, 2, 2, 1000), (1024, 2, 2, 510), (1048576, 2, 1, 1000000)])
+def test_ragged_lengths(ffc, N, B, H, L):
+    """L that is not a multiple of the kernels' tile (the reference only needs L even): host mirror zero-pads."""
+    d = orc.make_inputs(B, H, N, L, torch.bfloat16, seed=81, unit_scale=True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    u = d['u'].cuda().requires_grad_(True)
+    k = d['k'].cuda().requires_grad_(True)
+    y = conv(u, k)
+    assert y.shape == (B, H, L)
+    _check(y.detach(), orc.ref_fft_conv(d['u'], d['k'], N), f'ragged fwd L={L}')
+    y.backward(d['dout'].cuda())
+    du_ref, dk_ref = orc.ref_grads(d['u'], d['k'], d['dout'], N)
+    _check(u.grad, du_ref, 'ragged du')
+    _check(k.grad, dk_ref, 'ragged dk')
