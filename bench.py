@@ -24,6 +24,8 @@ sys.path.insert(0, os.path.join(ROOT, 'flash-fft-conv_b200'))
 
 import torch  # noqa: E402
 
+_OUT_FD = 1
+
 WORKLOADS = {
     # name: (N, B, H, L, gated)
     'c2': (8192, 16, 768, 8192, False),       # BASELINE.json configs[1]: M2-BERT dims, the metric's config
@@ -149,14 +151,14 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     val = Bs * Hs * args.steps / dt
     sample = f'each step = {Bs * Hs} convs (B={Bs},H={Hs}) of the N={N}, L={L} workload; fp32 torch.fft, {cores} threads'
-    print(json.dumps({
+    emit(json.dumps({
         'impl': 'reference', 'metric': 'fftconv_fwd_convs_per_sec', 'value': val, 'unit': 'convs/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': f'{args.workload}: N={N} B={B} H={H} L={L} ungated (bounded CPU sample)'},
         'cpu_baseline': {'value': val, 'unit': 'convs/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': val, 'unit': 'convs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0}))
+        'gpu_launches': 0}), _OUT_FD)
 
 
 def run_ours(args):
@@ -326,10 +328,29 @@ def run_ours(args):
         'clocks': sampler.summary() if sampler else None,
     }
     out['cpu_baseline'] = cpu_baseline(N, L, gated) if world == 1 else None
-    print(json.dumps(out))
+    emit(json.dumps(out), _OUT_FD)
 
 
 def main():
+    # libraries (NCCL prints its version banner) must not pollute the ONE JSON line on stdout: send fd 1 to stderr
+    # while the benchmark runs and restore it for the final print
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _main(saved_fd)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+
+
+def emit(line, saved_fd):
+    os.write(saved_fd, (line + '\n').encode())
+
+
+def _main(saved_fd):
+    global _OUT_FD
+    _OUT_FD = saved_fd
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)

@@ -10,6 +10,7 @@
 // No torch types cross this boundary; there is no CPU fallback.
 #include "bffc.h"
 #include "fwd_r128.cuh"
+#include "fwd3_r128.cuh"
 #include "dkf_r128.cuh"
 #include "outer_cuda.cuh"
 #include "outer_r128.cuh"
@@ -17,6 +18,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -183,6 +185,16 @@ __global__ void kf_pack_tiled_kernel(const float2* __restrict__ kf_nat, uint2* _
 
 constexpr int kInner = 8192;   // the fused tcgen05 kernel's size
 
+// BFFC_FWD3=0 selects the two-pipeline kernel (fwd_r128.cuh) for the ungated forward; default: three-pipeline variant
+bool use_fwd3() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BFFC_FWD3");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 }  // namespace
 
 struct bffc_level { int tc; int R; };   // tc = 1: tcgen05 radix-128 stage (outer_r128.cuh); 0: CUDA-core radix 2/4/8
@@ -305,6 +317,8 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
     CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<true, false, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<false, true, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalGated));
     CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<false, false, true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    CUDA_TRY(cudaFuncSetAttribute(fwd3_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal3));
+    CUDA_TRY(cudaFuncSetAttribute(fwd3_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal3));
     CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf));
     CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkfGated));
     CUDA_TRY(cudaFuncSetAttribute(outer_tc_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOuterGated));
@@ -339,14 +353,14 @@ int bffc_kf_pack(const bffc_plan* p, const void* kf_natural, void* kf_engine, in
     dim3 grid(kInner / 2 / 32, (p->lev[0].R / 32) * (p->nlev == 2 ? p->lev[1].R : 1), H);
     FMT_SWITCH(p->dtype, (kf_pack_tiled_kernel<false, F><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const float2*>(kf_natural), static_cast<uint2*>(kf_engine), p->NE, p->lev[0].R,
-        p->nlev == 2 ? p->lev[1].R : 1, 1.0f / float(p->NE), conj)););
+        p->nlev == 2 ? p->lev[1].R : 1, p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj)););
     CUDA_TRY(cudaGetLastError());
     return BFFC_OK;
   }
   dim3 grid(64, H);
   FMT_SWITCH(p->dtype, (kf_pack_kernel<false, F><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float*>(kf_natural), static_cast<uint32_t*>(kf_engine), p->perm, p->NE, 128 * p->R,
-      1.0f / float(p->NE), conj)););
+      p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj)););
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -357,14 +371,14 @@ int bffc_kf_pack_rfft(const bffc_plan* p, const void* kf_half, void* kf_engine, 
     dim3 grid(kInner / 2 / 32, (p->lev[0].R / 32) * (p->nlev == 2 ? p->lev[1].R : 1), H);
     FMT_SWITCH(p->dtype, (kf_pack_tiled_kernel<true, F><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const float2*>(kf_half), static_cast<uint2*>(kf_engine), p->NE, p->lev[0].R,
-        p->nlev == 2 ? p->lev[1].R : 1, 1.0f / float(p->NE), conj)););
+        p->nlev == 2 ? p->lev[1].R : 1, p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj)););
     CUDA_TRY(cudaGetLastError());
     return BFFC_OK;
   }
   dim3 grid(64, H);
   FMT_SWITCH(p->dtype, (kf_pack_kernel<true, F><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float*>(kf_half), static_cast<uint32_t*>(kf_engine), p->perm, p->NE, 128 * p->R,
-      1.0f / float(p->NE), conj)););
+      p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj)););
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -417,6 +431,7 @@ static void fill_params(const bffc_plan* p, bffc::FwdParams& prm, const void* kf
   prm.dftC = p->dftC;
   prm.dftS = p->dftS;
   prm.gtiles = p->gtiles;
+  prm.kf_scale = 1.0f / float(p->NE);   // applied in-kernel for fp16 only (bf16 k_f is pre-scaled by the pack kernel)
   prm.pregate = nullptr;
   prm.postgate = nullptr;
   prm.dbg = nullptr;
@@ -452,7 +467,11 @@ static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const
       fwd_kernel<true, false, false, F><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
     else if (pregate || postgate)
       fwd_kernel<false, true, false, F><<<grid, kThreads, kSmemTotalGated, st>>>(tm_u, tm_y, tm_g, prm);
-    else
+    else if (use_fwd3()) {
+      int g3 = (prm.units + kPipes3 - 1) / kPipes3;
+      if (g3 > p->num_sms) g3 = p->num_sms;
+      fwd3_kernel<false, F><<<g3, kThreads3, kSmemTotal3, st>>>(tm_u, tm_y, tm_g, prm);
+    } else
       fwd_kernel<false, false, false, F><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
   );
   CUDA_TRY(cudaGetLastError());
@@ -473,7 +492,13 @@ static int launch_planes(const bffc_plan* p, void* pre, void* pim, const void* k
   int grid = (prm.units + 1) / 2;
   if (grid > p->num_sms) grid = p->num_sms;
   using namespace bffc::r128;
-  FMT_SWITCH(p->dtype, (fwd_kernel<false, false, true, F><<<grid, kThreads, kSmemTotal, st>>>(tm_r, tm_r, tm_i, prm)););
+  if (use_fwd3()) {
+    int g3 = (prm.units + kPipes3 - 1) / kPipes3;
+    if (g3 > p->num_sms) g3 = p->num_sms;
+    FMT_SWITCH(p->dtype, (fwd3_kernel<true, F><<<g3, kThreads3, kSmemTotal3, st>>>(tm_r, tm_r, tm_i, prm)););
+  } else {
+    FMT_SWITCH(p->dtype, (fwd_kernel<false, false, true, F><<<grid, kThreads, kSmemTotal, st>>>(tm_r, tm_r, tm_i, prm)););
+  }
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }

@@ -1,0 +1,335 @@
+// Fused forward FFT-convolution kernel, N = 8192 — three-pipeline variant (v3), ungated.
+//
+// Same algorithm and stage list as fwd_r128.cuh.  The v2 kernel is latency-bound with only two sequence pairs in
+// flight per SM (TMEM: 128 columns DFT-128 + 2 x (128 accumulator + 64 operand)); see profiles/r1_v21_summary.md.
+// Here the A operand of the two radix-64 stages is staged in SHARED memory (the unit's own tile slot, K-major,
+// 128B swizzle — byte-for-byte the layout pass 5 already writes for stage 4) instead of TMEM, which frees the
+// operand columns: TMEM = 128 (DFT-128) + 3 x 128 accumulators, i.e. three pipelines of one warpgroup each.
+// Stage 2 / 3 become SS-mode MMAs (A and B descriptors), stage 1 / 4 stay TS-mode (DFT-128 in TMEM).
+#pragma once
+#include "fwd_r128.cuh"
+
+namespace bffc {
+namespace r128 {
+
+constexpr int kThreads3 = 384;
+constexpr int kPipes3 = 3;
+constexpr int kSmemData3 = kPipes3 * 2 * kSlotBytes;
+constexpr int kSmemBars3 = 128;
+constexpr int kSmemTotal3 = kSmemData3 + kSmemG + kSmemBars3 + 1024;
+
+// K-major, 128B-swizzled A operand tile (128 rows x 64 bf16): 8-row groups 1024 B apart
+DEVINL uint64_t atile_desc(uint32_t saddr) { return make_sdesc(saddr, 16, 1024, 2); }
+
+template <bool kPlanes, int kFmt>
+__global__ void __launch_bounds__(kThreads3, 1)
+fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_y,
+            const __grid_constant__ CUtensorMap tm_g, const FwdParams p) {
+  using NT = Num<kFmt>;
+  constexpr uint32_t ID_N128_MN = Idesc<kFmt>::N128_MN, ID_N64_MN = Idesc<kFmt>::N64_MN, ID_N64_MN_NEG = Idesc<kFmt>::N64_MN_NEG;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_g = sbase + kSmemData3;
+  const uint32_t s_bars = s_g + kSmemG;
+  uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
+
+  const int tid = threadIdx.x;
+  const int pipe = tid >> 7;           // one warpgroup = one pipeline
+  const int lane = tid & 127;          // TMEM lane (= k1, later = i)
+  const int warp_q = (tid >> 5) & 3;
+  const bool lead_warp = ((tid & 127) < 32);
+
+  const uint32_t bar_tma0 = s_bars + pipe * 24;
+  const uint32_t bar_mma = s_bars + pipe * 24 + 16;
+  const uint32_t s_tmemptr = s_bars + 96;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_u);
+    tma_prefetch_desc(&tm_y);
+    if (kPlanes) tma_prefetch_desc(&tm_g);
+  }
+  if ((tid & 127) == 0) {
+    mbar_init(bar_tma0, 1);
+    mbar_init(bar_tma0 + 8, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (tid < 32) {
+    tmem_alloc(s_tmemptr, 512);
+    tmem_relinquish();
+  }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.gtiles);
+    uint4* dst = reinterpret_cast<uint4*>(gen_base + kSmemData3);
+    for (int i = tid; i < kSmemG / 16; i += kThreads3) dst[i] = src[i];
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + kSmemData3 + kSmemG + 96);
+  const uint32_t tlane = tmem_base + (uint32_t(warp_q * 32) << 16);
+
+  // DFT-128 -> TMEM: pipeline 0 loads cos, pipeline 1 sin (64 columns each)
+  if (pipe < 2) {
+    const uint4* row = reinterpret_cast<const uint4*>((pipe == 0 ? p.dftC : p.dftS) + lane * 128);
+    const uint32_t tcol = tlane + (pipe == 0 ? kColC : kColS);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t v[16];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        uint4 w = row[q * 4 + r];
+        v[4 * r + 0] = w.x; v[4 * r + 1] = w.y; v[4 * r + 2] = w.z; v[4 * r + 3] = w.w;
+      }
+      tmem_st16(tcol + 16 * q, v);
+    }
+    tmem_st_wait();
+  }
+  // twiddles W_N^{k1*j}, j = 2q + {0,1}, q = 0..31
+  __half2 twc[32], tws[32];
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    float s0, c0, s1, c1;
+    sincospif(-2.0f * float((lane * (2 * q)) & 8191) / 8192.0f, &s0, &c0);
+    sincospif(-2.0f * float((lane * (2 * q + 1)) & 8191) / 8192.0f, &s1, &c1);
+    twc[q] = __floats2half2_rn(c0, c1);
+    tws[q] = __floats2half2_rn(s0, s1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const int gp = blockIdx.x * kPipes3 + pipe;
+  const int GP = gridDim.x * kPipes3;
+  const int u_begin = int((long long)p.units * gp / GP);
+  const int u_end = int((long long)p.units * (gp + 1) / GP);
+
+  const uint32_t s_slot0 = sbase + pipe * 2 * kSlotBytes;
+  const uint32_t tD = tlane + 128 + 128 * pipe;
+  const uint32_t tD0 = tmem_base + 128 + 128 * pipe;
+  const uint32_t tC0 = tmem_base + kColC;
+  const uint32_t tS0 = tmem_base + kColS;
+  const uint32_t bar_id = 1 + pipe;
+  const uint32_t sG0 = s_g;
+  const f32x2 kfs2 = pk2(p.kf_scale, p.kf_scale);
+
+  auto seq_index = [&](int unit, int which) {
+    const int h = unit / p.pairs, pr = unit - h * p.pairs;
+    if (kPlanes) return pr * p.H + h;
+    int b = 2 * pr + which;
+    if (b >= p.B) b = p.B - 1;
+    return b * p.H + h;
+  };
+  auto issue_load = [&](int unit, int slot) {
+    const uint32_t bar = bar_tma0 + 8 * slot;
+    const uint32_t dst = s_slot0 + slot * kSlotBytes;
+    mbar_expect_tx(bar, kSlotBytes);
+    tma_load_3d(dst, &tm_u, bar, 0, 0, seq_index(unit, 0));
+    tma_load_3d(dst + kTileBytes, kPlanes ? &tm_g : &tm_u, bar, 0, 0, seq_index(unit, 1));
+  };
+  uint32_t mma_phase = 0;
+  auto wait_mma = [&]() {
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+  };
+  // hand the freshly written smem operand tiles to the MMA issuer
+  auto sync_pipe_smem = [&]() {
+    fence_proxy_async_smem();
+    tc_fence_before();
+    named_bar_sync(bar_id, 128);
+  };
+  // row `lane` of the (re, im) tile pair: 16-byte chunk `chunk` (8 columns)
+  auto store_chunk = [&](uint32_t sX, int chunk, const uint32_t* re4, const uint32_t* im4) {
+    const uint32_t off = uint32_t(lane) * 128u + (uint32_t(chunk ^ (lane & 7)) << 4);
+    st_shared_v4(sX + off, re4[0], re4[1], re4[2], re4[3]);
+    st_shared_v4(sX + kTileBytes + off, im4[0], im4[1], im4[2], im4[3]);
+  };
+
+  if (lead_warp && u_begin < u_end) {
+    if (elect_one()) issue_load(u_begin, 0);
+    __syncwarp();
+  }
+
+  for (int unit = u_begin, n = 0; unit < u_end; ++unit, ++n) {
+    const int slot = n & 1;
+    const uint32_t sX = s_slot0 + slot * kSlotBytes;
+    const int h = unit / p.pairs;
+
+    // ---------------- stage 1 (TS): D1 = F128 * X
+    if (lead_warp) {
+      mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        for (int s = 0; s < p.ksteps; ++s) mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, s > 0);
+        for (int s = 0; s < p.ksteps; ++s) mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN, 1);
+        for (int s = 0; s < p.ksteps; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN_NEG, 1);
+        mma_commit(bar_mma);
+      }
+      __syncwarp();
+    }
+    wait_mma();
+
+    // ---------------- pass 1: * W^{k1 j} -> A1 tiles in the slot (K-major: row = lane, column = j)
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      uint32_t re[16], im[16];
+      tmem_ld16(tD + 16 * sub, re);
+      tmem_ld16(tD + 64 + 16 * sub, im);
+      tmem_ld_wait();
+      reg_fence(re); reg_fence(im);
+      uint32_t ore[8], oim[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float2 c = __half22float2(twc[8 * sub + q]), sn = __half22float2(tws[8 * sub + q]);
+        f32x2 vr, vi;
+        cmul2(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), pk2(c.x, c.y), pk2(sn.x, sn.y), vr, vi);
+        ore[q] = NT::pack_v(vr);
+        oim[q] = NT::pack_v(vi);
+      }
+      store_chunk(sX, 2 * sub, ore, oim);
+      store_chunk(sX, 2 * sub + 1, ore + 4, oim + 4);
+    }
+    sync_pipe_smem();
+    // ---------------- stage 2 (SS): D[:,0:128] = re * [Gr | Gi] + im * [-Gi | Gr]
+    if (lead_warp) {
+      tc_fence_after();
+      if (elect_one()) {
+        for (int s = 0; s < 4; ++s)
+          mma_ss(tD0, atile_desc(sX + 32 * s), pair_desc(sG0 + s * 2048, 8192), ID_N128_MN, s > 0);
+        for (int s = 0; s < 4; ++s)
+          mma_ss(tD0, atile_desc(sX + kTileBytes + 32 * s), pair_desc(sG0 + 16384 + s * 2048, 8192), ID_N128_MN, 1);
+        mma_commit(bar_mma);
+        if (unit + 1 < u_end) {
+          tma_store_wait_read0();
+          issue_load(unit + 1, slot ^ 1);
+        }
+      }
+      __syncwarp();
+    }
+    const uint4* kfp = reinterpret_cast<const uint4*>(p.kf) + size_t(h) * 16 * 128 + lane;
+    uint4 kfv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) kfv[c] = __ldg(kfp + c * 128);
+    wait_mma();
+
+    // ---------------- pass 3: * k_f -> A3 tiles
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      uint32_t re[16], im[16];
+      tmem_ld16(tD + 16 * sub, re);
+      tmem_ld16(tD + 64 + 16 * sub, im);
+      uint4 kn[4];
+      if (sub < 3) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) kn[c] = __ldg(kfp + (4 * (sub + 1) + c) * 128);
+      }
+      tmem_ld_wait();
+      reg_fence(re); reg_fence(im);
+      uint32_t ore[8], oim[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint4 kq = kfv[q >> 1];
+        const uint32_t wr = (q & 1) ? kq.z : kq.x, wi = (q & 1) ? kq.w : kq.y;
+        f32x2 vr, vi;
+        f32x2 kr2 = NT::unpack(wr), ki2 = NT::unpack(wi);
+        if (kFmt == 0) { kr2 = mul2(kr2, kfs2); ki2 = mul2(ki2, kfs2); }
+        cmul2(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), kr2, ki2, vr, vi);
+        ore[q] = NT::pack_v(vr);
+        oim[q] = NT::pack_v(vi);
+      }
+      store_chunk(sX, 2 * sub, ore, oim);
+      store_chunk(sX, 2 * sub + 1, ore + 4, oim + 4);
+      if (sub < 3) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) kfv[c] = kn[c];
+      }
+    }
+    sync_pipe_smem();
+    // ---------------- stage 3 (SS): inverse radix-64
+    if (lead_warp) {
+      tc_fence_after();
+      if (elect_one()) {
+        for (int s = 0; s < 4; ++s)
+          mma_ss(tD0, atile_desc(sX + 32 * s), pair_desc(sG0 + s * 2048, 16384), ID_N128_MN, s > 0);
+        for (int s = 0; s < 4; ++s)
+          mma_ss(tD0, atile_desc(sX + kTileBytes + 32 * s), pair_desc(sG0 + 8192 + s * 2048, 16384), ID_N128_MN, 1);
+        mma_commit(bar_mma);
+      }
+      __syncwarp();
+    }
+    wait_mma();
+
+    // ---------------- pass 5: * conj W -> Y tiles (MN-major B operand of stage 4; same bytes as a K-major A tile)
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      uint32_t re[16], im[16];
+      tmem_ld16(tD + 16 * sub, re);
+      tmem_ld16(tD + 64 + 16 * sub, im);
+      tmem_ld_wait();
+      reg_fence(re); reg_fence(im);
+      uint32_t ore[8], oim[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float2 c = __half22float2(twc[8 * sub + q]), sn = __half22float2(tws[8 * sub + q]);
+        f32x2 vr, vi;
+        cmul2_conj(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), pk2(c.x, c.y), pk2(sn.x, sn.y), vr, vi);
+        ore[q] = NT::pack_v(vr);
+        oim[q] = NT::pack_v(vi);
+      }
+      store_chunk(sX, 2 * sub, ore, oim);
+      store_chunk(sX, 2 * sub + 1, ore + 4, oim + 4);
+    }
+    sync_pipe_smem();
+    // ---------------- stage 4 (TS): conj F128 * Y
+    if (lead_warp) {
+      tc_fence_after();
+      if (elect_one()) {
+        for (int s = 0; s < 8; ++s) mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, s > 0);
+        for (int s = 0; s < 8; ++s) mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN_NEG, 1);
+        for (int s = 0; s < 8; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN, 1);
+        mma_commit(bar_mma);
+      }
+      __syncwarp();
+    }
+    wait_mma();
+
+    // ---------------- pass 6: fp32 -> 16 bit output tiles, TMA store
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      uint32_t re[16], im[16];
+      tmem_ld16(tD + 16 * sub, re);
+      tmem_ld16(tD + 64 + 16 * sub, im);
+      tmem_ld_wait();
+      reg_fence(re); reg_fence(im);
+      uint32_t ore[8], oim[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        ore[q] = NT::pack(__uint_as_float(re[2 * q]), __uint_as_float(re[2 * q + 1]));
+        oim[q] = NT::pack(__uint_as_float(im[2 * q]), __uint_as_float(im[2 * q + 1]));
+      }
+      store_chunk(sX, 2 * sub, ore, oim);
+      store_chunk(sX, 2 * sub + 1, ore + 4, oim + 4);
+    }
+    sync_pipe_smem();
+    if (lead_warp) {
+      if (elect_one()) {
+        const int pr = unit - h * p.pairs;
+        tma_store_3d(&tm_y, sX, 0, 0, seq_index(unit, 0));
+        if (kPlanes) tma_store_3d(&tm_g, sX + kTileBytes, 0, 0, seq_index(unit, 1));
+        else if (2 * pr + 1 < p.B) tma_store_3d(&tm_y, sX + kTileBytes, 0, 0, seq_index(unit, 1));
+        tma_store_commit();
+      }
+      __syncwarp();
+    }
+  }
+
+  if (lead_warp) tma_store_wait_all0();
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace r128
+}  // namespace bffc

@@ -32,6 +32,7 @@ struct FwdParams {
   const __nv_bfloat16* dftC; // [128][128] cos(2*pi*m*k/128)
   const __nv_bfloat16* dftS; // [128][128] sin(2*pi*m*k/128)
   const uint8_t* gtiles;     // DFT-64 tiles Gr, Gi, -Gi, Gr: each 64 rows x 128 B, 128B-swizzled image
+  float kf_scale;            // fp16 only: k_f is stored unscaled (1/N would underflow fp16) and scaled here in fp32
   const uint32_t* pregate;   // optional (B,H,L) bf16, or null
   const uint32_t* postgate;
   int B, H, L;               // batch, channels, sequence length
@@ -189,6 +190,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   const uint32_t tS0 = tmem_base + kColS;
   const uint32_t bar_id = 1 + pipe;
   const uint32_t sG0 = s_g;   // tiles: +0 Gr, +8K Gi, +16K -Gi, +24K Gr
+  const f32x2 kfs2 = pk2(p.kf_scale, p.kf_scale);
 
   auto seq_index = [&](int unit, int which) {   // global sequence index (b*H + h) of the re / im member
     const int h = unit / p.pairs, pr = unit - h * p.pairs;
@@ -349,7 +351,9 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
         const uint4 kq = kfv[4 * sub + (q >> 1)];
         const uint32_t wr = (q & 1) ? kq.z : kq.x, wi = (q & 1) ? kq.w : kq.y;
         f32x2 vr, vi;
-        cmul2(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), NT::unpack(wr), NT::unpack(wi), vr, vi);
+        f32x2 kr2 = NT::unpack(wr), ki2 = NT::unpack(wi);
+        if (kFmt == 0) { kr2 = mul2(kr2, kfs2); ki2 = mul2(ki2, kfs2); }
+        cmul2(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), kr2, ki2, vr, vi);
         ore[q] = NT::pack_v(vr);
         oim[q] = NT::pack_v(vi);
       }
