@@ -388,7 +388,9 @@ int bffc_dkf_unpack(const bffc_plan* p, const void* dkf_engine, void* dkf_natura
   dim3 grid(64, H);
   bffc::r128::dkf_unpack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float2*>(dkf_engine), static_cast<float2*>(dkf_natural), p->NE,
-      p->nlev >= 1 ? p->lev[0].R : 1, p->nlev >= 2 ? p->lev[1].R : 1);
+      p->nlev >= 1 ? p->lev[0].R : 1, p->nlev >= 2 ? p->lev[1].R : 1,
+      // fp16: both spectra carry 1/sqrt(128) (fused kernel) and 1/sqrt(R) per outer level: undo the product
+      p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 128.0f * float(p->R));
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -431,7 +433,12 @@ static void fill_params(const bffc_plan* p, bffc::FwdParams& prm, const void* kf
   prm.dftC = p->dftC;
   prm.dftS = p->dftS;
   prm.gtiles = p->gtiles;
-  prm.kf_scale = 1.0f / float(p->NE);   // applied in-kernel for fp16 only (bf16 k_f is pre-scaled by the pack kernel)
+  // Normalisation.  bf16: the whole 1/N is folded into k_f by the pack kernel (as the reference folds it into a
+  // twiddle table, conv.py:146).  fp16 cannot hold k_f/N (underflow): every DFT stage is scaled by 1/sqrt(radix)
+  // instead so intermediates stay near the input level: 1/sqrt(128) in the twiddle tables (passes 1 and 5),
+  // 1/64 with the (unscaled) k_f in pass 3, 1/sqrt(R) per direction in the outer stages.
+  prm.kf_scale = 1.0f / 64.0f;
+  prm.tw_scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 0.08838834764831845f;
   prm.pregate = nullptr;
   prm.postgate = nullptr;
   prm.dbg = nullptr;
@@ -565,6 +572,7 @@ static int tc_stage(const bffc_plan* p, bool inverse, const void* x, const void*
   prm.dftC = p->dftC; prm.dftS = p->dftS;
   prm.postgate = inverse ? static_cast<const uint32_t*>(gate) : nullptr;
   prm.has_pregate = (!inverse && gate) ? 1 : 0;
+  prm.tw_scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 0.08838834764831845f;
   prm.B = B; prm.H = H; prm.L = L; prm.pairs = pairs;
   prm.N = p->N; prm.M = M; prm.chunks = chunks;
   prm.ksteps = (L / M + 15) / 16;
@@ -601,6 +609,7 @@ static int transform_fwd(const bffc_plan* p, const void* x, const void* pregate,
     op.pregate = static_cast<const uint4*>(pregate);
     op.pre = reinterpret_cast<uint4*>(s0.re); op.pim = reinterpret_cast<uint4*>(s0.im);
     op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / l0.R;
+    op.scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 1.0f / sqrtf(float(l0.R));
     if (int rc = cc_stage(l0.R, false, pregate != nullptr, false, op, 0, st)) return rc;
   }
   *launches += 1;
@@ -611,6 +620,7 @@ static int transform_fwd(const bffc_plan* p, const void* x, const void* pregate,
     op.xre = reinterpret_cast<uint4*>(s0.re); op.xim = reinterpret_cast<uint4*>(s0.im);
     op.pre = reinterpret_cast<uint4*>(s1.re); op.pim = reinterpret_cast<uint4*>(s1.im);
     op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / (l0.R * l1.R);
+    op.scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 1.0f / sqrtf(float(l1.R));
     if (int rc = cc_stage(l1.R, false, false, true, op, pairs * H * l0.R, st)) return rc;
     *launches += 1;
     *out = s1;
@@ -629,6 +639,7 @@ static int transform_inv(const bffc_plan* p, void* y, const void* postgate, int 
     op.xre = reinterpret_cast<uint4*>(s0.re); op.xim = reinterpret_cast<uint4*>(s0.im);
     op.pre = reinterpret_cast<uint4*>(s1.re); op.pim = reinterpret_cast<uint4*>(s1.im);
     op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / (l0.R * l1.R);
+    op.scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 1.0f / sqrtf(float(l1.R));
     if (int rc = cc_stage(l1.R, true, false, true, op, pairs * H * l0.R, st)) return rc;
     *launches += 1;
   }
@@ -640,6 +651,7 @@ static int transform_inv(const bffc_plan* p, void* y, const void* postgate, int 
     op.postgate = static_cast<const uint4*>(postgate);
     op.pre = reinterpret_cast<uint4*>(s0.re); op.pim = reinterpret_cast<uint4*>(s0.im);
     op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / l0.R;
+    op.scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 1.0f / sqrtf(float(l0.R));
     if (int rc = cc_stage(l0.R, true, postgate != nullptr, false, op, 0, st)) return rc;
   }
   *launches += 1;
@@ -745,6 +757,7 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
   prm.gtiles = p->gtiles;
   prm.dkf = static_cast<float2*>(dkf);
   prm.pairs = pairs;
+  prm.tw_scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 0.08838834764831845f;
   using namespace bffc::r128;
   if (p->nlev == 0) {
     if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen 8192 in this build", L);

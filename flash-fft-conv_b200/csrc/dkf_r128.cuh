@@ -27,6 +27,7 @@ struct DkfParams {
   const uint8_t* gtiles;
   float2* dkf;               // [H][4][128][16] complex fp32: k2 = 16*q + t, frequency k = k1 + 128*k2
   int B, H, L, pairs, ksteps;
+  float tw_scale;            // see FwdParams::tw_scale; dkf_unpack compensates
   int gated;                 // 1: u is multiplied by pregate and dout by postgate on load (tm_ui / tm_di = gate maps)
 };
 
@@ -108,8 +109,8 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
     float s0, c0, s1, c1;
     sincospif(-2.0f * float((lane * (32 * half + 2 * q)) & 8191) / 8192.0f, &s0, &c0);
     sincospif(-2.0f * float((lane * (32 * half + 2 * q + 1)) & 8191) / 8192.0f, &s1, &c1);
-    twc[q] = __floats2half2_rn(c0, c1);
-    tws[q] = __floats2half2_rn(s0, s1);
+    twc[q] = __floats2half2_rn(c0 * p.tw_scale, c1 * p.tw_scale);
+    tws[q] = __floats2half2_rn(s0 * p.tw_scale, s1 * p.tw_scale);
   }
   tc_fence_before();
   __syncthreads();
@@ -285,14 +286,16 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
 
 // dk_f engine order -> natural order complex64 (reference analogue: the inverse permutation at conv.py:1818).
 // Composite sizes: channel row (h*R0 + c0)*R1 + c1 holds frequencies k = c0 + R0*(c1 + R1*(k1 + 128*k2)).
-__global__ void dkf_unpack_kernel(const float2* __restrict__ eng, float2* __restrict__ nat, int N, int R0, int R1) {
+__global__ void dkf_unpack_kernel(const float2* __restrict__ eng, float2* __restrict__ nat, int N, int R0, int R1,
+                                  float scale) {
   const int h = blockIdx.y;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
     const int c0 = k % R0, r0 = k / R0;
     const int c1 = r0 % R1, kk = r0 / R1;
     const int k1 = kk & 127, k2 = kk >> 7;
     const size_t row = (size_t(h) * R0 + c0) * R1 + c1;
-    nat[size_t(h) * N + k] = eng[((row * 4 + (k2 >> 4)) * 128 + k1) * 16 + (k2 & 15)];
+    const float2 v = eng[((row * 4 + (k2 >> 4)) * 128 + k1) * 16 + (k2 & 15)];
+    nat[size_t(h) * N + k] = make_float2(v.x * scale, v.y * scale);
   }
 }
 

@@ -93,8 +93,8 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     float s0, c0, s1, c1;
     sincospif(-2.0f * float((lane * (2 * q)) & 8191) / 8192.0f, &s0, &c0);
     sincospif(-2.0f * float((lane * (2 * q + 1)) & 8191) / 8192.0f, &s1, &c1);
-    twc[q] = __floats2half2_rn(c0, c1);
-    tws[q] = __floats2half2_rn(s0, s1);
+    twc[q] = __floats2half2_rn(c0 * p.tw_scale, c1 * p.tw_scale);
+    tws[q] = __floats2half2_rn(s0 * p.tw_scale, s1 * p.tw_scale);
   }
   tc_fence_before();
   __syncthreads();

@@ -33,6 +33,7 @@ struct FwdParams {
   const __nv_bfloat16* dftS; // [128][128] sin(2*pi*m*k/128)
   const uint8_t* gtiles;     // DFT-64 tiles Gr, Gi, -Gi, Gr: each 64 rows x 128 B, 128B-swizzled image
   float kf_scale;            // fp16 only: k_f is stored unscaled (1/N would underflow fp16) and scaled here in fp32
+  float tw_scale;            // folded into the twiddle table (fp16: 1/sqrt(128) keeps every stage near the input level)
   const uint32_t* pregate;   // optional (B,H,L) bf16, or null
   const uint32_t* postgate;
   int B, H, L;               // batch, channels, sequence length
@@ -167,8 +168,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
     float s0, c0, s1, c1;
     sincospif(-2.0f * float((lane * (32 * half + 2 * q)) & 8191) / 8192.0f, &s0, &c0);
     sincospif(-2.0f * float((lane * (32 * half + 2 * q + 1)) & 8191) / 8192.0f, &s1, &c1);
-    twc[q] = __floats2half2_rn(c0, c1);
-    tws[q] = __floats2half2_rn(s0, s1);
+    twc[q] = __floats2half2_rn(c0 * p.tw_scale, c1 * p.tw_scale);
+    tws[q] = __floats2half2_rn(s0 * p.tw_scale, s1 * p.tw_scale);
   }
 
   tc_fence_before();

@@ -46,6 +46,7 @@ struct OuterParams {
   uint4* pim;            // inner-side planes: imaginary parts
   int B, H, L, pairs;
   int M;                 // inner row length
+  float scale;           // applied to this stage's output (fp16: 1/sqrt(R) per direction; bf16: 1, 1/N lives in k_f)
 };
 
 // W_R^{a c} for R <= 8 as exact constants
@@ -122,8 +123,8 @@ __global__ void __launch_bounds__(128, (R <= 4) ? 4 : 2) fwd_kernel(const OuterP
     float or_[8], oi_[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-      or_[t] = vr[t] * wc[t] - vi[t] * ws[t];
-      oi_[t] = vr[t] * ws[t] + vi[t] * wc[t];
+      or_[t] = (vr[t] * wc[t] - vi[t] * ws[t]) * p.scale;
+      oi_[t] = (vr[t] * ws[t] + vi[t] * wc[t]) * p.scale;
       const float nc = wc[t] * w1c[t] - ws[t] * w1s[t];   // w_{c+1} = w_c * w_1
       ws[t] = wc[t] * w1s[t] + ws[t] * w1c[t];
       wc[t] = nc;
@@ -181,6 +182,8 @@ __global__ void __launch_bounds__(128, (R <= 4) ? 4 : 2) inv_kernel(const OuterP
           yi[t] += tr[c][t] * fs + ti[c][t] * fc;
         }
       }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { yr[t] *= p.scale; yi[t] *= p.scale; }
       if (kPlanes) {
         const size_t o = (size_t(blockIdx.x) * R * kM + n) / kVec;
         p.xre[o] = pack8<kFmt>(yr);

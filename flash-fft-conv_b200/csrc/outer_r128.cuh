@@ -23,6 +23,7 @@ struct OuterTcParams {
   const __nv_bfloat16* dftS;
   const uint32_t* postgate;   // inverse only, (B,H,L) bf16 or null
   int has_pregate;            // forward only: tm_g is the pregate map
+  float tw_scale;             // folded into the twiddle table (fp16: 1/sqrt(128))
   int B, H, L, pairs;
   int N, M, chunks;           // M = N/128, chunks = M/64
   int ksteps;                 // 16-row K steps of the [128][M] view that are non-zero: ceil(L/M/16)
@@ -108,8 +109,8 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
     float s0, c0, s1, c1;
     sincospif(-float(lane * (32 * half + 2 * q)) * invN2, &s0, &c0);
     sincospif(-float(lane * (32 * half + 2 * q + 1)) * invN2, &s1, &c1);
-    twc[q] = __floats2half2_rn(c0, c1);
-    tws[q] = __floats2half2_rn(s0, s1);
+    twc[q] = __floats2half2_rn(c0 * p.tw_scale, c1 * p.tw_scale);
+    tws[q] = __floats2half2_rn(s0 * p.tw_scale, s1 * p.tw_scale);
   }
   tc_fence_before();
   __syncthreads();

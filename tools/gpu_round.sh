@@ -8,6 +8,6 @@ done
 timeout 300 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/bench_ref.json 2>> gpurun_out/bench_ref.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_c2.csv \
   python bench.py --steps 3 --warmup 3 > gpurun_out/launches_c2.log 2>&1
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:fwd_kernel -s 1 -c 1 -f -o gpurun_out/prof_fwd8k \
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:fwd3_kernel -s 1 -c 1 -f -o gpurun_out/prof_fwd8k \
   python tools/prof_fwd.py > gpurun_out/prof.log 2>&1
 cat gpurun_out/tests.log; for w in c2 c3 c4 c5; do head -c 600 gpurun_out/bench_$w.json; echo; tail -2 gpurun_out/bench_$w.err; done
