@@ -526,6 +526,13 @@ static int make_map4(CUtensorMap* map, const void* base, int chunks, int rows, i
 
 struct PlaneSet { uint8_t* re; uint8_t* im; };
 
+static void fill_step(bffc::outer::OuterParams& op, double n_level) {
+  for (int t = 0; t < 8; ++t) {
+    const double ang = -2.0 * 3.14159265358979323846 * t / n_level;
+    op.step[t] = make_float2(float(cos(ang)), float(sin(ang)));
+  }
+}
+
 template <int R, int F>
 static void launch_cc(bool inverse, bool gated, bool planes, const bffc::outer::OuterParams& op, int rows, cudaStream_t st) {
   using namespace bffc::outer;
@@ -610,6 +617,7 @@ static int transform_fwd(const bffc_plan* p, const void* x, const void* pregate,
     op.pre = reinterpret_cast<uint4*>(s0.re); op.pim = reinterpret_cast<uint4*>(s0.im);
     op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / l0.R;
     op.scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 1.0f / sqrtf(float(l0.R));
+    fill_step(op, double(p->N));
     if (int rc = cc_stage(l0.R, false, pregate != nullptr, false, op, 0, st)) return rc;
   }
   *launches += 1;
@@ -621,6 +629,7 @@ static int transform_fwd(const bffc_plan* p, const void* x, const void* pregate,
     op.pre = reinterpret_cast<uint4*>(s1.re); op.pim = reinterpret_cast<uint4*>(s1.im);
     op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / (l0.R * l1.R);
     op.scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 1.0f / sqrtf(float(l1.R));
+    fill_step(op, double(p->N) / l0.R);
     if (int rc = cc_stage(l1.R, false, false, true, op, pairs * H * l0.R, st)) return rc;
     *launches += 1;
     *out = s1;
@@ -640,6 +649,7 @@ static int transform_inv(const bffc_plan* p, void* y, const void* postgate, int 
     op.pre = reinterpret_cast<uint4*>(s1.re); op.pim = reinterpret_cast<uint4*>(s1.im);
     op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / (l0.R * l1.R);
     op.scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 1.0f / sqrtf(float(l1.R));
+    fill_step(op, double(p->N) / l0.R);
     if (int rc = cc_stage(l1.R, true, false, true, op, pairs * H * l0.R, st)) return rc;
     *launches += 1;
   }
@@ -652,6 +662,7 @@ static int transform_inv(const bffc_plan* p, void* y, const void* postgate, int 
     op.pre = reinterpret_cast<uint4*>(s0.re); op.pim = reinterpret_cast<uint4*>(s0.im);
     op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / l0.R;
     op.scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 1.0f / sqrtf(float(l0.R));
+    fill_step(op, double(p->N));
     if (int rc = cc_stage(l0.R, true, postgate != nullptr, false, op, 0, st)) return rc;
   }
   *launches += 1;

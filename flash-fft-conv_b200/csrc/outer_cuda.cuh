@@ -46,6 +46,7 @@ struct OuterParams {
   uint4* pim;            // inner-side planes: imaginary parts
   int B, H, L, pairs;
   int M;                 // inner row length
+  float2 step[8];        // exp(-2 pi i t / (R*M)), t = 0..7: neighbour twiddle steps (host computed, double precision)
   float scale;           // applied to this stage's output (fp16: 1/sqrt(R) per direction; bf16: 1, 1/N lives in k_f)
 };
 
@@ -58,6 +59,50 @@ DEVINL void wr(int R, int e, float& c, float& s) {   // exp(-2 pi i e / R)
   c = cs[t]; s = sn[t];
 }
 
+DEVINL f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// v += z * exp(-2 pi i e8 / 8)   (e8 = eighths of a turn, a compile-time constant after unrolling)
+DEVINL void rot_acc(int e8, f32x2 zr, f32x2 zi, f32x2& vr, f32x2& vi) {
+  e8 &= 7;
+  const float h = 0.70710678118654752f;
+  if (e8 == 0) { vr = add2(vr, zr); vi = add2(vi, zi); }
+  else if (e8 == 2) { vr = add2(vr, zi); vi = sub2(vi, zr); }          // * (-i)
+  else if (e8 == 4) { vr = sub2(vr, zr); vi = sub2(vi, zi); }          // * (-1)
+  else if (e8 == 6) { vr = sub2(vr, zi); vi = add2(vi, zr); }          // * (+i)
+  else {
+    const float fc = (e8 == 1 || e8 == 7) ? h : -h, fs = (e8 == 1 || e8 == 3) ? -h : h;   // cos, sin of -2 pi e8/8
+    const f32x2 c2 = pk2(fc, fc), s2 = pk2(fs, fs), ns2 = pk2(-fs, -fs);
+    vr = fma2(zr, c2, fma2(zi, ns2, vr));
+    vi = fma2(zr, s2, fma2(zi, c2, vi));
+  }
+}
+
+template <int kFmt>
+DEVINL void unpack8v(const uint4& v, f32x2 (&f)[4]) {
+  f[0] = Num<kFmt>::unpack(v.x); f[1] = Num<kFmt>::unpack(v.y); f[2] = Num<kFmt>::unpack(v.z); f[3] = Num<kFmt>::unpack(v.w);
+}
+template <int kFmt>
+DEVINL uint4 pack8v(const f32x2 (&f)[4]) {
+  using NT = Num<kFmt>;
+  return make_uint4(NT::pack_v(f[0]), NT::pack_v(f[1]), NT::pack_v(f[2]), NT::pack_v(f[3]));
+}
+
+// twiddles of 8 consecutive positions: w1[t] = exp(sign * 2 pi i (np + t) / Nl), as 4 packed pairs.
+// One accurate sincos for position np, the other seven by the per-level constants step[t] = exp(sign 2 pi i t / Nl).
+DEVINL void twiddle8(int np, float inv_nl2, const float2* step, f32x2 (&wc)[4], f32x2 (&ws)[4]) {
+  float s0, c0;
+  sincospif(float(np) * inv_nl2, &s0, &c0);
+  float c[8], s[8];
+  c[0] = c0; s[0] = s0;
+#pragma unroll
+  for (int t = 1; t < 8; ++t) {
+    c[t] = c0 * step[t].x - s0 * step[t].y;
+    s[t] = c0 * step[t].y + s0 * step[t].x;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { wc[q] = pk2(c[2 * q], c[2 * q + 1]); ws[q] = pk2(s[2 * q], s[2 * q + 1]); }
+}
+
 // forward: grid (M / (kVec*blockDim.x), H, pairs)   [kPlanes: (rows, M / (kVec*blockDim.x), 1)]
 template <int R, bool kGated, bool kPlanes, int kFmt>
 __global__ void __launch_bounds__(128, (R <= 4) ? 4 : 2) fwd_kernel(const OuterParams p) {
@@ -66,7 +111,7 @@ __global__ void __launch_bounds__(128, (R <= 4) ? 4 : 2) fwd_kernel(const OuterP
   const int h = blockIdx.y, pr = blockIdx.z;
   const int b0 = 2 * pr, b1 = 2 * pr + 1;
   const size_t L8 = size_t(p.L) / kVec;
-  float zr[R][8], zi[R][8];
+  f32x2 zr[R][4], zi[R][4];
   int rows = 0;
 #pragma unroll
   for (int a = 0; a < R; ++a) {
@@ -74,64 +119,58 @@ __global__ void __launch_bounds__(128, (R <= 4) ? 4 : 2) fwd_kernel(const OuterP
     if (kPlanes) {
       rows = R;
       const size_t o = (size_t(blockIdx.x) * R * kM + n) / kVec;
-      unpack8<kFmt>(__ldg(p.xre + o), zr[a]);
-      unpack8<kFmt>(__ldg(p.xim + o), zi[a]);
+      unpack8v<kFmt>(__ldg(p.xre + o), zr[a]);
+      unpack8v<kFmt>(__ldg(p.xim + o), zi[a]);
     } else if (n < p.L) {
       rows = a + 1;
       const size_t o0 = (size_t(b0) * p.H + h) * L8 + n / kVec;
       uint4 v0 = __ldg(p.u + o0);
       if (kGated) v0 = hmul8<kFmt>(v0, __ldg(p.pregate + o0));
-      unpack8<kFmt>(v0, zr[a]);
+      unpack8v<kFmt>(v0, zr[a]);
       if (b1 < p.B) {
         const size_t o1 = (size_t(b1) * p.H + h) * L8 + n / kVec;
         uint4 v1 = __ldg(p.u + o1);
         if (kGated) v1 = hmul8<kFmt>(v1, __ldg(p.pregate + o1));
-        unpack8<kFmt>(v1, zi[a]);
+        unpack8v<kFmt>(v1, zi[a]);
       } else {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) zi[a][t] = 0.f;
+        for (int q = 0; q < 4; ++q) zi[a][q] = 0ull;
       }
     } else {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) { zr[a][t] = 0.f; zi[a][t] = 0.f; }
+      for (int q = 0; q < 4; ++q) { zr[a][q] = 0ull; zi[a][q] = 0ull; }
     }
   }
-  // w1[t] = W_N^{n'+t}
-  float w1c[8], w1s[8];
+  f32x2 w1c[4], w1s[4];                      // W_N^{n'+t}
+  twiddle8(np, -2.0f / float(R * kM), p.step, w1c, w1s);
+  f32x2 wc[4], ws[4];                        // running W_N^{(n'+t) c}, carrying the stage's output scale
 #pragma unroll
-  for (int t = 0; t < 8; ++t) sincospif(-2.0f * float(np + t) / float(R * kM), &w1s[t], &w1c[t]);
-  float wc[8], ws[8];
-#pragma unroll
-  for (int t = 0; t < 8; ++t) { wc[t] = 1.f; ws[t] = 0.f; }
+  for (int q = 0; q < 4; ++q) { wc[q] = pk2(p.scale, p.scale); ws[q] = 0ull; }
 #pragma unroll
   for (int c = 0; c < R; ++c) {
-    float vr[8], vi[8];
+    f32x2 vr[4], vi[4];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) { vr[t] = 0.f; vi[t] = 0.f; }
+    for (int q = 0; q < 4; ++q) { vr[q] = 0ull; vi[q] = 0ull; }
 #pragma unroll
     for (int a = 0; a < R; ++a) {
       if (a < rows) {
-        float fc, fs;
-        wr(R, a * c, fc, fs);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          vr[t] += zr[a][t] * fc - zi[a][t] * fs;
-          vi[t] += zr[a][t] * fs + zi[a][t] * fc;
-        }
+        for (int q = 0; q < 4; ++q) rot_acc((a * c % R) * (8 / R), zr[a][q], zi[a][q], vr[q], vi[q]);
       }
     }
-    float or_[8], oi_[8];
+    f32x2 orr[4], oii[4];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      or_[t] = (vr[t] * wc[t] - vi[t] * ws[t]) * p.scale;
-      oi_[t] = (vr[t] * ws[t] + vi[t] * wc[t]) * p.scale;
-      const float nc = wc[t] * w1c[t] - ws[t] * w1s[t];   // w_{c+1} = w_c * w_1
-      ws[t] = wc[t] * w1s[t] + ws[t] * w1c[t];
-      wc[t] = nc;
+    for (int q = 0; q < 4; ++q) {
+      cmul2(vr[q], vi[q], wc[q], ws[q], orr[q], oii[q]);
+      if (c + 1 < R) {
+        f32x2 nc, ns;
+        cmul2(wc[q], ws[q], w1c[q], w1s[q], nc, ns);   // w_{c+1} = w_c * w_1
+        wc[q] = nc; ws[q] = ns;
+      }
     }
     const size_t row = (kPlanes ? size_t(blockIdx.x) : (size_t(pr) * p.H + h)) * R + c;
-    p.pre[row * (kM / kVec) + np / kVec] = pack8<kFmt>(or_);
-    p.pim[row * (kM / kVec) + np / kVec] = pack8<kFmt>(oi_);
+    p.pre[row * (kM / kVec) + np / kVec] = pack8v<kFmt>(orr);
+    p.pim[row * (kM / kVec) + np / kVec] = pack8v<kFmt>(oii);
   }
 }
 
@@ -143,60 +182,56 @@ __global__ void __launch_bounds__(128, (R <= 4) ? 4 : 2) inv_kernel(const OuterP
   const int h = blockIdx.y, pr = blockIdx.z;
   const int b0 = 2 * pr, b1 = 2 * pr + 1;
   const size_t L8 = size_t(p.L) / kVec;
-  float w1c[8], w1s[8];
+  f32x2 w1c[4], w1s[4];                      // conj twiddle: exp(+2 pi i (n'+t) / N)
+  float2 stepc[8];
 #pragma unroll
-  for (int t = 0; t < 8; ++t) sincospif(2.0f * float(np + t) / float(R * kM), &w1s[t], &w1c[t]);   // conj twiddle
-  float wc[8], ws[8];
+  for (int t = 0; t < 8; ++t) stepc[t] = make_float2(p.step[t].x, -p.step[t].y);
+  twiddle8(np, 2.0f / float(R * kM), stepc, w1c, w1s);
+  f32x2 wc[4], ws[4];
 #pragma unroll
-  for (int t = 0; t < 8; ++t) { wc[t] = 1.f; ws[t] = 0.f; }
-  float tr[R][8], ti[R][8];
+  for (int q = 0; q < 4; ++q) { wc[q] = pk2(p.scale, p.scale); ws[q] = 0ull; }
+  f32x2 tr[R][4], ti[R][4];
 #pragma unroll
   for (int c = 0; c < R; ++c) {
     const size_t row = (kPlanes ? size_t(blockIdx.x) : (size_t(pr) * p.H + h)) * R + c;
-    float xr[8], xi[8];
-    unpack8<kFmt>(__ldg(p.pre + row * (kM / kVec) + np / kVec), xr);
-    unpack8<kFmt>(__ldg(p.pim + row * (kM / kVec) + np / kVec), xi);
+    f32x2 xr[4], xi[4];
+    unpack8v<kFmt>(__ldg(p.pre + row * (kM / kVec) + np / kVec), xr);
+    unpack8v<kFmt>(__ldg(p.pim + row * (kM / kVec) + np / kVec), xi);
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      tr[c][t] = xr[t] * wc[t] - xi[t] * ws[t];
-      ti[c][t] = xr[t] * ws[t] + xi[t] * wc[t];
-      const float nc = wc[t] * w1c[t] - ws[t] * w1s[t];
-      ws[t] = wc[t] * w1s[t] + ws[t] * w1c[t];
-      wc[t] = nc;
+    for (int q = 0; q < 4; ++q) {
+      cmul2(xr[q], xi[q], wc[q], ws[q], tr[c][q], ti[c][q]);
+      if (c + 1 < R) {
+        f32x2 nc, ns;
+        cmul2(wc[q], ws[q], w1c[q], w1s[q], nc, ns);
+        wc[q] = nc; ws[q] = ns;
+      }
     }
   }
 #pragma unroll
   for (int a = 0; a < R; ++a) {
     const int n = a * kM + np;
     if (kPlanes || n < p.L) {
-      float yr[8], yi[8];
+      f32x2 yr[4], yi[4];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) { yr[t] = 0.f; yi[t] = 0.f; }
+      for (int q = 0; q < 4; ++q) { yr[q] = 0ull; yi[q] = 0ull; }
 #pragma unroll
       for (int c = 0; c < R; ++c) {
-        float fc, fs;
-        wr(R, -a * c, fc, fs);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          yr[t] += tr[c][t] * fc - ti[c][t] * fs;
-          yi[t] += tr[c][t] * fs + ti[c][t] * fc;
-        }
+        for (int q = 0; q < 4; ++q) rot_acc(((R * R - a * c) % R) * (8 / R), tr[c][q], ti[c][q], yr[q], yi[q]);   // W_R^{-ac}
       }
-#pragma unroll
-      for (int t = 0; t < 8; ++t) { yr[t] *= p.scale; yi[t] *= p.scale; }
       if (kPlanes) {
         const size_t o = (size_t(blockIdx.x) * R * kM + n) / kVec;
-        p.xre[o] = pack8<kFmt>(yr);
-        p.xim[o] = pack8<kFmt>(yi);
+        p.xre[o] = pack8v<kFmt>(yr);
+        p.xim[o] = pack8v<kFmt>(yi);
         continue;
       }
       const size_t o0 = (size_t(b0) * p.H + h) * L8 + n / kVec;
-      uint4 v0 = pack8<kFmt>(yr);
+      uint4 v0 = pack8v<kFmt>(yr);
       if (kGated) v0 = hmul8<kFmt>(v0, __ldg(p.postgate + o0));
       p.y[o0] = v0;
       if (b1 < p.B) {
         const size_t o1 = (size_t(b1) * p.H + h) * L8 + n / kVec;
-        uint4 v1 = pack8<kFmt>(yi);
+        uint4 v1 = pack8v<kFmt>(yi);
         if (kGated) v1 = hmul8<kFmt>(v1, __ldg(p.postgate + o1));
         p.y[o1] = v1;
       }
