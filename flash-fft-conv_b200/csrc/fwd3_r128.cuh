@@ -86,16 +86,29 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     }
     tmem_st_wait();
   }
-  // twiddles W_N^{k1*j}, j = 2q + {0,1}, q = 0..31
-  __half2 twc[32], tws[32];
+  // twiddles W_N^{k1*j} (k1 = lane), factored as A[j >> 3] * B[j & 7]: B (8 columns, half2 pairs) is a table, A is
+  // advanced block by block with the per-lane step W_N^{8*k1} (fp32 recurrence over 8 blocks).  10 registers instead of
+  // 64: with the full shared-memory carve-out there is no L1 behind local memory, so spills cost an L2 round trip.
+  __half2 twBc[4], twBs[4];
+  float stc, sts;
+  sincospif(-2.0f * float(lane * 8) / 8192.0f, &sts, &stc);
 #pragma unroll
-  for (int q = 0; q < 32; ++q) {
+  for (int q = 0; q < 4; ++q) {
     float s0, c0, s1, c1;
-    sincospif(-2.0f * float((lane * (2 * q)) & 8191) / 8192.0f, &s0, &c0);
-    sincospif(-2.0f * float((lane * (2 * q + 1)) & 8191) / 8192.0f, &s1, &c1);
-    twc[q] = __floats2half2_rn(c0 * p.tw_scale, c1 * p.tw_scale);
-    tws[q] = __floats2half2_rn(s0 * p.tw_scale, s1 * p.tw_scale);
+    sincospif(-2.0f * float(lane * (2 * q)) / 8192.0f, &s0, &c0);
+    sincospif(-2.0f * float(lane * (2 * q + 1)) / 8192.0f, &s1, &c1);
+    twBc[q] = __floats2half2_rn(c0, c1);
+    twBs[q] = __floats2half2_rn(s0, s1);
   }
+  // twiddles of the four column pairs of one 8-column block whose block factor is (ac, as)
+  auto block_tw = [&](float ac, float as, f32x2 (&tc)[4], f32x2 (&ts)[4]) {
+    const f32x2 ac2 = pk2(ac, ac), as2 = pk2(as, as);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 bc = __half22float2(twBc[q]), bs = __half22float2(twBs[q]);
+      cmul2(ac2, as2, pk2(bc.x, bc.y), pk2(bs.x, bs.y), tc[q], ts[q]);
+    }
+  };
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -172,24 +185,31 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     wait_mma();
 
     // ---------------- pass 1: * W^{k1 j} -> A1 tiles in the slot (K-major: row = lane, column = j)
-#pragma unroll
+    {
+      float ac = p.tw_scale, as = 0.f;     // block factor W_N^{8*k1*block}
+#pragma unroll 1
     for (int sub = 0; sub < 4; ++sub) {
       uint32_t re[16], im[16];
       tmem_ld16(tD + 16 * sub, re);
       tmem_ld16(tD + 64 + 16 * sub, im);
       tmem_ld_wait();
       reg_fence(re); reg_fence(im);
-      uint32_t ore[8], oim[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float2 c = __half22float2(twc[8 * sub + q]), sn = __half22float2(tws[8 * sub + q]);
-        f32x2 vr, vi;
-        cmul2(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), pk2(c.x, c.y), pk2(sn.x, sn.y), vr, vi);
-        ore[q] = NT::pack_v(vr);
-        oim[q] = NT::pack_v(vi);
+      for (int blk = 0; blk < 2; ++blk) {
+        f32x2 tc[4], ts[4];
+        block_tw(ac, as, tc, ts);
+        uint32_t ore[4], oim[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          f32x2 vr, vi;
+          cmul2(pk2u(re[8 * blk + 2 * q], re[8 * blk + 2 * q + 1]), pk2u(im[8 * blk + 2 * q], im[8 * blk + 2 * q + 1]), tc[q], ts[q], vr, vi);
+          ore[q] = NT::pack_v(vr);
+          oim[q] = NT::pack_v(vi);
+        }
+        store_chunk(sX, 2 * sub + blk, ore, oim);
+        { const float nc = ac * stc - as * sts; as = ac * sts + as * stc; ac = nc; }
       }
-      store_chunk(sX, 2 * sub, ore, oim);
-      store_chunk(sX, 2 * sub + 1, ore + 4, oim + 4);
+    }
     }
     sync_pipe_smem();
     // ---------------- stage 2 (SS): D[:,0:128] = re * [Gr | Gi] + im * [-Gi | Gr]
@@ -208,42 +228,41 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
       }
       __syncwarp();
     }
+    // k_f of this lane: 16 vectors of 4 complex.  No L1 (see above): every load is an L2 round trip (~10 % of all stall
+    // samples when fetched inside pass 3, profiles/r1_v3).  The first half is fetched here, where nothing else is live
+    // (the MMA wait hides it), the second half at the start of pass 3 (hidden by the first half's arithmetic).
     const uint4* kfp = reinterpret_cast<const uint4*>(p.kf) + size_t(h) * 16 * 128 + lane;
-    uint4 kfv[4];
+    uint4 kfa[8], kfb[8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) kfv[c] = __ldg(kfp + c * 128);
+    for (int c = 0; c < 8; ++c) kfa[c] = __ldg(kfp + c * 128);
     wait_mma();
 
     // ---------------- pass 3: * k_f -> A3 tiles
 #pragma unroll
-    for (int sub = 0; sub < 4; ++sub) {
-      uint32_t re[16], im[16];
-      tmem_ld16(tD + 16 * sub, re);
-      tmem_ld16(tD + 64 + 16 * sub, im);
-      uint4 kn[4];
-      if (sub < 3) {
+    for (int c = 0; c < 8; ++c) kfb[c] = __ldg(kfp + (8 + c) * 128);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) kn[c] = __ldg(kfp + (4 * (sub + 1) + c) * 128);
-      }
-      tmem_ld_wait();
-      reg_fence(re); reg_fence(im);
-      uint32_t ore[8], oim[8];
+    for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const uint4 kq = kfv[q >> 1];
-        const uint32_t wr = (q & 1) ? kq.z : kq.x, wi = (q & 1) ? kq.w : kq.y;
-        f32x2 vr, vi;
-        f32x2 kr2 = NT::unpack(wr), ki2 = NT::unpack(wi);
-        if (kFmt == 0) { kr2 = mul2(kr2, kfs2); ki2 = mul2(ki2, kfs2); }
-        cmul2(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), kr2, ki2, vr, vi);
-        ore[q] = NT::pack_v(vr);
-        oim[q] = NT::pack_v(vi);
-      }
-      store_chunk(sX, 2 * sub, ore, oim);
-      store_chunk(sX, 2 * sub + 1, ore + 4, oim + 4);
-      if (sub < 3) {
+      for (int s4 = 0; s4 < 4; ++s4) {
+        const int sub = 4 * hf + s4;
+        uint32_t re[8], im[8];
+        tmem_ld8(tD + 8 * sub, re);
+        tmem_ld8(tD + 64 + 8 * sub, im);
+        tmem_ld_wait();
+        reg_fence(re); reg_fence(im);
+        uint32_t ore[4], oim[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) kfv[c] = kn[c];
+        for (int q = 0; q < 4; ++q) {
+          const uint4 kq = hf == 0 ? kfa[2 * s4 + (q >> 1)] : kfb[2 * s4 + (q >> 1)];
+          const uint32_t wr = (q & 1) ? kq.z : kq.x, wi = (q & 1) ? kq.w : kq.y;
+          f32x2 kr2 = NT::unpack(wr), ki2 = NT::unpack(wi);
+          if (kFmt == 0) { kr2 = mul2(kr2, kfs2); ki2 = mul2(ki2, kfs2); }
+          f32x2 vr, vi;
+          cmul2(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), kr2, ki2, vr, vi);
+          ore[q] = NT::pack_v(vr);
+          oim[q] = NT::pack_v(vi);
+        }
+        store_chunk(sX, sub, ore, oim);
       }
     }
     sync_pipe_smem();
@@ -262,24 +281,31 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     wait_mma();
 
     // ---------------- pass 5: * conj W -> Y tiles (MN-major B operand of stage 4; same bytes as a K-major A tile)
-#pragma unroll
+    {
+      float ac = p.tw_scale, as = 0.f;     // block factor W_N^{8*k1*block}
+#pragma unroll 1
     for (int sub = 0; sub < 4; ++sub) {
       uint32_t re[16], im[16];
       tmem_ld16(tD + 16 * sub, re);
       tmem_ld16(tD + 64 + 16 * sub, im);
       tmem_ld_wait();
       reg_fence(re); reg_fence(im);
-      uint32_t ore[8], oim[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float2 c = __half22float2(twc[8 * sub + q]), sn = __half22float2(tws[8 * sub + q]);
-        f32x2 vr, vi;
-        cmul2_conj(pk2u(re[2 * q], re[2 * q + 1]), pk2u(im[2 * q], im[2 * q + 1]), pk2(c.x, c.y), pk2(sn.x, sn.y), vr, vi);
-        ore[q] = NT::pack_v(vr);
-        oim[q] = NT::pack_v(vi);
+      for (int blk = 0; blk < 2; ++blk) {
+        f32x2 tc[4], ts[4];
+        block_tw(ac, as, tc, ts);
+        uint32_t ore[4], oim[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          f32x2 vr, vi;
+          cmul2_conj(pk2u(re[8 * blk + 2 * q], re[8 * blk + 2 * q + 1]), pk2u(im[8 * blk + 2 * q], im[8 * blk + 2 * q + 1]), tc[q], ts[q], vr, vi);
+          ore[q] = NT::pack_v(vr);
+          oim[q] = NT::pack_v(vi);
+        }
+        store_chunk(sX, 2 * sub + blk, ore, oim);
+        { const float nc = ac * stc - as * sts; as = ac * sts + as * stc; ac = nc; }
       }
-      store_chunk(sX, 2 * sub, ore, oim);
-      store_chunk(sX, 2 * sub + 1, ore + 4, oim + 4);
+    }
     }
     sync_pipe_smem();
     // ---------------- stage 4 (TS): conj F128 * Y
@@ -296,21 +322,25 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     wait_mma();
 
     // ---------------- pass 6: fp32 -> 16 bit output tiles, TMA store
-#pragma unroll
+    {
+#pragma unroll 1
     for (int sub = 0; sub < 4; ++sub) {
       uint32_t re[16], im[16];
       tmem_ld16(tD + 16 * sub, re);
       tmem_ld16(tD + 64 + 16 * sub, im);
       tmem_ld_wait();
       reg_fence(re); reg_fence(im);
-      uint32_t ore[8], oim[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        ore[q] = NT::pack(__uint_as_float(re[2 * q]), __uint_as_float(re[2 * q + 1]));
-        oim[q] = NT::pack(__uint_as_float(im[2 * q]), __uint_as_float(im[2 * q + 1]));
+      for (int blk = 0; blk < 2; ++blk) {
+        uint32_t ore[4], oim[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          ore[q] = NT::pack(__uint_as_float(re[8 * blk + 2 * q]), __uint_as_float(re[8 * blk + 2 * q + 1]));
+          oim[q] = NT::pack(__uint_as_float(im[8 * blk + 2 * q]), __uint_as_float(im[8 * blk + 2 * q + 1]));
+        }
+        store_chunk(sX, 2 * sub + blk, ore, oim);
       }
-      store_chunk(sX, 2 * sub, ore, oim);
-      store_chunk(sX, 2 * sub + 1, ore + 4, oim + 4);
+    }
     }
     sync_pipe_smem();
     if (lead_warp) {

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(512, 1) k_ld(int iters, int mode, long long* o
 
 // one thread issues `nmma` MMAs (M=128, N=ncols, K=16, A from TMEM, B from smem) then commit; measures cycles until the
 // mbarrier flips.  B contents irrelevant.
-__global__ void __launch_bounds__(128, 1) k_mma(int nmma, int ncols, int reps, long long* out) {
+__global__ void __launch_bounds__(128, 1) k_mma(int nmma, int ncols, int reps, int variant, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint32_t tptr;
   __shared__ __align__(8) unsigned long long bar;
@@ -74,17 +74,33 @@ __global__ void __launch_bounds__(128, 1) k_mma(int nmma, int ncols, int reps, l
   const uint32_t idesc = make_idesc(1, ncols, true, false);
   long long total = 0;
   uint32_t phase = 0;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
+   if (elect_one()) {      // same warp-uniform election pattern as the kernels (operands stay in uniform registers)
     for (int r = 0; r < reps; ++r) {
       long long t0 = clock64();
-      for (int s = 0; s < nmma; ++s)
-        mma_ts(tptr + 128, tptr + 8 * (s & 7), make_sdesc(sb + (s & 7) * 2048, 16384, 1024, 2), idesc, s > 0);
+      if (variant == 0) {          // one dependent accumulation chain
+        for (int s = 0; s < nmma; ++s)
+          mma_ts(tptr + 128, tptr + 8 * (s & 7), make_sdesc(sb + (s & 7) * 2048, 16384, 1024, 2), idesc, s > 0);
+      } else if (variant == 1) {   // two independent chains, interleaved
+        for (int s = 0; s < nmma; ++s)
+          mma_ts(tptr + 128 + 128 * (s & 1), tptr + 8 * (s & 7), make_sdesc(sb + (s & 7) * 2048, 16384, 1024, 2), idesc, s > 1);
+      } else if (variant == 2) {   // three independent chains
+        for (int s = 0; s < nmma; ++s)
+          mma_ts(tptr + 128 + 128 * (s % 3), tptr + 8 * (s & 7), make_sdesc(sb + (s & 7) * 2048, 16384, 1024, 2), idesc, s > 2);
+      } else {                     // one chain, descriptor arithmetic hoisted (constant descriptor / A address)
+        const uint64_t d0 = make_sdesc(sb, 16384, 1024, 2);
+        const uint32_t a0 = tptr, dd = tptr + 128;
+#pragma unroll 8
+        for (int s = 0; s < nmma; ++s) mma_ts(dd, a0, d0, idesc, 1);
+      }
       mma_commit(smem_u32(&bar));
       mbar_wait(smem_u32(&bar), phase);
       phase ^= 1;
       total += clock64() - t0;
     }
     out[0] = total / reps;
+   }
+   __syncwarp();
   }
   tc_fence_before(); __syncthreads();
   if (threadIdx.x < 32) tmem_dealloc(tptr, 512);
@@ -104,14 +120,16 @@ int main() {
       const double bytes = double(iters) * cols * 4 * 32 * warps;
       printf("%-22s warps=%2d  cycles/iter=%7.1f  bytes/clk/SM=%7.1f\n", names[mode], warps, double(h[0]) / iters, bytes / double(h[0]));
     }
-  cudaFuncSetAttribute(k_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
-  for (int ncols : {64, 128})
-    for (int nmma : {1, 4, 8, 16, 24}) {
-      k_mma<<<1, 128, 40000>>>(nmma, ncols, 50, d);
-      cudaDeviceSynchronize();
-      cudaMemcpy(h, d, 8, cudaMemcpyDeviceToHost);
-      printf("mma batch N=%3d count=%2d  cycles issue->barrier=%6lld  (model %d)\n", ncols, nmma, h[0], nmma * ncols / 2);
-    }
+  cudaFuncSetAttribute(k_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 100000);
+  for (int variant = 0; variant < 4; ++variant)
+    for (int ncols : {64, 128, 256})
+      for (int nmma : {1, 8, 24}) {
+        if (ncols == 256 && variant != 0 && variant != 3) continue;   // two 256-column tiles do not fit next to A
+        k_mma<<<1, 128, 100000>>>(nmma, ncols, 50, variant, d);
+        cudaDeviceSynchronize();
+        cudaMemcpy(h, d, 8, cudaMemcpyDeviceToHost);
+        printf("mma variant=%d N=%3d count=%2d  cycles issue->barrier=%6lld  (model %d)\n", variant, ncols, nmma, h[0], nmma * ncols / 2);
+      }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
