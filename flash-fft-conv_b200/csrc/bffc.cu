@@ -95,25 +95,35 @@ uint16_t f2bf(double x) {  // round-to-nearest-even float -> bf16 bits
   return static_cast<uint16_t>((u + r) >> 16);
 }
 
+// k_f -> engine order.  One thread produces one 16-byte engine vector = 4 consecutive inner frequencies k2 = 4cc..4cc+3
+// of one (row, k1): words (re k2, re k2+1) (im ..) (re k2+2, re k2+3) (im ..).  Reads are coalesced along k1
+// (stride R complex numbers), writes are fully coalesced.
 // kHalf: the source holds only frequencies 0..N/2 of a real filter (torch.fft.rfft); k > N/2 is conj(src[N-k]).
 template <bool kHalf, int kFmt>
-__global__ void kf_pack_kernel(const float* __restrict__ kf_nat, uint32_t* __restrict__ kf_eng,
-                               const int* __restrict__ perm, int N, int pair_stride, float scale, int conj) {
+__global__ void kf_pack_kernel(const float2* __restrict__ kf_nat, uint4* __restrict__ kf_eng, int N, int R0, int R1,
+                               float scale, int conj) {
   const int h = blockIdx.y;
-  const float* src = kf_nat + size_t(h) * (kHalf ? (N / 2 + 1) : N) * 2;      // interleaved (re, im) fp32
-  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < N; w += gridDim.x * blockDim.x) {
-    const int pw = perm[w];
-    const int part = pw & 1;
-    float v2[2];
+  const int R = R0 * R1;
+  const float2* src = kf_nat + size_t(h) * (kHalf ? (N / 2 + 1) : N);
+  const int nvec = N / 4;                              // engine vectors per channel
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
+    const int row = v / 2048, rem = v % 2048;          // 2048 vectors per 8192-word row
+    const int cc = rem >> 7, k1 = rem & 127;
+    const int c0 = row / R1, c1 = row % R1;
+    float2 e[4];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      int k = (pw >> 1) + e * pair_stride;               // natural frequency of this element
-      float sc = (part && conj) ? -scale : scale;
-      if (kHalf && k > N / 2) { k = N - k; if (part) sc = -sc; }
-      v2[e] = src[2 * k + part] * sc;
+    for (int i = 0; i < 4; ++i) {
+      int k = c0 + R0 * (c1 + R1 * (k1 + 128 * (4 * cc + i)));
+      float sg = conj ? -1.f : 1.f;
+      if (kHalf && k > N / 2) { k = N - k; sg = -sg; }
+      const float2 t = src[k];
+      e[i] = make_float2(t.x * scale, t.y * scale * sg);
     }
-    kf_eng[size_t(h) * N + w] = bffc::Num<kFmt>::pack(v2[0], v2[1]);
+    using NT = bffc::Num<kFmt>;
+    kf_eng[size_t(h) * nvec + v] = make_uint4(NT::pack(e[0].x, e[1].x), NT::pack(e[0].y, e[1].y),
+                                              NT::pack(e[2].x, e[3].x), NT::pack(e[2].y, e[3].y));
   }
+  (void)R;
 }
 
 // Tiled variant for a large outermost radix R0 (tcgen05 outer stage, R0 = 128): consecutive c0 are adjacent in the
@@ -211,7 +221,6 @@ struct bffc_plan {
   __nv_bfloat16* dftC = nullptr;
   __nv_bfloat16* dftS = nullptr;
   uint8_t* gtiles = nullptr;
-  int* perm = nullptr;  // engine word index -> 2 * natural frequency index + part
   int num_sms = 0;
 };
 
@@ -294,22 +303,9 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   CUDA_TRY(cudaMalloc(&p->gtiles, gt.size()));
   CUDA_TRY(cudaMemcpy(p->gtiles, gt.data(), gt.size(), cudaMemcpyHostToDevice));
 
-  // engine order (32-bit words), per channel h: R rows of 8192 words, row = c0*R1 + c1 (outer digits); inside a row
-  //   w = (cc*128 + k1)*4 + 2*pp + part  holds the bf16 pair (part ? imag : real) of k_f at inner frequencies
-  //   k'' = k1 + 128*k2 with k2 = 4cc + 2pp and k2 + 1; natural frequency k = c0 + R0*(c1 + R1*k'').
-  // perm[row*8192 + w] = 2 * (natural index of the first element) + part; the second element is 128*R further.
-  const int R0 = p->nlev >= 1 ? p->lev[0].R : 1, R1 = p->nlev >= 2 ? p->lev[1].R : 1;
-  std::vector<int> perm(p->NE);
-  for (int c0 = 0; c0 < R0; ++c0)
-    for (int c1 = 0; c1 < R1; ++c1)
-      for (int cc = 0; cc < 16; ++cc)
-        for (int k1 = 0; k1 < 128; ++k1)
-          for (int pp = 0; pp < 2; ++pp)
-            for (int part = 0; part < 2; ++part)
-              perm[(c0 * R1 + c1) * kInner + (cc * 128 + k1) * 4 + 2 * pp + part] =
-                  (c0 + R0 * (c1 + R1 * (k1 + 128 * (4 * cc + 2 * pp)))) * 2 + part;
-  CUDA_TRY(cudaMalloc(&p->perm, perm.size() * sizeof(int)));
-  CUDA_TRY(cudaMemcpy(p->perm, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice));
+  // engine order of k_f (32-bit words), per channel h: R rows of 8192 words, row = c0*R1 + c1 (outer digits); inside a
+  // row  w = (cc*128 + k1)*4 + 2*pp + part  holds the 16-bit pair (part ? imag : real) of k_f at inner frequencies
+  // k'' = k1 + 128*k2 with k2 = 4cc + 2pp and k2 + 1; natural frequency k = c0 + R0*(c1 + R1*k'').  See kf_pack_kernel.
 
   using namespace bffc::r128;
   FMT_SWITCH(dtype,
@@ -342,7 +338,6 @@ int bffc_plan_destroy(bffc_plan* p) {
   cudaFree(p->dftC);
   cudaFree(p->dftS);
   cudaFree(p->gtiles);
-  cudaFree(p->perm);
   delete p;
   return BFFC_OK;
 }
@@ -357,10 +352,10 @@ int bffc_kf_pack(const bffc_plan* p, const void* kf_natural, void* kf_engine, in
     CUDA_TRY(cudaGetLastError());
     return BFFC_OK;
   }
-  dim3 grid(64, H);
+  dim3 grid((p->NE / 4 + 255) / 256 > 32 ? 32 : (p->NE / 4 + 255) / 256, H);
   FMT_SWITCH(p->dtype, (kf_pack_kernel<false, F><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float*>(kf_natural), static_cast<uint32_t*>(kf_engine), p->perm, p->NE, 128 * p->R,
-      p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj)););
+      static_cast<const float2*>(kf_natural), static_cast<uint4*>(kf_engine), p->NE, p->nlev >= 1 ? p->lev[0].R : 1,
+      p->nlev == 2 ? p->lev[1].R : 1, p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj)););
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -375,10 +370,10 @@ int bffc_kf_pack_rfft(const bffc_plan* p, const void* kf_half, void* kf_engine, 
     CUDA_TRY(cudaGetLastError());
     return BFFC_OK;
   }
-  dim3 grid(64, H);
+  dim3 grid((p->NE / 4 + 255) / 256 > 32 ? 32 : (p->NE / 4 + 255) / 256, H);
   FMT_SWITCH(p->dtype, (kf_pack_kernel<true, F><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float*>(kf_half), static_cast<uint32_t*>(kf_engine), p->perm, p->NE, 128 * p->R,
-      p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj)););
+      static_cast<const float2*>(kf_half), static_cast<uint4*>(kf_engine), p->NE, p->nlev >= 1 ? p->lev[0].R : 1,
+      p->nlev == 2 ? p->lev[1].R : 1, p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj)););
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }

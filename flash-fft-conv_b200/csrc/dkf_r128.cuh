@@ -286,16 +286,26 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
 
 // dk_f engine order -> natural order complex64 (reference analogue: the inverse permutation at conv.py:1818).
 // Composite sizes: channel row (h*R0 + c0)*R1 + c1 holds frequencies k = c0 + R0*(c1 + R1*(k1 + 128*k2)).
+// One thread moves the 16 consecutive-k2 values of one (row, quarter, k1): 128 contiguous bytes in, 16 stores that are
+// contiguous across the k1 lanes of a warp.
 __global__ void dkf_unpack_kernel(const float2* __restrict__ eng, float2* __restrict__ nat, int N, int R0, int R1,
                                   float scale) {
   const int h = blockIdx.y;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
-    const int c0 = k % R0, r0 = k / R0;
-    const int c1 = r0 % R1, kk = r0 / R1;
-    const int k1 = kk & 127, k2 = kk >> 7;
-    const size_t row = (size_t(h) * R0 + c0) * R1 + c1;
-    const float2 v = eng[((row * 4 + (k2 >> 4)) * 128 + k1) * 16 + (k2 & 15)];
-    nat[size_t(h) * N + k] = make_float2(v.x * scale, v.y * scale);
+  const int R = R0 * R1;
+  const int ngroups = R * 4 * 128;                      // (row, quarter, k1) groups per channel
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gridDim.x * blockDim.x) {
+    const int k1 = g & 127, qd = (g >> 7) & 3, row = g >> 9;
+    const int c0 = row / R1, c1 = row % R1;
+    const float4* in = reinterpret_cast<const float4*>(eng + ((size_t(h) * R + row) * 4 + qd) * 128 * 16 + size_t(k1) * 16);
+#pragma unroll
+    for (int t2 = 0; t2 < 8; ++t2) {
+      const float4 v = in[t2];
+      const int k2 = 16 * qd + 2 * t2;
+      const size_t ka = size_t(c0) + size_t(R0) * (c1 + size_t(R1) * (k1 + 128 * k2));
+      const size_t kb = size_t(c0) + size_t(R0) * (c1 + size_t(R1) * (k1 + 128 * (k2 + 1)));
+      nat[size_t(h) * N + ka] = make_float2(v.x * scale, v.y * scale);
+      nat[size_t(h) * N + kb] = make_float2(v.z * scale, v.w * scale);
+    }
   }
 }
 
