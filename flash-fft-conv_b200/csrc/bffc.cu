@@ -132,16 +132,21 @@ __global__ void kf_pack_kernel(const float2* __restrict__ kf_nat, uint4* __restr
 // grid: (8192/2/32 word-pair tiles, R0/32 * R1, H)
 constexpr int kInnerWords = 8192;
 
-// small sizes: y[n] = t[n] + t[n + off] (* postgate), n < L; t rows have Lt elements.  8 elements per thread.
+// small sizes: y[b,h,n] = t[n] + t[(n + off) mod 8192] (* postgate), n < L, inside the segment of batch member b:
+// scratch row = 2*(h*G + g) + (b & 1), segment s = (b >> 1) % S starting at s*2N, g = b / (2S).  8 elements per thread.
 template <int kFmt>
 __global__ void fold_kernel(const uint4* __restrict__ t, const uint4* __restrict__ postgate, uint4* __restrict__ y,
-                            int L, int Lt, int off, size_t rows) {
+                            int L, int N, int S, int G, int H, int off, size_t rows) {
   const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int per = L / 8;
   if (idx >= rows * per) return;
-  const size_t r = idx / per;
+  const size_t r = idx / per;                       // b*H + h
   const int v = int(idx - r * per);
-  const uint4 a = t[r * (Lt / 8) + v], b = t[r * (Lt / 8) + v + off / 8];
+  const int b_ = int(r / H), h = int(r - size_t(b_) * H);
+  const int g = b_ / (2 * S), sg = (b_ >> 1) % S;
+  const size_t trow = (size_t(h) * G + g) * 2 + (b_ & 1);
+  const int v0 = sg * (2 * N / 8) + v;
+  const uint4 a = t[trow * 1024 + v0], b = t[trow * 1024 + ((v0 + off / 8) & 1023)];
   const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
   uint32_t o[4];
 #pragma unroll
@@ -398,7 +403,10 @@ static size_t plane_bytes(const bffc_plan* p, int B, int H) { return size_t((B +
 extern "C" size_t bffc_workspace_bytes(const bffc_plan* p, int B, int H, int L) {
   (void)L;
   if (!p) return 0;
-  if (p->N < kInner) return size_t(B) * H * kInner * 2;     // small sizes: one (B, H, 8192) bf16 scratch
+  if (p->N < kInner) {   // small sizes: S = 4096/N batch members share one 8192-point slot; scratch of full output tiles
+    const int S = 4096 / p->N, G = (B + 2 * S - 1) / (2 * S);
+    return size_t(H) * G * 2 * kInner * 2;
+  }
   if (p->nlev == 0) return 0;
   // plane sets (real + imaginary plane each): forward nlev sets; backward nlev + 1 (transformed u and dout)
   return size_t(2 * (p->nlev + 1)) * plane_bytes(p, B, H);
@@ -409,12 +417,12 @@ static void set_map_dtype(const bffc_plan* p) {
   g_tm_dtype = p->dtype == BFFC_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 }
 
-static int make_map(CUtensorMap* map, const void* base, int rows, int L) {
+static int make_map(CUtensorMap* map, const void* base, int rows, int L, int box_rows = 128) {
   // (rows, L) bf16 viewed as [row][L/64][64]; box = one (128 x 64) tile, 128B swizzle;
   // tile rows >= L/64 are out of bounds: zero-filled on load (implicit padding), dropped on store.
   cuuint64_t dims[3] = {64, cuuint64_t(L / 64), cuuint64_t(rows)};
   cuuint64_t strides[2] = {128, cuuint64_t(L) * 2};
-  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t box[3] = {64, cuuint32_t(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_encode(map, g_tm_dtype, 3, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -440,23 +448,41 @@ static void fill_params(const bffc_plan* p, bffc::FwdParams& prm, const void* kf
   prm.dbg_stages = 0;
 }
 
-// fused 8192-point kernel on (B, H, L) real sequences
+// Segment geometry of the input tiles: S = 4096/N batch members per 8192-point slot for the small sizes, else 1.
+struct SegGeom { int S, seg_rows, groups, kmask; };
+static SegGeom seg_geom(const bffc_plan* p, int B, int L) {
+  SegGeom g;
+  g.S = p->N < kInner ? 4096 / p->N : 1;
+  g.seg_rows = 128 / g.S;
+  g.groups = (B + 2 * g.S - 1) / (2 * g.S);
+  g.kmask = 0;
+  const int used = (L + 63) / 64;                 // non-zero 64-element rows per segment
+  for (int r = 0; r < 128; ++r)
+    if (r % g.seg_rows < used) g.kmask |= 1 << (r / 16);
+  return g;
+}
+
+// fused 8192-point kernel on (B, H, L) real sequences.  Small sizes (p->N < 8192): `y` is the fold scratch.
 static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const void* pregate, const void* postgate,
-                        void* y, int B, int H, int L, float* dbg, int dbg_stages, int max_units, cudaStream_t st,
-                        int L_out = 0) {
+                        void* y, int B, int H, int L, float* dbg, int dbg_stages, int max_units, cudaStream_t st) {
   if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen <= 8192 in this build", L);
-  if (L_out == 0) L_out = L;
+  const bool small = p->N < kInner;
+  const SegGeom sg = seg_geom(p, B, L);
   CUtensorMap tm_u, tm_y, tm_g;
-  if (int rc = make_map(&tm_u, u, B * H, L)) return rc;
-  if (int rc = make_map(&tm_y, y, B * H, L_out)) return rc;
-  if (int rc = make_map(&tm_g, pregate ? pregate : u, B * H, L)) return rc;
+  if (int rc = make_map(&tm_u, u, B * H, L, sg.seg_rows)) return rc;
+  if (small) { if (int rc = make_map(&tm_y, y, H * sg.groups * 2, kInner)) return rc; }
+  else if (int rc = make_map(&tm_y, y, B * H, L)) return rc;
+  if (int rc = make_map(&tm_g, pregate ? pregate : u, B * H, L, sg.seg_rows)) return rc;
   bffc::FwdParams prm;
   fill_params(p, prm, kf);
   prm.pregate = static_cast<const uint32_t*>(pregate);
   prm.postgate = static_cast<const uint32_t*>(postgate);
   prm.B = B; prm.H = H; prm.L = L;
-  prm.pairs = (B + 1) / 2;
-  prm.ksteps = (L / 64 + 15) / 16;
+  prm.pairs = sg.groups;
+  prm.kmask = sg.kmask;
+  prm.nseg = sg.S;
+  prm.seg_bytes = sg.seg_rows * 128;
+  prm.small_out = small ? 1 : 0;
   prm.units = H * prm.pairs;
   if (max_units > 0 && prm.units > max_units) prm.units = max_units;
   prm.dbg = dbg;
@@ -489,7 +515,7 @@ static int launch_planes(const bffc_plan* p, void* pre, void* pim, const void* k
   fill_params(p, prm, kf);
   prm.B = 2 * pairs; prm.H = kf_rows; prm.L = kInner;
   prm.pairs = pairs;
-  prm.ksteps = 8;
+  prm.kmask = 0xff; prm.nseg = 1; prm.seg_bytes = 16384; prm.small_out = 0;
   prm.units = kf_rows * pairs;
   int grid = (prm.units + 1) / 2;
   if (grid > p->num_sms) grid = p->num_sms;
@@ -680,12 +706,14 @@ static int conv_forward(const bffc_plan* p, const void* u, const void* kf, const
     // small sizes (reference: the 2-stage / r2r kernels for 256..2048 and 16_16_16 for 4096, conv.py:78-131): zero-padded
     // operands make the 8192-point circular result a LINEAR (corr = 0) convolution or correlation (corr = 1, du path)
     // of support < 2N; folding it modulo N gives the N-point circular result.
-    const int Lt = corr ? kInner : 2 * p->N;
+    // S = 4096/N batch members of a channel share one 8192-point slot (spacing 2N), so a unit carries 2S sequences.
     const int off = corr ? kInner - p->N : p->N;
-    if (int rc = launch_fused(p, u, kf, pregate, nullptr, ws, B, H, L, nullptr, 0, 0, st, Lt)) return rc;
+    const SegGeom sg = seg_geom(p, B, L);
+    if (int rc = launch_fused(p, u, kf, pregate, nullptr, ws, B, H, L, nullptr, 0, 0, st)) return rc;
     const size_t rows = size_t(B) * H, total = rows * (L / 8);
     FMT_SWITCH(p->dtype, (fold_kernel<F><<<unsigned((total + 255) / 256), 256, 0, st>>>(
-        static_cast<const uint4*>(ws), static_cast<const uint4*>(postgate), static_cast<uint4*>(y), L, Lt, off, rows)););
+        static_cast<const uint4*>(ws), static_cast<const uint4*>(postgate), static_cast<uint4*>(y), L, p->N, sg.S,
+        sg.groups, H, off, rows)););
     CUDA_TRY(cudaGetLastError());
     *launches += 2;
     return BFFC_OK;
@@ -768,12 +796,14 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
   if (p->nlev == 0) {
     if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen 8192 in this build", L);
     CUtensorMap tm_u, tm_d, tm_p, tm_q;
-    if (int rc = make_map(&tm_u, u, B * H, L)) return rc;
-    if (int rc = make_map(&tm_d, dout, B * H, L)) return rc;
-    if (int rc = make_map(&tm_p, gated ? pregate : u, B * H, L)) return rc;
-    if (int rc = make_map(&tm_q, gated ? postgate : dout, B * H, L)) return rc;
+    const SegGeom sg = seg_geom(p, B, L);
+    if (int rc = make_map(&tm_u, u, B * H, L, sg.seg_rows)) return rc;
+    if (int rc = make_map(&tm_d, dout, B * H, L, sg.seg_rows)) return rc;
+    if (int rc = make_map(&tm_p, gated ? pregate : u, B * H, L, sg.seg_rows)) return rc;
+    if (int rc = make_map(&tm_q, gated ? postgate : dout, B * H, L, sg.seg_rows)) return rc;
     prm.B = B; prm.H = H; prm.L = L;
-    prm.ksteps = (L / 64 + 15) / 16;
+    prm.pairs = sg.groups;
+    prm.kmask = sg.kmask; prm.nseg = sg.S; prm.seg_bytes = sg.seg_rows * 128;
     prm.gated = gated ? 1 : 0;
     int grid = H < p->num_sms ? H : p->num_sms;
     FMT_SWITCH(p->dtype, (dkf_kernel<false, F><<<grid, kThreads, gated ? kSmemTotalDkfGated : kSmemTotalDkf, st>>>(tm_u, tm_d, tm_p, tm_q, prm)););
@@ -798,7 +828,7 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
     if (int rc = make_map(&tdr, rd.re, pairs * rows, kInner)) return rc;
     if (int rc = make_map(&tdi, rd.im, pairs * rows, kInner)) return rc;
     prm.B = 2 * pairs; prm.H = rows; prm.L = kInner;
-    prm.ksteps = 8;
+    prm.kmask = 0xff; prm.nseg = 1; prm.seg_bytes = 16384;
     prm.gated = 0;
     int grid = rows < p->num_sms ? rows : p->num_sms;
     FMT_SWITCH(p->dtype, (dkf_kernel<true, F><<<grid, kThreads, kSmemTotalDkf, st>>>(tur, tdr, tui, tdi, prm)););

@@ -26,7 +26,8 @@ struct DkfParams {
   const __nv_bfloat16* dftS;
   const uint8_t* gtiles;
   float2* dkf;               // [H][4][128][16] complex fp32: k2 = 16*q + t, frequency k = k1 + 128*k2
-  int B, H, L, pairs, ksteps;
+  int B, H, L, pairs, kmask;  // pairs = batch groups per channel; kmask as in FwdParams
+  int nseg, seg_bytes;        // segmented tiles (small sizes), see load_tile()
   float tw_scale;            // see FwdParams::tw_scale; dkf_unpack compensates
   int gated;                 // 1: u is multiplied by pregate and dout by postgate on load (tm_ui / tm_di = gate maps)
 };
@@ -128,7 +129,6 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   const uint32_t sG0 = s_g;
   const CUtensorMap* tm = (pipe == 0) ? &tm_u : &tm_d;
   const CUtensorMap* tmi = (kPlanes || p.gated) ? ((pipe == 0) ? &tm_ui : &tm_di) : tm;   // imaginary plane / gate
-  const int BH = p.B * p.H;
 
   // units of this CTA: (h, pr) for h = blockIdx.x, blockIdx.x + gridDim.x, ...
   const int nh = (p.H - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
@@ -136,7 +136,6 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   auto unit_h = [&](int n) { return int(blockIdx.x) + (n / p.pairs) * int(gridDim.x); };
   auto issue_load = [&](int n, int slot) {
     const int h = unit_h(n), pr = n % p.pairs;
-    const int b0 = 2 * pr, b1 = 2 * pr + 1;
     const uint32_t bar = bar_tma0 + 8 * slot;
     const uint32_t dst = s_slot0 + slot * kSlotBytes;
     mbar_expect_tx(bar, (!kPlanes && p.gated) ? 2 * kSlotBytes : kSlotBytes);
@@ -144,12 +143,12 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
       tma_load_3d(dst, tm, bar, 0, 0, pr * p.H + h);
       tma_load_3d(dst + kTileBytes, tmi, bar, 0, 0, pr * p.H + h);
     } else {
-      tma_load_3d(dst, tm, bar, 0, 0, b0 * p.H + h);
-      tma_load_3d(dst + kTileBytes, tm, bar, 0, 0, b1 < p.B ? b1 * p.H + h : BH);   // out of bounds -> zeros
+      load_tile(dst, tm, bar, p.B, p.H, h, pr, 0, p.nseg, p.seg_bytes);              // members beyond the batch: zeros
+      load_tile(dst + kTileBytes, tm, bar, p.B, p.H, h, pr, 1, p.nseg, p.seg_bytes);
       if (p.gated) {       // gate tiles (pregate for u, postgate for dout) into this pipeline's gate slot
         const uint32_t gd = s_gate0 + pipe * kSlotBytes;
-        tma_load_3d(gd, tmi, bar, 0, 0, b0 * p.H + h);
-        tma_load_3d(gd + kTileBytes, tmi, bar, 0, 0, b1 < p.B ? b1 * p.H + h : BH);
+        load_tile(gd, tmi, bar, p.B, p.H, h, pr, 0, p.nseg, p.seg_bytes);
+        load_tile(gd + kTileBytes, tmi, bar, p.B, p.H, h, pr, 1, p.nseg, p.seg_bytes);
       }
     }
   };
@@ -193,10 +192,13 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
       if (!(!kPlanes && p.gated)) mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
-        for (int s = 0; s < p.ksteps; ++s) mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, s > 0);
-        for (int s = 0; s < p.ksteps; ++s)
-          mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN, 1);
-        for (int s = 0; s < p.ksteps; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN_NEG, 1);
+        uint32_t acc = 0;
+        for (int s = 0; s < 8; ++s)
+          if ((p.kmask >> s) & 1) { mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, acc); acc = 1; }
+        for (int s = 0; s < 8; ++s)
+          if ((p.kmask >> s) & 1) mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN, 1);
+        for (int s = 0; s < 8; ++s)
+          if ((p.kmask >> s) & 1) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN_NEG, 1);
         mma_commit(bar_mma);
         if (n + 1 < n_units) issue_load(n + 1, slot ^ 1);   // other slot: its stage 1 finished a unit ago
       }

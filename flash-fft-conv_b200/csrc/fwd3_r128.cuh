@@ -130,16 +130,21 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   auto seq_index = [&](int unit, int which) {
     const int h = unit / p.pairs, pr = unit - h * p.pairs;
     if (kPlanes) return pr * p.H + h;
-    int b = 2 * pr + which;
-    if (b >= p.B) b = p.B - 1;
-    return b * p.H + h;
+    if (p.small_out) return 2 * unit + which;
+    return (2 * pr + which) * p.H + h;
   };
   auto issue_load = [&](int unit, int slot) {
     const uint32_t bar = bar_tma0 + 8 * slot;
     const uint32_t dst = s_slot0 + slot * kSlotBytes;
     mbar_expect_tx(bar, kSlotBytes);
-    tma_load_3d(dst, &tm_u, bar, 0, 0, seq_index(unit, 0));
-    tma_load_3d(dst + kTileBytes, kPlanes ? &tm_g : &tm_u, bar, 0, 0, seq_index(unit, 1));
+    if (kPlanes) {
+      tma_load_3d(dst, &tm_u, bar, 0, 0, seq_index(unit, 0));
+      tma_load_3d(dst + kTileBytes, &tm_g, bar, 0, 0, seq_index(unit, 1));
+    } else {
+      const int uh = unit / p.pairs, ug = unit - uh * p.pairs;
+      load_tile(dst, &tm_u, bar, p.B, p.H, uh, ug, 0, p.nseg, p.seg_bytes);
+      load_tile(dst + kTileBytes, &tm_u, bar, p.B, p.H, uh, ug, 1, p.nseg, p.seg_bytes);
+    }
   };
   uint32_t mma_phase = 0;
   auto wait_mma = [&]() {
@@ -175,9 +180,13 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
       mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
-        for (int s = 0; s < p.ksteps; ++s) mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, s > 0);
-        for (int s = 0; s < p.ksteps; ++s) mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN, 1);
-        for (int s = 0; s < p.ksteps; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN_NEG, 1);
+        uint32_t acc = 0;
+        for (int s = 0; s < 8; ++s)
+          if ((p.kmask >> s) & 1) { mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, acc); acc = 1; }
+        for (int s = 0; s < 8; ++s)
+          if ((p.kmask >> s) & 1) mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN, 1);
+        for (int s = 0; s < 8; ++s)
+          if ((p.kmask >> s) & 1) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN_NEG, 1);
         mma_commit(bar_mma);
       }
       __syncwarp();
@@ -348,7 +357,7 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         const int pr = unit - h * p.pairs;
         tma_store_3d(&tm_y, sX, 0, 0, seq_index(unit, 0));
         if (kPlanes) tma_store_3d(&tm_g, sX + kTileBytes, 0, 0, seq_index(unit, 1));
-        else if (2 * pr + 1 < p.B) tma_store_3d(&tm_y, sX + kTileBytes, 0, 0, seq_index(unit, 1));
+        else if (p.small_out || 2 * pr + 1 < p.B) tma_store_3d(&tm_y, sX + kTileBytes, 0, 0, seq_index(unit, 1));
         tma_store_commit();
       }
       __syncwarp();

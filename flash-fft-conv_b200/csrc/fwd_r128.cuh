@@ -38,7 +38,10 @@ struct FwdParams {
   const uint32_t* postgate;
   int B, H, L;               // batch, channels, sequence length
   int pairs;                 // ceil(B/2)
-  int ksteps;                // number of 16-row K steps of the input tile that are non-zero
+  int kmask;                 // bit s set: 16-row K step s of the input tile can be non-zero (the rest is skipped)
+  int nseg;                  // segments per tile (small sizes: 4096/N batch members share one 8192 slot), else 1
+  int seg_bytes;             // bytes of one segment inside a tile = (128 / nseg) rows x 128 B
+  int small_out;             // 1: store the full tiles to the fold scratch, row = 2*unit + which
   int units;                 // H * pairs
   float* dbg;                // optional stage dump [stage][128][128]
   int dbg_stages;
@@ -74,6 +77,17 @@ DEVINL void cmul(float ar, float ai, float br, float bi, float& cr, float& ci) {
   ci = ar * bi + ai * br;
 }
 DEVINL uint64_t tile_desc(uint32_t saddr) { return make_sdesc(saddr, kTileBytes, 1024, 2); }
+
+// One (128 x 64) input tile = nseg segments; segment s is the zero-padded (TMA out-of-bounds fill) start of batch member
+// b = (g*nseg + s)*2 + which of channel h.  nseg == 1 is the ordinary case b = 2g + which.  A member beyond the batch
+// is fetched from sequence index B*H, which is out of bounds for the tensor map: an all-zero tile.
+DEVINL void load_tile(uint32_t dst, const void* map, uint32_t bar, int B, int H, int h, int g, int which, int nseg,
+                      int seg_bytes) {
+  for (int s = 0; s < nseg; ++s) {
+    const int b = (g * nseg + s) * 2 + which;
+    tma_load_3d(dst + s * seg_bytes, map, bar, 0, 0, b < B ? b * H + h : B * H);
+  }
+}
 // N=128 B operand made of two 64-column tiles `lbo` bytes apart
 DEVINL uint64_t pair_desc(uint32_t saddr, uint32_t lbo) { return make_sdesc(saddr, lbo, 1024, 2); }
 
@@ -193,24 +207,29 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   const uint32_t sG0 = s_g;   // tiles: +0 Gr, +8K Gi, +16K -Gi, +24K Gr
   const f32x2 kfs2 = pk2(p.kf_scale, p.kf_scale);
 
-  auto seq_index = [&](int unit, int which) {   // global sequence index (b*H + h) of the re / im member
+  auto seq_index = [&](int unit, int which) {   // row of the output (and, in planes mode, input) tensor maps
     const int h = unit / p.pairs, pr = unit - h * p.pairs;
     if (kPlanes) return pr * p.H + h;           // row of both planes
-    int b = 2 * pr + which;
-    if (b >= p.B) b = p.B - 1;                  // odd batch: duplicate, result discarded
-    return b * p.H + h;
+    if (p.small_out) return 2 * unit + which;   // fold scratch
+    return (2 * pr + which) * p.H + h;          // (b*H + h); members beyond the batch are not stored
   };
   auto issue_load = [&](int unit, int slot) {
     const uint32_t bar = bar_tma0 + 8 * slot;
     const uint32_t dst = s_slot0 + slot * kSlotBytes;
     const bool has_pre = kGated && p.pregate != nullptr;
     mbar_expect_tx(bar, has_pre ? 2 * kSlotBytes : kSlotBytes);
-    tma_load_3d(dst, &tm_u, bar, 0, 0, seq_index(unit, 0));
-    tma_load_3d(dst + kTileBytes, kPlanes ? &tm_g : &tm_u, bar, 0, 0, seq_index(unit, 1));
+    const int uh = unit / p.pairs, ug = unit - uh * p.pairs;
+    if (kPlanes) {
+      tma_load_3d(dst, &tm_u, bar, 0, 0, seq_index(unit, 0));
+      tma_load_3d(dst + kTileBytes, &tm_g, bar, 0, 0, seq_index(unit, 1));
+    } else {
+      load_tile(dst, &tm_u, bar, p.B, p.H, uh, ug, 0, p.nseg, p.seg_bytes);
+      load_tile(dst + kTileBytes, &tm_u, bar, p.B, p.H, uh, ug, 1, p.nseg, p.seg_bytes);
+    }
     if (has_pre) {   // single pregate slot per pipeline: free again once pass 0 of the current unit is done
       const uint32_t gd = s_gate0 + pipe * kSlotBytes;
-      tma_load_3d(gd, &tm_g, bar, 0, 0, seq_index(unit, 0));
-      tma_load_3d(gd + kTileBytes, &tm_g, bar, 0, 0, seq_index(unit, 1));
+      load_tile(gd, &tm_g, bar, p.B, p.H, uh, ug, 0, p.nseg, p.seg_bytes);
+      load_tile(gd + kTileBytes, &tm_g, bar, p.B, p.H, uh, ug, 1, p.nseg, p.seg_bytes);
     }
   };
 
@@ -277,11 +296,14 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
       tc_fence_after();
       if (elect_one()) {
       // D[:,0:128]  = C * [Xr | Xi]
-      for (int s = 0; s < p.ksteps; ++s) mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, s > 0);
+      uint32_t acc = 0;
+      for (int s = 0; s < 8; ++s)
+        if ((p.kmask >> s) & 1) { mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, acc); acc = 1; }
       // D[:,0:64]  += S * Xi ;  D[:,64:128] += (-S) * Xr        (F = C - iS)
-      for (int s = 0; s < p.ksteps; ++s)
-        mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN, 1);
-      for (int s = 0; s < p.ksteps; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN_NEG, 1);
+      for (int s = 0; s < 8; ++s)
+        if ((p.kmask >> s) & 1) mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN, 1);
+      for (int s = 0; s < 8; ++s)
+        if ((p.kmask >> s) & 1) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN_NEG, 1);
       mma_commit(bar_mma);
       }
       __syncwarp();
@@ -422,7 +444,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
       const bool row_ok = lane * 64 < p.L;
 #pragma unroll
       for (int part = 0; part < 2; ++part) {
-        const uint4* gp_ = reinterpret_cast<const uint4*>(p.postgate + (size_t(seq_index(unit, part)) * p.L + lane * 64) / 2) + 4 * half;
+        const int pb = 2 * (unit - h * p.pairs) + part;     // batch member (gated kernels never run segmented outputs)
+        const uint4* gp_ = reinterpret_cast<const uint4*>(p.postgate + (size_t(pb < p.B ? pb : p.B - 1) * p.H + h) * p.L / 2 + lane * 32) + 4 * half;
 #pragma unroll
         for (int c = 0; c < 4; ++c) pg[part][c] = row_ok ? __ldg(gp_ + c) : make_uint4(0, 0, 0, 0);
       }
@@ -463,7 +486,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
         const int pr = unit - h * p.pairs;
         tma_store_3d(&tm_y, sX, 0, 0, seq_index(unit, 0));
         if (kPlanes) tma_store_3d(&tm_g, sX + kTileBytes, 0, 0, seq_index(unit, 1));
-        else if (2 * pr + 1 < p.B) tma_store_3d(&tm_y, sX + kTileBytes, 0, 0, seq_index(unit, 1));
+        else if (p.small_out || 2 * pr + 1 < p.B) tma_store_3d(&tm_y, sX + kTileBytes, 0, 0, seq_index(unit, 1));
         tma_store_commit();
       }
       __syncwarp();
