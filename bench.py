@@ -267,16 +267,12 @@ def run_ours(args):
     u_h = u.cpu().pin_memory(); k_h = k.cpu().pin_memory()
     g_h = [g.cpu().pin_memory() for g in gates]
     y_h = torch.empty_like(u_h).pin_memory()
-    u_d = torch.empty_like(u); k_d = torch.empty_like(k)
-    g_d = [torch.empty_like(g) for g in gates]
     e2e_steps = max(2, min(args.steps, 5))
 
     def e2e_step():
-        u_d.copy_(u_h, non_blocking=True); k_d.copy_(k_h, non_blocking=True)
-        for a, b in zip(g_d, g_h):
-            a.copy_(b, non_blocking=True)
-        yy = conv(u_d, k_d, *g_d)
-        y_h.copy_(yy, non_blocking=True)
+        # public host-buffer call: k -> device, k_f, then u (and gates) host -> device, conv, y device -> host,
+        # pipelined over batch chunks inside bffc_fwd_host (include/bffc.h)
+        conv.forward_host(u_h, k_h, *g_h, out=y_h, device=dev)
     e2e_step()
     barrier()
     s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)

@@ -227,6 +227,9 @@ struct bffc_plan {
   __nv_bfloat16* dftS = nullptr;
   uint8_t* gtiles = nullptr;
   int num_sms = 0;
+  // bffc_fwd_host: copy-in / compute / copy-out streams and the per-slot events, created on first use
+  mutable cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
+  mutable cudaEvent_t hev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 extern "C" {
@@ -343,6 +346,8 @@ int bffc_plan_destroy(bffc_plan* p) {
   cudaFree(p->dftC);
   cudaFree(p->dftS);
   cudaFree(p->gtiles);
+  for (auto& st : p->hs) if (st) cudaStreamDestroy(st);
+  for (auto& ev : p->hev) if (ev) cudaEventDestroy(ev);
   delete p;
   return BFFC_OK;
 }
@@ -835,6 +840,99 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
     CUDA_TRY(cudaGetLastError());
     launches += 1;
   }
+  g_launches = launches;
+  return BFFC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- host streaming
+// Chunk geometry of the host pipeline: bc batch members x hc channels per chunk, ~12 MB per chunk tensor — a copy of
+// ~0.25 ms (PCIe 5 x16) still runs at link speed, and the fill / drain of the three-stage pipeline (one chunk copy-in
+// before, one copy-out after the overlapped part) stays small.  bc is even so that batch pairs stay together; wide
+// rows (H*L*2 bytes > 6 MB) are split over channels instead and moved with pitched (2-D) copies.
+struct HostChunk { int bc, hc; };
+static HostChunk host_chunk(int B, int H, int L) {
+  const size_t target = size_t(12) << 20, row = size_t(H) * L * 2;
+  HostChunk g{2, H};
+  if (2 * row > target) {
+    const int nh = int((2 * row + target - 1) / target);
+    g.hc = (H + nh - 1) / nh;
+  } else {
+    g.bc = int((target / row) & ~size_t(1));
+  }
+  if (g.bc > B) g.bc = B;
+  return g;
+}
+
+int bffc_host_chunk_batch(const bffc_plan* p, int B, int H, int L) {
+  if (!p || B <= 0 || H <= 0 || L <= 0) return 0;
+  return host_chunk(B, H, L).bc;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+size_t bffc_host_workspace_bytes(const bffc_plan* p, int B, int H, int L, int gated) {
+  if (!p || B <= 0 || H <= 0 || L <= 0) return 0;
+  const HostChunk g = host_chunk(B, H, L);
+  const size_t t = align256(size_t(g.bc) * g.hc * L * 2);
+  return 2 * ((gated ? 4 : 2) * t + align256(bffc_workspace_bytes(p, g.bc, g.hc, L)));
+}
+
+int bffc_fwd_host(const bffc_plan* p, const void* u_host, const void* kf, const void* pre_host, const void* post_host,
+                  void* y_host, int B, int H, int L, void* dev_ws, size_t dev_ws_bytes, void* stream) {
+  if ((pre_host == nullptr) != (post_host == nullptr))
+    return fail(BFFC_ERR_INVALID, "bffc_fwd_host: pregate and postgate must both be given or both be null");
+  if (!u_host || !kf || !y_host) return fail(BFFC_ERR_INVALID, "bffc_fwd_host: null pointer");
+  if (int rc = check_common(p, B, H, L, kf, dev_ws, nullptr)) return rc;
+  const bool gated = pre_host != nullptr;
+  if (!dev_ws || dev_ws_bytes < bffc_host_workspace_bytes(p, B, H, L, gated))
+    return fail(BFFC_ERR_INVALID, "bffc_fwd_host: device workspace of %zu bytes required", bffc_host_workspace_bytes(p, B, H, L, gated));
+  set_map_dtype(p); g_cur_dtype = p->dtype;
+  if (!p->hs[0]) {
+    for (auto& st : p->hs) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& ev : p->hev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  cudaStream_t user = static_cast<cudaStream_t>(stream), s_in = p->hs[0], s_cmp = p->hs[1], s_out = p->hs[2];
+  cudaEvent_t ev_start = p->hev[0];
+  cudaEvent_t* ev_in = &p->hev[1];    // [slot] chunk copied in
+  cudaEvent_t* ev_cmp = &p->hev[3];   // [slot] chunk convolved (input slot free again)
+  cudaEvent_t* ev_out = &p->hev[5];   // [slot] chunk copied out (output slot free again)
+  const HostChunk g = host_chunk(B, H, L);
+  const size_t t = align256(size_t(g.bc) * g.hc * L * 2);
+  const size_t conv_ws = bffc_workspace_bytes(p, g.bc, g.hc, L);
+  const size_t slot_bytes = (gated ? 4 : 2) * t + align256(conv_ws);
+  const size_t host_pitch = size_t(H) * L * 2;                   // one batch member of the host tensors
+  const size_t kf_row = size_t(p->NE) * 4;                       // one channel of kf_engine
+  CUDA_TRY(cudaEventRecord(ev_start, user));
+  CUDA_TRY(cudaStreamWaitEvent(s_in, ev_start, 0));
+  CUDA_TRY(cudaStreamWaitEvent(s_out, ev_start, 0));
+  int launches = 0, c = 0;
+  for (int b0 = 0; b0 < B; b0 += g.bc)
+    for (int h0 = 0; h0 < H; h0 += g.hc, ++c) {
+      const int nb = B - b0 < g.bc ? B - b0 : g.bc, nh = H - h0 < g.hc ? H - h0 : g.hc, slot = c & 1;
+      uint8_t* base = static_cast<uint8_t*>(dev_ws) + slot * slot_bytes;
+      uint8_t *d_u = base, *d_y = base + t, *d_p = gated ? base + 2 * t : nullptr, *d_q = gated ? base + 3 * t : nullptr;
+      uint8_t* d_ws = base + (gated ? 4 : 2) * t;
+      // chunk = rows b0..b0+nb of a (B, H*L) matrix, columns h0*L..(h0+nh)*L: pitched on the host, dense on the device
+      const size_t off = size_t(b0) * host_pitch + size_t(h0) * L * 2, width = size_t(nh) * L * 2;
+      if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(s_in, ev_cmp[slot], 0));
+      CUDA_TRY(cudaMemcpy2DAsync(d_u, width, static_cast<const uint8_t*>(u_host) + off, host_pitch, width, nb, cudaMemcpyHostToDevice, s_in));
+      if (gated) {
+        CUDA_TRY(cudaMemcpy2DAsync(d_p, width, static_cast<const uint8_t*>(pre_host) + off, host_pitch, width, nb, cudaMemcpyHostToDevice, s_in));
+        CUDA_TRY(cudaMemcpy2DAsync(d_q, width, static_cast<const uint8_t*>(post_host) + off, host_pitch, width, nb, cudaMemcpyHostToDevice, s_in));
+      }
+      CUDA_TRY(cudaEventRecord(ev_in[slot], s_in));
+      CUDA_TRY(cudaStreamWaitEvent(s_cmp, ev_in[slot], 0));
+      if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(s_cmp, ev_out[slot], 0));
+      if (int rc = conv_forward(p, d_u, static_cast<const uint8_t*>(kf) + size_t(h0) * kf_row, d_p, d_q, d_y, nb, nh, L,
+                                conv_ws ? d_ws : nullptr, s_cmp, &launches)) return rc;
+      CUDA_TRY(cudaEventRecord(ev_cmp[slot], s_cmp));
+      CUDA_TRY(cudaStreamWaitEvent(s_out, ev_cmp[slot], 0));
+      CUDA_TRY(cudaMemcpy2DAsync(static_cast<uint8_t*>(y_host) + off, host_pitch, d_y, width, width, nb, cudaMemcpyDeviceToHost, s_out));
+      CUDA_TRY(cudaEventRecord(ev_out[slot], s_out));
+    }
+  // join: everything enqueued above is complete when the last copy-out is (s_out is in order and waited on each
+  // chunk's compute, which waited on its copy-in)
+  CUDA_TRY(cudaStreamWaitEvent(user, ev_out[(c - 1) & 1], 0));
   g_launches = launches;
   return BFFC_OK;
 }

@@ -41,6 +41,7 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 
   const uint32_t bar_tma0 = s_bars + pipe * 24;
   const uint32_t bar_mma = s_bars + pipe * 24 + 16;
+  const uint32_t bar_g = s_bars + 80;
   const uint32_t s_tmemptr = s_bars + 96;
 
   if (tid == 0) {
@@ -54,78 +55,22 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     mbar_init(bar_mma, 1);
     fence_barrier_init();
   }
+  if (tid == 0) { mbar_init(bar_g, 1); fence_barrier_init(); }
   if (tid < 32) {
     tmem_alloc(s_tmemptr, 512);
     tmem_relinquish();
   }
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(p.gtiles);
-    uint4* dst = reinterpret_cast<uint4*>(gen_base + kSmemData3);
-    for (int i = tid; i < kSmemG / 16; i += kThreads3) dst[i] = src[i];
-  }
-  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + kSmemData3 + kSmemG + 96);
   const uint32_t tlane = tmem_base + (uint32_t(warp_q * 32) << 16);
 
-  // DFT-128 -> TMEM: pipeline 0 loads cos, pipeline 1 sin (64 columns each)
-  if (pipe < 2) {
-    const uint4* row = reinterpret_cast<const uint4*>((pipe == 0 ? p.dftC : p.dftS) + lane * 128);
-    const uint32_t tcol = tlane + (pipe == 0 ? kColC : kColS);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint32_t v[16];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        uint4 w = row[q * 4 + r];
-        v[4 * r + 0] = w.x; v[4 * r + 1] = w.y; v[4 * r + 2] = w.z; v[4 * r + 3] = w.w;
-      }
-      tmem_st16(tcol + 16 * q, v);
-    }
-    tmem_st_wait();
-  }
-  // twiddles W_N^{k1*j} (k1 = lane), factored as A[j >> 3] * B[j & 7]: B (8 columns, half2 pairs) is a table, A is
-  // advanced block by block with the per-lane step W_N^{8*k1} (fp32 recurrence over 8 blocks).  10 registers instead of
-  // 64: with the full shared-memory carve-out there is no L1 behind local memory, so spills cost an L2 round trip.
-  __half2 twBc[4], twBs[4];
-  float stc, sts;
-  sincospif(-2.0f * float(lane * 8) / 8192.0f, &sts, &stc);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float s0, c0, s1, c1;
-    sincospif(-2.0f * float(lane * (2 * q)) / 8192.0f, &s0, &c0);
-    sincospif(-2.0f * float(lane * (2 * q + 1)) / 8192.0f, &s1, &c1);
-    twBc[q] = __floats2half2_rn(c0, c1);
-    twBs[q] = __floats2half2_rn(s0, s1);
-  }
-  // twiddles of the four column pairs of one 8-column block whose block factor is (ac, as)
-  auto block_tw = [&](float ac, float as, f32x2 (&tc)[4], f32x2 (&ts)[4]) {
-    const f32x2 ac2 = pk2(ac, ac), as2 = pk2(as, as);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float2 bc = __half22float2(twBc[q]), bs = __half22float2(twBs[q]);
-      cmul2(ac2, as2, pk2(bc.x, bc.y), pk2(bs.x, bs.y), tc[q], ts[q]);
-    }
-  };
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-
   const int gp = blockIdx.x * kPipes3 + pipe;
   const int GP = gridDim.x * kPipes3;
   const int u_begin = int((long long)p.units * gp / GP);
   const int u_end = int((long long)p.units * (gp + 1) / GP);
-
   const uint32_t s_slot0 = sbase + pipe * 2 * kSlotBytes;
-  const uint32_t tD = tlane + 128 + 128 * pipe;
-  const uint32_t tD0 = tmem_base + 128 + 128 * pipe;
-  const uint32_t tC0 = tmem_base + kColC;
-  const uint32_t tS0 = tmem_base + kColS;
-  const uint32_t bar_id = 1 + pipe;
-  const uint32_t sG0 = s_g;
-  const f32x2 kfs2 = pk2(p.kf_scale, p.kf_scale);
 
   auto seq_index = [&](int unit, int which) {
     const int h = unit / p.pairs, pr = unit - h * p.pairs;
@@ -146,6 +91,65 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
       load_tile(dst + kTileBytes, &tm_u, bar, p.B, p.H, uh, ug, 1, p.nseg, p.seg_bytes);
     }
   };
+  // Everything the first stage needs from global memory is requested up front and lands while the tables below are
+  // built: the first unit's tiles (TMA), the DFT-64 tiles (one bulk copy, needed before the first stage 2 only).
+  if (lead_warp && u_begin < u_end) {
+    if (elect_one()) issue_load(u_begin, 0);
+    __syncwarp();
+  }
+  if (tid == 0) {
+    mbar_expect_tx(bar_g, kSmemG);
+    for (int c = 0; c < kSmemG; c += 8192) bulk_load(s_g + c, reinterpret_cast<const uint8_t*>(p.gtiles) + c, 8192, bar_g);
+  }
+
+  // DFT-128 -> TMEM: pipeline 0 loads cos, pipeline 1 sin (64 columns each)
+  if (pipe < 2) {
+    const uint4* row = reinterpret_cast<const uint4*>((pipe == 0 ? p.dftC : p.dftS) + lane * 128);
+    const uint32_t tcol = tlane + (pipe == 0 ? kColC : kColS);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t v[16];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        uint4 w = row[q * 4 + r];
+        v[4 * r + 0] = w.x; v[4 * r + 1] = w.y; v[4 * r + 2] = w.z; v[4 * r + 3] = w.w;
+      }
+      tmem_st16(tcol + 16 * q, v);
+    }
+    tmem_st_wait();
+  }
+  // twiddles W_N^{k1*j} (k1 = lane), factored as A[j >> 3] * B[j & 7]: B (8 columns, half2 pairs) is a table, A is
+  // advanced block by block with the per-lane step W_N^{8*k1} (fp32 recurrence over 8 blocks).  10 registers instead of
+  // 64: with the full shared-memory carve-out there is no L1 behind local memory, so spills cost an L2 round trip.
+  f32x2 twBc[4], twBs[4];
+  float stc, sts;
+  sincospif(-2.0f * float(lane * 8) / 8192.0f, &sts, &stc);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float s0, c0, s1, c1;
+    sincospif(-2.0f * float(lane * (2 * q)) / 8192.0f, &s0, &c0);
+    sincospif(-2.0f * float(lane * (2 * q + 1)) / 8192.0f, &s1, &c1);
+    twBc[q] = pk2(c0, c1);
+    twBs[q] = pk2(s0, s1);
+  }
+  // twiddles of the four column pairs of one 8-column block whose block factor is (ac, as)
+  auto block_tw = [&](float ac, float as, f32x2 (&tc)[4], f32x2 (&ts)[4]) {
+    const f32x2 ac2 = pk2(ac, ac), as2 = pk2(as, as);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cmul2(ac2, as2, twBc[q], twBs[q], tc[q], ts[q]);
+  };
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const uint32_t tD = tlane + 128 + 128 * pipe;
+  const uint32_t tD0 = tmem_base + 128 + 128 * pipe;
+  const uint32_t tC0 = tmem_base + kColC;
+  const uint32_t tS0 = tmem_base + kColS;
+  const uint32_t bar_id = 1 + pipe;
+  const uint32_t sG0 = s_g;
+  const f32x2 kfs2 = pk2(p.kf_scale, p.kf_scale);
+
   uint32_t mma_phase = 0;
   auto wait_mma = [&]() {
     mbar_wait(bar_mma, mma_phase);
@@ -165,10 +169,7 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     st_shared_v4(sX + kTileBytes + off, im4[0], im4[1], im4[2], im4[3]);
   };
 
-  if (lead_warp && u_begin < u_end) {
-    if (elect_one()) issue_load(u_begin, 0);
-    __syncwarp();
-  }
+  if (lead_warp) mbar_wait(bar_g, 0);     // DFT-64 tiles have landed (long ago: hidden behind the table set-up)
 
   for (int unit = u_begin, n = 0; unit < u_end; ++unit, ++n) {
     const int slot = n & 1;
@@ -241,14 +242,13 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     // samples when fetched inside pass 3, profiles/r1_v3).  The first half is fetched here, where nothing else is live
     // (the MMA wait hides it), the second half at the start of pass 3 (hidden by the first half's arithmetic).
     const uint4* kfp = reinterpret_cast<const uint4*>(p.kf) + size_t(h) * 16 * 128 + lane;
-    uint4 kfa[8], kfb[8];
+    uint4 kfa[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) kfa[c] = __ldg(kfp + c * 128);
     wait_mma();
 
-    // ---------------- pass 3: * k_f -> A3 tiles
-#pragma unroll
-    for (int c = 0; c < 8; ++c) kfb[c] = __ldg(kfp + (8 + c) * 128);
+    // ---------------- pass 3: * k_f -> A3 tiles.  Each first-half vector is replaced by its second-half counterpart
+    // as soon as it has been used (4 steps = several hundred cycles before the second half needs it).
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
@@ -262,7 +262,7 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         uint32_t ore[4], oim[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint4 kq = hf == 0 ? kfa[2 * s4 + (q >> 1)] : kfb[2 * s4 + (q >> 1)];
+          const uint4 kq = kfa[2 * s4 + (q >> 1)];
           const uint32_t wr = (q & 1) ? kq.z : kq.x, wi = (q & 1) ? kq.w : kq.y;
           f32x2 kr2 = NT::unpack(wr), ki2 = NT::unpack(wi);
           if (kFmt == 0) { kr2 = mul2(kr2, kfs2); ki2 = mul2(ki2, kfs2); }
@@ -272,6 +272,10 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
           oim[q] = NT::pack_v(vi);
         }
         store_chunk(sX, sub, ore, oim);
+        if (hf == 0) {
+          kfa[2 * s4] = __ldg(kfp + (8 + 2 * s4) * 128);
+          kfa[2 * s4 + 1] = __ldg(kfp + (9 + 2 * s4) * 128);
+        }
       }
     }
     sync_pipe_smem();

@@ -53,6 +53,7 @@ class FlashFFTConv(torch.nn.Module):
         if not _lib.lib().bffc_supported(self.seqlen, _DT[dtype]):
             raise NotImplementedError(f'seqlen {seqlen} not supported')   # conv.py:550-551
         self._plans = {}
+        self._host_ws = {}
 
     def plan(self, device):
         key = (device.type, device.index)
@@ -64,11 +65,53 @@ class FlashFFTConv(torch.nn.Module):
         """FFT size of the engine: seqlen, or 8192 for the small sizes (computed as a folded linear convolution)."""
         return _lib.lib().bffc_fft_size(self.plan(device).handle)
 
+    def forward_host(self, u, k, pregate=None, postgate=None, out=None, device=None):
+        """Forward on HOST tensors: y = forward(u.cuda(), k.cuda(), ...).cpu(), with the host->device copies, the
+        convolution and the device->host copy pipelined over batch chunks (bffc_fwd_host, include/bffc.h), so both
+        PCIe directions are busy at once.  u / gates / out: (B, H, L) host tensors of the module dtype (pin them, or
+        the copies serialise); k: (H, Lk) fp32, host or device.  The result is complete once the current CUDA stream
+        of `device` is (the call is asynchronous).  Inference only (no autograd)."""
+        device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        return _forward_host(self, u, k, pregate, postgate, out, device)
+
     def forward(self, u, k, pregate=None, postgate=None):
         if pregate is not None or postgate is not None:
             assert pregate is not None and postgate is not None       # conv.py:557-558
             return GatedFlashFFTConvFunc.apply(u, k, self, pregate, postgate)
         return FlashFFTConvFunc.apply(u, k, self)
+
+
+def _forward_host(mod, u, k, pregate, postgate, out, device):
+    """See FlashFFTConv.forward_host."""
+    if (pregate is None) != (postgate is None):
+        raise AssertionError('pregate and postgate must both be given or both be None')       # conv.py:557-558
+    gates = [g for g in (pregate, postgate) if g is not None]
+    for t in [u] + gates:
+        if t.is_cuda or t.dtype != mod.dtype or t.dim() != 3 or not t.is_contiguous() or t.shape != u.shape:
+            raise RuntimeError(f'forward_host: u / gates must be contiguous host (B, H, L) tensors of dtype {mod.dtype}')
+    B, H, L = u.shape
+    if k.dim() != 2 or k.shape[0] != H or k.shape[1] > mod.seqlen or L > mod.seqlen:
+        raise RuntimeError(f'k must be (H={H}, Lk<={mod.seqlen}) and L <= seqlen, got {tuple(k.shape)}, L={L}')
+    if L % _lib.lib().bffc_length_multiple(mod.plan(device).handle):
+        raise RuntimeError(f'forward_host: L={L} must be a multiple of bffc_length_multiple(); pad on the host or '
+                           'use forward() with device tensors')
+    if out is None:
+        out = torch.empty(u.shape, dtype=u.dtype, pin_memory=True)
+    if out.is_cuda or out.shape != u.shape or out.dtype != u.dtype or not out.is_contiguous():
+        raise RuntimeError('forward_host: out must be a contiguous host tensor like u')
+    plan = mod.plan(device)
+    with torch.cuda.device(device):
+        kf_engine = _pack_kf(mod, plan, k.to(device, non_blocking=True), 0)
+        nws = _lib.lib().bffc_host_workspace_bytes(plan.handle, B, H, L, 1 if gates else 0)
+        ws = mod._host_ws.get((device, nws))
+        if ws is None:
+            mod._host_ws.clear()
+            ws = mod._host_ws[(device, nws)] = torch.empty(nws, dtype=torch.uint8, device=device)
+        _lib.check(_lib.lib().bffc_fwd_host(plan.handle, _ptr(u), _ptr(kf_engine), _ptr(pregate), _ptr(postgate),
+                                            _ptr(out), B, H, L, _ptr(ws), nws, _stream()))
+        # the library joins its internal streams back into the current stream before returning, so the caching
+        # allocator (stream-ordered on the current stream) may recycle kf_engine / ws after this point
+    return out
 
 
 def _check_inputs(u, k, mod, gates=()):

@@ -111,7 +111,24 @@ int bffc_bwd(const bffc_plan* plan, const void* dout, const void* u, const void*
              void* dkf_engine, void* dpregate, void* dpostgate, int B, int H, int L,
              void* workspace, size_t workspace_bytes, void* stream);
 
-/* Number of kernel launches the last bffc_fwd / bffc_bwd on this thread enqueued (bench.py). */
+/*
+ * Forward on HOST buffers (the reference has no counterpart: its user writes u.cuda() -> conv -> y.cpu(),
+ * README.md:108-149, three serial steps on one stream).  u_host, pregate_host, postgate_host, y_host: (B, H, L)
+ * contiguous host memory of the plan dtype — page-locked for the copies to overlap; kf_engine: DEVICE, from
+ * bffc_kf_pack*.  The batch is cut into chunks of bffc_host_chunk_batch() members (wide rows also over channels,
+ * ~12 MB per chunk); chunk c+1 is copied in, chunk c convolved and chunk c-1 copied out at the same time on three
+ * internal streams (both PCIe directions busy), all
+ * ordered after the work already enqueued on `stream` and joined back into `stream` before the call returns (the
+ * call itself is asynchronous like every other entry point).  dev_workspace: device scratch of
+ * bffc_host_workspace_bytes() bytes (two staging slots of inputs, output and conv workspace).
+ */
+int bffc_host_chunk_batch(const bffc_plan* plan, int B, int H, int L);
+size_t bffc_host_workspace_bytes(const bffc_plan* plan, int B, int H, int L, int gated);
+int bffc_fwd_host(const bffc_plan* plan, const void* u_host, const void* kf_engine,
+                  const void* pregate_host, const void* postgate_host, void* y_host, int B, int H,
+                  int L, void* dev_workspace, size_t dev_workspace_bytes, void* stream);
+
+/* Number of kernel launches the last bffc_fwd / bffc_bwd / bffc_fwd_host on this thread enqueued (bench.py). */
 int bffc_last_launch_count(void);
 
 /*

@@ -341,3 +341,44 @@ def test_ragged_lengths(ffc, N, B, H, L):
     du_ref, dk_ref = orc.ref_grads(d['u'], d['k'], d['dout'], N)
     _check(u.grad, du_ref, 'ragged du')
     _check(k.grad, dk_ref, 'ragged dk')
+
+
+# ----------------------------------------------------------------------------- host-buffer streaming entry point (bffc_fwd_host)
+@pytest.mark.parametrize('N,B,H,L,gated', [(8192, 7, 5, 8192, False), (8192, 4, 3, 4096, True), (1024, 9, 4, 1024, False),
+                                           (32768, 3, 2, 32768, True), (8192, 40, 192, 8192, False),
+                                           (8192, 5, 500, 8192, True)])
+def test_forward_host_matches_device_path(ffc, N, B, H, L, gated):
+    """forward_host (chunked copy-in / conv / copy-out on three streams) == forward on device tensors, bit for bit;
+    the last two cases need many chunks (so the two-slot ring is reused): batch chunks of 2 members, and — rows of more
+    than 6 MB — chunks of 2 members x 250 of the 500 channels moved with pitched copies."""
+    d = orc.make_inputs(B, H, N, L, torch.bfloat16, seed=91 + B, gated=gated, unit_scale=True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    gates = [d['pregate'], d['postgate']] if gated else []
+    y_dev = conv(d['u'].cuda(), d['k'].cuda(), *[g.cuda() for g in gates]).cpu()
+    u_h = d['u'].pin_memory()
+    g_h = [g.pin_memory() for g in gates]
+    out = torch.full(u_h.shape, float('nan'), dtype=torch.bfloat16).pin_memory()
+    for _ in range(2):                                   # second call reuses streams, events and the staging workspace
+        y = conv.forward_host(u_h, d['k'], *g_h, out=out)
+        torch.cuda.current_stream().synchronize()        # asynchronous like every entry point: joined into this stream
+        assert y is out
+        assert torch.equal(y, y_dev)
+    if B <= 9:
+        ref = orc.ref_fft_conv_gated(d['u'], d['k'], *gates, N) if gated else orc.ref_fft_conv(d['u'], d['k'], N)
+        _check(y, ref, 'forward_host vs oracle')
+
+
+def test_forward_host_rejects_bad_arguments(ffc):
+    conv = ffc.FlashFFTConv(8192, dtype=torch.bfloat16).cuda()
+    u = torch.zeros(2, 2, 8192, dtype=torch.bfloat16)
+    k = torch.zeros(2, 8192)
+    with pytest.raises(RuntimeError):
+        conv.forward_host(u.cuda(), k)                   # device tensor
+    with pytest.raises(RuntimeError):
+        conv.forward_host(u.float(), k)                  # wrong dtype
+    with pytest.raises(AssertionError):
+        conv.forward_host(u, k, pregate=u)               # one gate only
+    lib = ffc._lib.lib()
+    plan = conv.plan(torch.device('cuda', 0))
+    rc = lib.bffc_fwd_host(plan.handle, u.data_ptr(), None, None, None, u.data_ptr(), 2, 2, 8192, None, 0, None)
+    assert rc != 0 and b'null' in lib.bffc_last_error()
