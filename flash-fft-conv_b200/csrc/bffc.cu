@@ -14,6 +14,7 @@
 #include "dkf_r128.cuh"
 #include "outer_cuda.cuh"
 #include "outer_r128.cuh"
+#include "filter_fft.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -226,6 +227,7 @@ struct bffc_plan {
   __nv_bfloat16* dftC = nullptr;
   __nv_bfloat16* dftS = nullptr;
   uint8_t* gtiles = nullptr;
+  float2* tw8192 = nullptr;   // e^{-2 pi i t / 8192}, t < 8192: twiddles of the fp32 filter-side FFTs (filter_fft.cuh)
   int num_sms = 0;
   // bffc_fwd_host: copy-in / compute / copy-out streams and the per-slot events, created on first use
   mutable cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
@@ -311,6 +313,16 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   CUDA_TRY(cudaMalloc(&p->gtiles, gt.size()));
   CUDA_TRY(cudaMemcpy(p->gtiles, gt.data(), gt.size(), cudaMemcpyHostToDevice));
 
+  if (p->NE == kInner) {
+    std::vector<float2> tw(kInner);
+    for (int t = 0; t < kInner; ++t) {
+      const double a = -2.0 * M_PI * double(t) / double(kInner);
+      tw[t] = make_float2(float(cos(a)), float(sin(a)));
+    }
+    CUDA_TRY(cudaMalloc(&p->tw8192, tw.size() * sizeof(float2)));
+    CUDA_TRY(cudaMemcpy(p->tw8192, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  }
+
   // engine order of k_f (32-bit words), per channel h: R rows of 8192 words, row = c0*R1 + c1 (outer digits); inside a
   // row  w = (cc*128 + k1)*4 + 2*pp + part  holds the 16-bit pair (part ? imag : real) of k_f at inner frequencies
   // k'' = k1 + 128*k2 with k2 = 4cc + 2pp and k2 + 1; natural frequency k = c0 + R0*(c1 + R1*k'').  See kf_pack_kernel.
@@ -327,7 +339,9 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
     CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkfGated));
     CUDA_TRY(cudaFuncSetAttribute(outer_tc_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOuterGated));
     CUDA_TRY(cudaFuncSetAttribute(outer_tc_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOuter));
+    CUDA_TRY(cudaFuncSetAttribute(bffc::ffft::kf_from_filter_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, bffc::ffft::kSmemBytes));
   );
+  CUDA_TRY(cudaFuncSetAttribute(bffc::ffft::dk_from_dkf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bffc::ffft::kSmemBytes));
   *out = p;
   return BFFC_OK;
 }
@@ -346,6 +360,7 @@ int bffc_plan_destroy(bffc_plan* p) {
   cudaFree(p->dftC);
   cudaFree(p->dftS);
   cudaFree(p->gtiles);
+  cudaFree(p->tw8192);
   for (auto& st : p->hs) if (st) cudaStreamDestroy(st);
   for (auto& ev : p->hev) if (ev) cudaEventDestroy(ev);
   delete p;
@@ -384,6 +399,32 @@ int bffc_kf_pack_rfft(const bffc_plan* p, const void* kf_half, void* kf_engine, 
   FMT_SWITCH(p->dtype, (kf_pack_kernel<true, F><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float2*>(kf_half), static_cast<uint4*>(kf_engine), p->NE, p->nlev >= 1 ? p->lev[0].R : 1,
       p->nlev == 2 ? p->lev[1].R : 1, p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj)););
+  CUDA_TRY(cudaGetLastError());
+  return BFFC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- filter-side FFTs
+int bffc_kf_from_filter(const bffc_plan* p, const void* k, int Lk, void* kf_engine, int H, int conj, void* stream) {
+  if (!p || !k || !kf_engine || H <= 0 || Lk <= 0) return fail(BFFC_ERR_INVALID, "bffc_kf_from_filter: bad argument");
+  if (p->NE != kInner) return fail(BFFC_ERR_UNSUPPORTED, "bffc_kf_from_filter: engine FFT size %d (only 8192 in this build; use rfft + bffc_kf_pack_rfft)", p->NE);
+  if (Lk > p->N) return fail(BFFC_ERR_INVALID, "bffc_kf_from_filter: Lk=%d exceeds seqlen %d", Lk, p->N);
+  using namespace bffc::ffft;
+  const float scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f;
+  FMT_SWITCH(p->dtype, (kf_from_filter_kernel<F><<<(H + 1) / 2, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(k), Lk, static_cast<uint4*>(kf_engine), H, scale, conj, p->tw8192)););
+  CUDA_TRY(cudaGetLastError());
+  return BFFC_OK;
+}
+
+int bffc_dk_from_dkf(const bffc_plan* p, const void* dkf_engine, void* dk, int Lk, int H, void* stream) {
+  if (!p || !dkf_engine || !dk || H <= 0 || Lk <= 0) return fail(BFFC_ERR_INVALID, "bffc_dk_from_dkf: bad argument");
+  if (p->NE != kInner) return fail(BFFC_ERR_UNSUPPORTED, "bffc_dk_from_dkf: engine FFT size %d (only 8192 in this build; use bffc_dkf_unpack + ifft)", p->NE);
+  if (Lk > p->N) return fail(BFFC_ERR_INVALID, "bffc_dk_from_dkf: Lk=%d exceeds seqlen %d", Lk, p->N);
+  using namespace bffc::ffft;
+  dk_from_dkf_kernel<<<H, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float2*>(dkf_engine), static_cast<float*>(dk), Lk,
+      p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 128.0f * float(p->R),      // as bffc_dkf_unpack
+      p->N < kInner ? kInner - p->N : 0, p->tw8192);
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -451,6 +492,25 @@ static void fill_params(const bffc_plan* p, bffc::FwdParams& prm, const void* kf
   prm.postgate = nullptr;
   prm.dbg = nullptr;
   prm.dbg_stages = 0;
+  prm.trace = nullptr;
+}
+
+// bring-up: BFFC_TRACE=<file> makes every ungated fused launch record the phase timeline of CTA 0 (tools/trace_fwd3.py)
+static long long* g_trace = nullptr;
+static long long* trace_buffer() {
+  static bool init = false;
+  if (!init) {
+    init = true;
+    if (getenv("BFFC_TRACE")) cudaMalloc(&g_trace, 3 * 2 * 64 * 16 * sizeof(long long));
+  }
+  if (g_trace) cudaMemset(g_trace, 0, 3 * 2 * 64 * 16 * sizeof(long long));
+  return g_trace;
+}
+static void trace_dump(cudaStream_t st) {
+  std::vector<long long> h(3 * 2 * 64 * 16);
+  cudaStreamSynchronize(st);
+  cudaMemcpy(h.data(), g_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+  if (FILE* f = fopen(getenv("BFFC_TRACE"), "wb")) { fwrite(h.data(), sizeof(long long), h.size(), f); fclose(f); }
 }
 
 // Segment geometry of the input tiles: S = 4096/N batch members per 8192-point slot for the small sizes, else 1.
@@ -503,7 +563,9 @@ static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const
     else if (use_fwd3()) {
       int g3 = (prm.units + kPipes3 - 1) / kPipes3;
       if (g3 > p->num_sms) g3 = p->num_sms;
+      prm.trace = trace_buffer();
       fwd3_kernel<false, F><<<g3, kThreads3, kSmemTotal3, st>>>(tm_u, tm_y, tm_g, prm);
+      if (prm.trace) trace_dump(st);
     } else
       fwd_kernel<false, false, false, F><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
   );

@@ -34,7 +34,9 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
 
   const int tid = threadIdx.x;
-  const int pipe = tid >> 7;           // one warpgroup = one pipeline
+  // one warpgroup = one pipeline.  Taken through a shuffle so that the compiler knows it is warp-uniform: everything
+  // the MMA issuer needs (slot addresses, TMEM columns, barriers, unit range) then lives in uniform registers.
+  const int pipe = __shfl_sync(0xffffffffu, tid >> 7, 0);
   const int lane = tid & 127;          // TMEM lane (= k1, later = i)
   const int warp_q = (tid >> 5) & 3;
   const bool lead_warp = ((tid & 127) < 32);
@@ -150,6 +152,11 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   const uint32_t sG0 = s_g;
   const f32x2 kfs2 = pk2(p.kf_scale, p.kf_scale);
 
+  // bring-up timeline (tools/trace_fwd3.py): lane 0 of warp 0 and of warp 3 of every pipeline of CTA 0
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && (tid & 31) == 0 && (warp_q == 0 || warp_q == 3);
+  long long* trace_base = p.trace + (size_t(pipe) * 2 + (warp_q == 3)) * 64 * 16;
+  int trace_n = 0;
+  auto stamp = [&](int ev) { if (tracing && trace_n < 64) trace_base[trace_n * 16 + ev] = clock64(); };
   uint32_t mma_phase = 0;
   auto wait_mma = [&]() {
     mbar_wait(bar_mma, mma_phase);
@@ -175,24 +182,39 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     const int slot = n & 1;
     const uint32_t sX = s_slot0 + slot * kSlotBytes;
     const int h = unit / p.pairs;
+    stamp(0);
 
     // ---------------- stage 1 (TS): D1 = F128 * X
     if (lead_warp) {
       mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
       tc_fence_after();
+      stamp(1);
       if (elect_one()) {
-        uint32_t acc = 0;
-        for (int s = 0; s < 8; ++s)
-          if ((p.kmask >> s) & 1) { mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, acc); acc = 1; }
-        for (int s = 0; s < 8; ++s)
-          if ((p.kmask >> s) & 1) mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN, 1);
-        for (int s = 0; s < 8; ++s)
-          if ((p.kmask >> s) & 1) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN_NEG, 1);
+        // descriptors are built once per unit; a K step moves the start-address field by (2048 >> 4)
+        const uint64_t dXr = tile_desc(sX), dXi = tile_desc(sX + kTileBytes);
+        if (p.kmask == 0xff) {      // full tiles: straight-line issue (the tensor pipe needs an MMA every 32-64 cycles)
+#pragma unroll
+          for (int s = 0; s < 8; ++s) mma_ts(tD0, tC0 + 8 * s, dXr + 128 * s, ID_N128_MN, s > 0);
+#pragma unroll
+          for (int s = 0; s < 8; ++s) mma_ts(tD0, tS0 + 8 * s, dXi + 128 * s, ID_N64_MN, 1);
+#pragma unroll
+          for (int s = 0; s < 8; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, dXr + 128 * s, ID_N64_MN_NEG, 1);
+        } else {                    // zero K steps (implicit padding, segmented small sizes) are skipped
+          uint32_t acc = 0;
+          for (int s = 0; s < 8; ++s)
+            if ((p.kmask >> s) & 1) { mma_ts(tD0, tC0 + 8 * s, dXr + 128 * s, ID_N128_MN, acc); acc = 1; }
+          for (int s = 0; s < 8; ++s)
+            if ((p.kmask >> s) & 1) mma_ts(tD0, tS0 + 8 * s, dXi + 128 * s, ID_N64_MN, 1);
+          for (int s = 0; s < 8; ++s)
+            if ((p.kmask >> s) & 1) mma_ts(tD0 + 64, tS0 + 8 * s, dXr + 128 * s, ID_N64_MN_NEG, 1);
+        }
         mma_commit(bar_mma);
       }
       __syncwarp();
     }
+    stamp(2);
     wait_mma();
+    stamp(3);
 
     // ---------------- pass 1: * W^{k1 j} -> A1 tiles in the slot (K-major: row = lane, column = j)
     {
@@ -221,15 +243,19 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
       }
     }
     }
+    stamp(4);
     sync_pipe_smem();
+    stamp(5);
     // ---------------- stage 2 (SS): D[:,0:128] = re * [Gr | Gi] + im * [-Gi | Gr]
     if (lead_warp) {
       tc_fence_after();
       if (elect_one()) {
-        for (int s = 0; s < 4; ++s)
-          mma_ss(tD0, atile_desc(sX + 32 * s), pair_desc(sG0 + s * 2048, 8192), ID_N128_MN, s > 0);
-        for (int s = 0; s < 4; ++s)
-          mma_ss(tD0, atile_desc(sX + kTileBytes + 32 * s), pair_desc(sG0 + 16384 + s * 2048, 8192), ID_N128_MN, 1);
+        const uint64_t dAr = atile_desc(sX), dAi = atile_desc(sX + kTileBytes);
+        const uint64_t dG0 = pair_desc(sG0, 8192), dG1 = pair_desc(sG0 + 16384, 8192);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) mma_ss(tD0, dAr + 2 * s, dG0 + 128 * s, ID_N128_MN, s > 0);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) mma_ss(tD0, dAi + 2 * s, dG1 + 128 * s, ID_N128_MN, 1);
         mma_commit(bar_mma);
         if (unit + 1 < u_end) {
           tma_store_wait_read0();
@@ -245,7 +271,9 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     uint4 kfa[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) kfa[c] = __ldg(kfp + c * 128);
+    stamp(6);
     wait_mma();
+    stamp(7);
 
     // ---------------- pass 3: * k_f -> A3 tiles.  Each first-half vector is replaced by its second-half counterpart
     // as soon as it has been used (4 steps = several hundred cycles before the second half needs it).
@@ -278,20 +306,25 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         }
       }
     }
+    stamp(8);
     sync_pipe_smem();
     // ---------------- stage 3 (SS): inverse radix-64
     if (lead_warp) {
       tc_fence_after();
       if (elect_one()) {
-        for (int s = 0; s < 4; ++s)
-          mma_ss(tD0, atile_desc(sX + 32 * s), pair_desc(sG0 + s * 2048, 16384), ID_N128_MN, s > 0);
-        for (int s = 0; s < 4; ++s)
-          mma_ss(tD0, atile_desc(sX + kTileBytes + 32 * s), pair_desc(sG0 + 8192 + s * 2048, 16384), ID_N128_MN, 1);
+        const uint64_t dAr = atile_desc(sX), dAi = atile_desc(sX + kTileBytes);
+        const uint64_t dG0 = pair_desc(sG0, 16384), dG1 = pair_desc(sG0 + 8192, 16384);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) mma_ss(tD0, dAr + 2 * s, dG0 + 128 * s, ID_N128_MN, s > 0);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) mma_ss(tD0, dAi + 2 * s, dG1 + 128 * s, ID_N128_MN, 1);
         mma_commit(bar_mma);
       }
       __syncwarp();
     }
+    stamp(9);
     wait_mma();
+    stamp(10);
 
     // ---------------- pass 5: * conj W -> Y tiles (MN-major B operand of stage 4; same bytes as a K-major A tile)
     {
@@ -320,19 +353,26 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
       }
     }
     }
+    stamp(11);
     sync_pipe_smem();
     // ---------------- stage 4 (TS): conj F128 * Y
     if (lead_warp) {
       tc_fence_after();
       if (elect_one()) {
-        for (int s = 0; s < 8; ++s) mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, s > 0);
-        for (int s = 0; s < 8; ++s) mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN_NEG, 1);
-        for (int s = 0; s < 8; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN, 1);
+        const uint64_t dYr = tile_desc(sX), dYi = tile_desc(sX + kTileBytes);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_ts(tD0, tC0 + 8 * s, dYr + 128 * s, ID_N128_MN, s > 0);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_ts(tD0, tS0 + 8 * s, dYi + 128 * s, ID_N64_MN_NEG, 1);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, dYr + 128 * s, ID_N64_MN, 1);
         mma_commit(bar_mma);
       }
       __syncwarp();
     }
+    stamp(12);
     wait_mma();
+    stamp(13);
 
     // ---------------- pass 6: fp32 -> 16 bit output tiles, TMA store
     {
@@ -355,6 +395,7 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
       }
     }
     }
+    stamp(14);
     sync_pipe_smem();
     if (lead_warp) {
       if (elect_one()) {
@@ -366,6 +407,8 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
       }
       __syncwarp();
     }
+    stamp(15);
+    ++trace_n;
   }
 
   if (lead_warp) tma_store_wait_all0();

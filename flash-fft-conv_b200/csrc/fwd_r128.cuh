@@ -45,6 +45,7 @@ struct FwdParams {
   int units;                 // H * pairs
   float* dbg;                // optional stage dump [stage][128][128]
   int dbg_stages;
+  long long* trace;          // bring-up only (env BFFC_TRACE): clock64 stamps of CTA 0, [pipe][warp 0|3][unit][16]
 };
 
 namespace r128 {

@@ -6,8 +6,10 @@ Drop-in for `flashfftconv.FlashFFTConv` (reference flashfftconv/conv.py:71-560):
 (`backward -> (du, dk, None[, dpregate, dpostgate])`, conv.py:1822, :3939).
 
 All arithmetic on the hot path happens in libbffc.so (hand-written sm_100a CUDA, C ABI in
-include/bffc.h).  PyTorch is used for device memory, streams and — exactly as the reference does at
-conv.py:575 and :1817 — for the fp32 FFT of the filter `k` and the inverse FFT of `dk_f`.
+include/bffc.h).  PyTorch is used for device memory and streams.  For seqlen <= 8192 the filter-side
+transforms (k -> k_f, dk_f -> dk) are library launches too (bffc_kf_from_filter / bffc_dk_from_dkf);
+for longer sequences they still go through torch.fft in fp32 exactly as the reference does at
+conv.py:575 and :1817, followed by the library's pack / unpack kernels.
 """
 import ctypes
 
@@ -146,8 +148,27 @@ def _pack_kf_from_natural(mod, plan, k_f, conj):
     return kf_engine
 
 
+def _filter_state(mod, k):
+    """What forward keeps of the filter for backward.  Engine FFT size 8192 (seqlen <= 8192): the fp32 filter itself —
+    its spectrum is produced in engine order by ONE launch of the library (bffc_kf_from_filter) whenever needed.
+    Larger sizes: the rfft of the filter, as the reference keeps k_f (conv.py:575, :588)."""
+    if mod.fft_size(k.device) == 8192:
+        return k.detach().to(torch.float32).contiguous()
+    return _kf_natural(mod, k)
+
+
+def _kf_engine(mod, plan, state, conj):
+    """engine-order packed k_f (H, N) from _filter_state()."""
+    if state.is_complex():
+        return _pack_kf_from_natural(mod, plan, state, conj)
+    H, Lk = state.shape
+    kf_engine = torch.empty((H, 8192), dtype=torch.int32, device=state.device)
+    _lib.check(_lib.lib().bffc_kf_from_filter(plan.handle, _ptr(state), int(Lk), _ptr(kf_engine), int(H), int(conj), _stream()))
+    return kf_engine
+
+
 def _pack_kf(mod, plan, k, conj):
-    return _pack_kf_from_natural(mod, plan, _kf_natural(mod, k), conj)
+    return _kf_engine(mod, plan, _filter_state(mod, k), conj)
 
 
 def _pad_len(mod, device, L):
@@ -174,8 +195,8 @@ def _fwd(mod, u, k, pregate, postgate):
     B, H, L = u.shape
     plan = mod.plan(u.device)
     with torch.cuda.device(u.device):
-        k_f = _kf_natural(mod, k)
-        kf_engine = _pack_kf_from_natural(mod, plan, k_f, conj=0)
+        k_f = _filter_state(mod, k)
+        kf_engine = _kf_engine(mod, plan, k_f, conj=0)
         y = torch.empty_like(u)
         ws_bytes = _lib.lib().bffc_workspace_bytes(plan.handle, B, H, L)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=u.device) if ws_bytes else None
@@ -197,8 +218,8 @@ def _bwd(mod, dout, u, k_f, k_len, pregate, postgate):
     plan = mod.plan(u.device)
     dout = dout.contiguous()                                          # conv.py:1742
     with torch.cuda.device(u.device):
-        kf_conj = _pack_kf_from_natural(mod, plan, k_f, conj=1)
-        kf_eng = _pack_kf_from_natural(mod, plan, k_f, conj=0) if pregate is not None else None
+        kf_conj = _kf_engine(mod, plan, k_f, conj=1)
+        kf_eng = _kf_engine(mod, plan, k_f, conj=0) if pregate is not None else None
         du = torch.empty_like(u)
         dkf_engine = torch.empty((H, N, 2), dtype=torch.float32, device=u.device)
         dpre = torch.empty_like(u) if pregate is not None else None
@@ -208,14 +229,16 @@ def _bwd(mod, dout, u, k_f, k_len, pregate, postgate):
         _lib.check(_lib.lib().bffc_bwd(plan.handle, _ptr(dout), _ptr(u), _ptr(kf_eng), _ptr(kf_conj), _ptr(pregate),
                                        _ptr(postgate), _ptr(du), _ptr(dkf_engine), _ptr(dpre), _ptr(dpost),
                                        B, H, L, _ptr(ws), ws_bytes, _stream()))
+        if N == 8192:
+            # one launch: inverse fp32 FFT straight from engine order, 1/N, real part, fold of the small sizes, [:k_len]
+            dk = torch.empty((H, k_len), dtype=torch.float32, device=u.device)
+            _lib.check(_lib.lib().bffc_dk_from_dkf(plan.handle, _ptr(dkf_engine), _ptr(dk), int(k_len), H, _stream()))
+            return du, dk, dpre, dpost
         dkf_nat = torch.empty((H, N), dtype=torch.complex64, device=u.device)
         _lib.check(_lib.lib().bffc_dkf_unpack(plan.handle, _ptr(dkf_engine), _ptr(torch.view_as_real(dkf_nat)), H,
                                               _stream()))
         # the kernel accumulates unnormalised spectra; ifft's 1/N completes the correlation (conv.py:1817-1820)
-        c = torch.fft.ifft(dkf_nat, dim=-1).real
-        if N != mod.seqlen:        # small sizes: fold the linear correlation (lags -seqlen..seqlen) modulo seqlen
-            c = c[..., : mod.seqlen] + c[..., N - mod.seqlen:]
-        dk = c[..., :k_len].contiguous()
+        dk = torch.fft.ifft(dkf_nat, dim=-1).real[..., :k_len].contiguous()
     return du, dk, dpre, dpost
 
 

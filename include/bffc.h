@@ -87,6 +87,19 @@ int bffc_kf_pack_rfft(const bffc_plan* plan, const void* kf_half, void* kf_engin
 int bffc_dkf_unpack(const bffc_plan* plan, const void* dkf_engine, void* dkf_natural, int H,
                     void* stream);
 
+/*
+ * Filter-side transforms in one launch each, for plans whose bffc_fft_size() is 8192 (seqlen <= 8192; other plans
+ * return BFFC_ERR_UNSUPPORTED and the caller uses rfft + bffc_kf_pack_rfft / bffc_dkf_unpack + ifft):
+ *   bffc_kf_from_filter: k (H, Lk) fp32 device, Lk <= seqlen  ->  kf_engine, = bffc_kf_pack_rfft(rfft(k, n=8192))
+ *                        (replaces conv.py:572-575 + :640, fp32 FFT on CUDA cores, two channels per complex FFT)
+ *   bffc_dk_from_dkf:    dkf_engine (H, 8192) float2 as written by bffc_bwd  ->  dk (H, Lk) fp32
+ *                        = ifft(unpack(dkf)).real[:, :Lk] incl. the fold of the small sizes (replaces conv.py:1817-1820)
+ */
+int bffc_kf_from_filter(const bffc_plan* plan, const void* k, int Lk, void* kf_engine, int H, int conj,
+                        void* stream);
+int bffc_dk_from_dkf(const bffc_plan* plan, const void* dkf_engine, void* dk, int Lk, int H,
+                     void* stream);
+
 /* Scratch the caller must provide to bffc_fwd / bffc_bwd (0 for fully fused sizes). */
 size_t bffc_workspace_bytes(const bffc_plan* plan, int B, int H, int L);
 

@@ -382,3 +382,60 @@ def test_forward_host_rejects_bad_arguments(ffc):
     plan = conv.plan(torch.device('cuda', 0))
     rc = lib.bffc_fwd_host(plan.handle, u.data_ptr(), None, None, None, u.data_ptr(), 2, 2, 8192, None, 0, None)
     assert rc != 0 and b'null' in lib.bffc_last_error()
+
+
+# ----------------------------------------------------------------------------- filter-side FFT kernels (seqlen <= 8192)
+def _unpack_kf(kf_engine, dtype):
+    """engine words (H, 8192) int32 = (re01, im01, re23, im23) groups -> (H, 2048, 4) complex64, engine order"""
+    w = kf_engine.view(torch.int16).view(dtype).float().reshape(kf_engine.shape[0], -1, 4, 2)     # [v][re01 im01 re23 im23][2]
+    re = torch.stack([w[:, :, 0, 0], w[:, :, 0, 1], w[:, :, 2, 0], w[:, :, 2, 1]], dim=-1)
+    im = torch.stack([w[:, :, 1, 0], w[:, :, 1, 1], w[:, :, 3, 0], w[:, :, 3, 1]], dim=-1)
+    return torch.complex(re, im)
+
+
+@pytest.mark.parametrize('N,H,Lk,dtype', [(8192, 5, 8192, torch.bfloat16), (8192, 4, 1000, torch.bfloat16),
+                                          (1024, 3, 1024, torch.bfloat16), (8192, 2, 8192, torch.float16)])
+@pytest.mark.parametrize('conj', [0, 1])
+def test_kf_from_filter_matches_rfft_pack(ffc, N, H, Lk, dtype, conj):
+    """bffc_kf_from_filter (own fp32 FFT, two channels per complex transform, engine order) == rfft + bffc_kf_pack_rfft
+    up to fp32 round-off before the 16-bit rounding (<= 1 ulp of the 16-bit format on a few elements)."""
+    from flashfftconv import conv as C
+    torch.manual_seed(5)
+    mod = ffc.FlashFFTConv(N, dtype=dtype).cuda()
+    dev = torch.device('cuda', 0)
+    plan = mod.plan(dev)
+    k = (torch.randn(H, Lk) * torch.exp(-0.002 * torch.arange(Lk))).cuda()
+    a = _unpack_kf(C._kf_engine(mod, plan, C._filter_state(mod, k), conj), dtype)
+    b = _unpack_kf(C._pack_kf_from_natural(mod, plan, C._kf_natural(mod, k), conj), dtype)
+    ulp = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10    # largest relative spacing of the 16-bit format
+    err = (a - b).abs()
+    tol = ulp * b.abs().clamp_min(1e-30) * 1.5 + 1e-6 * b.abs().max()     # both components may flip one spacing
+    assert bool((err <= tol).all()), f'max excess {(err - tol).max().item():.3e}'
+    assert float((err > 0).float().mean()) < 0.02          # 16-bit roundings flip on a small fraction only
+
+
+@pytest.mark.parametrize('N,H,Lk', [(8192, 3, 8192), (8192, 2, 777), (2048, 3, 2048), (256, 2, 100)])
+def test_dk_from_dkf_matches_unpack_ifft(ffc, N, H, Lk):
+    torch.manual_seed(6)
+    mod = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    plan = mod.plan(torch.device('cuda', 0))
+    lib = ffc._lib.lib()
+    dkf = torch.randn(H, 8192, 2, device='cuda')
+    nat = torch.empty(H, 8192, dtype=torch.complex64, device='cuda')
+    ffc._lib.check(lib.bffc_dkf_unpack(plan.handle, dkf.data_ptr(), torch.view_as_real(nat).data_ptr(), H, None))
+    c = torch.fft.ifft(nat, dim=-1).real
+    if N != 8192:
+        c = c[..., :N] + c[..., 8192 - N:]
+    dk = torch.empty(H, Lk, device='cuda')
+    ffc._lib.check(lib.bffc_dk_from_dkf(plan.handle, dkf.data_ptr(), dk.data_ptr(), Lk, H, None))
+    torch.cuda.synchronize()
+    assert torch.allclose(dk, c[..., :Lk], rtol=1e-4, atol=1e-5 * c.abs().max().item())
+
+
+def test_filter_fft_entry_points_reject_long_plans(ffc):
+    mod = ffc.FlashFFTConv(32768, dtype=torch.bfloat16).cuda()
+    plan = mod.plan(torch.device('cuda', 0))
+    lib = ffc._lib.lib()
+    x = torch.zeros(2, 32768, device='cuda')
+    assert lib.bffc_kf_from_filter(plan.handle, x.data_ptr(), 32768, x.data_ptr(), 2, 0, None) != 0
+    assert b'8192' in lib.bffc_last_error()

@@ -1,5 +1,5 @@
 #!/bin/bash
-# quick correctness + kernel-time check of the fused forward kernel
+# quick correctness + timing check
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_parity_gpu.py -x -q -m gpu -k "fwd or small or composite or long" 2>&1 | tail -4
-timeout 300 python tools/step_breakdown.py 2>&1 | head -4
+timeout 900 python -m pytest tests/test_parity_gpu.py -x -q -m gpu 2>&1 | tail -6
+timeout 300 python tools/step_breakdown.py 2>&1 | tail -9
