@@ -40,6 +40,27 @@ def algorithmic_bytes(N, B, H, L, gated):
     return (8 if gated else 4) * L * B * H + 4 * N * H
 
 
+def issued_tensor_flops(N, B, H):
+    """Matmul flops the inner 8192-point kernel issues: 25.2 MFLOP per unit (a pair of sequences of one
+    channel; an odd batch still runs a full unit), N/8192 units per pair for the composite sizes; the outer radix-128
+    stage of the 1M+ sizes adds 2 x 128 x 256 x 2 flops per complex column.  Sizes below 8192 share one unit between
+    4096/N batch pairs."""
+    unit = 2.0 * 128 * 128 * (2 * 256 + 2 * 128)
+    ne = max(N, 8192)
+    seg = 4096 // N if N < 8192 else 1
+    groups = (B + 2 * seg - 1) // (2 * seg)
+    flops = groups * H * (ne // 8192) * unit
+    if N >= (1 << 20):
+        flops += ((B + 1) // 2) * H * 2.0 * (2.0 * 128 * 128 * 256) * (N // 128 // 64)
+    return flops
+
+
+def reference_tensor_flops(N, B, H):
+    """SURVEY.md §8(d) 'algorithmic flops per conv' of the reference's own factorisation, forward."""
+    per_conv = {8192: 6.29e6, 32768: 41.9e6, 1 << 20: 1.88e9, 1 << 22: 10.7e9}.get(N)
+    return per_conv * B * H if per_conv else None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks + throttle reasons while the GPU is under the benchmark load
     (B200_PROFILING.md 'clocks line'): one persistent `nvidia-smi -lms 100`, samples are time-stamped and only
@@ -291,6 +312,11 @@ def run_ours(args):
     except Exception:
         pass
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    bf16_peak = float(peaks.get('bf16_tflops', peaks.get('bf16_tfs', 0)) or 0)
+    if not bf16_peak:
+        bf16_peak = next((float(v) for k_, v in peaks.items() if 'bf16' in k_.lower() and isinstance(v, (int, float))), 1640.0)
+    tflops_issued = issued_tensor_flops(N, B, H)
+    ref_flops = reference_tensor_flops(N, B, H)
     peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s'
     abytes = algorithmic_bytes(N, B, H, L, gated)
     achieved = abytes / (kern_ms * 1e-3) / 1e9
@@ -305,15 +331,21 @@ def run_ours(args):
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
         'config': {'workload': f'{args.workload}: FlashFFTConv({N}, bf16) fwd, B={B} H={H} L={L} '
                                f'{"gated" if gated else "ungated"} per GPU (BASELINE.json configs); '
-                               f'step = k->k_f (torch.fft.rfft + bffc_kf_pack_rfft) + conv kernels',
+                               f'step = k->k_f (bffc_kf_from_filter for seqlen <= 8192, else torch.fft.rfft + bffc_kf_pack_rfft) + conv kernels',
                    'l2': f'inputs+outputs {abytes / 1e6:.0f} MB per step exceed the 126 MB L2 (no flush needed)',
                    'sharding': 'B x H sharded over ranks, no data-path collective'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
                      'traffic': traffic,
-                     'kernel': 'bffc::r128::fwd_kernel' if N == 8192 else 'bffc_fwd native path (outer stages + bffc::r128::fwd_kernel)',
+                     'kernel': 'bffc::r128::fwd3_kernel' if N == 8192 and not gated else 'bffc_fwd native path (outer stages / fold + bffc::r128 fused kernel)',
                      'kernel_ms': kern_ms,
                      'algorithmic_bytes': abytes, 'peak_source': peak_src,
                      'kernel_convs_per_sec': convs_per_step / (kern_ms * 1e-3)},
+        # the tighter roofline at 8192 under this factorisation (report both): flops actually issued
+        # to the tensor pipe per launch vs the measured dense bf16 peak (itself power limited on this board)
+        'roofline_tensor': {'bound': 'tensor', 'achieved': tflops_issued / (kern_ms * 1e-3) / 1e12, 'peak': bf16_peak,
+                            'unit': 'TFLOP/s', 'frac': tflops_issued / (kern_ms * 1e-3) / 1e12 / bf16_peak,
+                            'issued_flops': tflops_issued, 'reference_factorisation_flops': ref_flops,
+                            'note': 'radix 128 x 64 issues 2x the matmul flops of the reference split (DESIGN.md §6)'},
         'e2e': {'value': convs_per_step * world / (e2e_ms * 1e-3), 'unit': 'convs/s',
                 'h2d_bytes_per_step': u_h.numel() * 2 * (3 if gated else 1) + k_h.numel() * 4,
                 'd2h_bytes_per_step': y_h.numel() * 2,

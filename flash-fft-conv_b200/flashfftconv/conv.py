@@ -12,6 +12,7 @@ for longer sequences they still go through torch.fft in fp32 exactly as the refe
 conv.py:575 and :1817, followed by the library's pack / unpack kernels.
 """
 import ctypes
+import os
 
 import torch
 
@@ -152,7 +153,7 @@ def _filter_state(mod, k):
     """What forward keeps of the filter for backward.  Engine FFT size 8192 (seqlen <= 8192): the fp32 filter itself —
     its spectrum is produced in engine order by ONE launch of the library (bffc_kf_from_filter) whenever needed.
     Larger sizes: the rfft of the filter, as the reference keeps k_f (conv.py:575, :588)."""
-    if mod.fft_size(k.device) == 8192:
+    if mod.fft_size(k.device) == 8192 and os.environ.get('BFFC_FILTER_FFT', '1') != '0':   # '0': A/B against cuFFT + pack
         return k.detach().to(torch.float32).contiguous()
     return _kf_natural(mod, k)
 
@@ -229,7 +230,7 @@ def _bwd(mod, dout, u, k_f, k_len, pregate, postgate):
         _lib.check(_lib.lib().bffc_bwd(plan.handle, _ptr(dout), _ptr(u), _ptr(kf_eng), _ptr(kf_conj), _ptr(pregate),
                                        _ptr(postgate), _ptr(du), _ptr(dkf_engine), _ptr(dpre), _ptr(dpost),
                                        B, H, L, _ptr(ws), ws_bytes, _stream()))
-        if N == 8192:
+        if N == 8192 and not k_f.is_complex():
             # one launch: inverse fp32 FFT straight from engine order, 1/N, real part, fold of the small sizes, [:k_len]
             dk = torch.empty((H, k_len), dtype=torch.float32, device=u.device)
             _lib.check(_lib.lib().bffc_dk_from_dkf(plan.handle, _ptr(dkf_engine), _ptr(dk), int(k_len), H, _stream()))
@@ -238,7 +239,10 @@ def _bwd(mod, dout, u, k_f, k_len, pregate, postgate):
         _lib.check(_lib.lib().bffc_dkf_unpack(plan.handle, _ptr(dkf_engine), _ptr(torch.view_as_real(dkf_nat)), H,
                                               _stream()))
         # the kernel accumulates unnormalised spectra; ifft's 1/N completes the correlation (conv.py:1817-1820)
-        dk = torch.fft.ifft(dkf_nat, dim=-1).real[..., :k_len].contiguous()
+        c = torch.fft.ifft(dkf_nat, dim=-1).real
+        if N != mod.seqlen:        # small sizes: fold the linear correlation (lags -seqlen..seqlen) modulo seqlen
+            c = c[..., : mod.seqlen] + c[..., N - mod.seqlen:]
+        dk = c[..., :k_len].contiguous()
     return du, dk, dpre, dpost
 
 
