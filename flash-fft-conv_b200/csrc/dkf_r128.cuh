@@ -53,7 +53,7 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
 
   const int tid = threadIdx.x;
-  const int pipe = tid >> 8;           // 0: u, 1: dout
+  const int pipe = __shfl_sync(0xffffffffu, tid >> 8, 0);   // warp-uniform for the compiler (uniform-register MMA issue)           // 0: u, 1: dout
   const int half = (tid >> 7) & 1;
   const int lane = tid & 127;
   const int warp_q = (tid >> 5) & 3;
@@ -192,13 +192,23 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
       if (!(!kPlanes && p.gated)) mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
-        uint32_t acc = 0;
-        for (int s = 0; s < 8; ++s)
-          if ((p.kmask >> s) & 1) { mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, acc); acc = 1; }
-        for (int s = 0; s < 8; ++s)
-          if ((p.kmask >> s) & 1) mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN, 1);
-        for (int s = 0; s < 8; ++s)
-          if ((p.kmask >> s) & 1) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN_NEG, 1);
+        const uint64_t dXr = tile_desc(sX), dXi = tile_desc(sX + kTileBytes);   // a K step = +(2048 >> 4) in the address field
+        if (p.kmask == 0xff) {
+#pragma unroll
+          for (int s = 0; s < 8; ++s) mma_ts(tD0, tC0 + 8 * s, dXr + 128 * s, ID_N128_MN, s > 0);
+#pragma unroll
+          for (int s = 0; s < 8; ++s) mma_ts(tD0, tS0 + 8 * s, dXi + 128 * s, ID_N64_MN, 1);
+#pragma unroll
+          for (int s = 0; s < 8; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, dXr + 128 * s, ID_N64_MN_NEG, 1);
+        } else {
+          uint32_t acc = 0;
+          for (int s = 0; s < 8; ++s)
+            if ((p.kmask >> s) & 1) { mma_ts(tD0, tC0 + 8 * s, dXr + 128 * s, ID_N128_MN, acc); acc = 1; }
+          for (int s = 0; s < 8; ++s)
+            if ((p.kmask >> s) & 1) mma_ts(tD0, tS0 + 8 * s, dXi + 128 * s, ID_N64_MN, 1);
+          for (int s = 0; s < 8; ++s)
+            if ((p.kmask >> s) & 1) mma_ts(tD0 + 64, tS0 + 8 * s, dXr + 128 * s, ID_N64_MN_NEG, 1);
+        }
         mma_commit(bar_mma);
         if (n + 1 < n_units) issue_load(n + 1, slot ^ 1);   // other slot: its stage 1 finished a unit ago
       }
@@ -232,8 +242,11 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
     if (lead_warp) {
       tc_fence_after();
       if (elect_one()) {
-        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 8 * s, pair_desc(sG0 + s * 2048, 8192), ID_N128_MN, s > 0);
-        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 32 + 8 * s, pair_desc(sG0 + 16384 + s * 2048, 8192), ID_N128_MN, 1);
+        const uint64_t dG0 = pair_desc(sG0, 8192), dG1 = pair_desc(sG0 + 16384, 8192);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 8 * s, dG0 + 128 * s, ID_N128_MN, s > 0);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 32 + 8 * s, dG1 + 128 * s, ID_N128_MN, 1);
         mma_commit(bar_mma);
       }
       __syncwarp();

@@ -119,7 +119,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));  // generic pointer to aligned base
 
   const int tid = threadIdx.x;
-  const int pipe = tid >> 8;           // pipeline = pair of warpgroups
+  const int pipe = __shfl_sync(0xffffffffu, tid >> 8, 0);   // warp-uniform for the compiler (uniform-register MMA issue)           // pipeline = pair of warpgroups
   const int half = (tid >> 7) & 1;     // which 32-column half of every pass this warpgroup handles
   const int lane = tid & 127;          // TMEM lane owned by this thread (= k1, later = i)
   const int warp_q = (tid >> 5) & 3;   // TMEM sub-partition of this warp
@@ -296,15 +296,24 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
       if (!(kGated && p.pregate != nullptr)) mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
-      // D[:,0:128]  = C * [Xr | Xi]
-      uint32_t acc = 0;
-      for (int s = 0; s < 8; ++s)
-        if ((p.kmask >> s) & 1) { mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, acc); acc = 1; }
-      // D[:,0:64]  += S * Xi ;  D[:,64:128] += (-S) * Xr        (F = C - iS)
-      for (int s = 0; s < 8; ++s)
-        if ((p.kmask >> s) & 1) mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN, 1);
-      for (int s = 0; s < 8; ++s)
-        if ((p.kmask >> s) & 1) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN_NEG, 1);
+      // D[:,0:128]  = C * [Xr | Xi];  D[:,0:64]  += S * Xi ;  D[:,64:128] += (-S) * Xr        (F = C - iS)
+      const uint64_t dXr = tile_desc(sX), dXi = tile_desc(sX + kTileBytes);   // a K step = +(2048 >> 4) in the address field
+      if (p.kmask == 0xff) {
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_ts(tD0, tC0 + 8 * s, dXr + 128 * s, ID_N128_MN, s > 0);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_ts(tD0, tS0 + 8 * s, dXi + 128 * s, ID_N64_MN, 1);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, dXr + 128 * s, ID_N64_MN_NEG, 1);
+      } else {
+        uint32_t acc = 0;
+        for (int s = 0; s < 8; ++s)
+          if ((p.kmask >> s) & 1) { mma_ts(tD0, tC0 + 8 * s, dXr + 128 * s, ID_N128_MN, acc); acc = 1; }
+        for (int s = 0; s < 8; ++s)
+          if ((p.kmask >> s) & 1) mma_ts(tD0, tS0 + 8 * s, dXi + 128 * s, ID_N64_MN, 1);
+        for (int s = 0; s < 8; ++s)
+          if ((p.kmask >> s) & 1) mma_ts(tD0 + 64, tS0 + 8 * s, dXr + 128 * s, ID_N64_MN_NEG, 1);
+      }
       mma_commit(bar_mma);
       }
       __syncwarp();
@@ -345,8 +354,11 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
     if (lead_warp) {
       tc_fence_after();
       if (elect_one()) {
-        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 8 * s, pair_desc(sG0 + s * 2048, 8192), ID_N128_MN, s > 0);
-        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 32 + 8 * s, pair_desc(sG0 + 16384 + s * 2048, 8192), ID_N128_MN, 1);
+        const uint64_t dG0 = pair_desc(sG0, 8192), dG1 = pair_desc(sG0 + 16384, 8192);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 8 * s, dG0 + 128 * s, ID_N128_MN, s > 0);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 32 + 8 * s, dG1 + 128 * s, ID_N128_MN, 1);
         mma_commit(bar_mma);
         // prefetch the next unit into the other slot.  Its last reader was the previous unit's TMA store, issued
         // a full stage-1 + pass-1 ago: waiting for it here (not before stage 1) keeps the issuing warp from
@@ -389,8 +401,11 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
     if (lead_warp) {
       tc_fence_after();
       if (elect_one()) {
-        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 8 * s, pair_desc(sG0 + s * 2048, 16384), ID_N128_MN, s > 0);
-        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 32 + 8 * s, pair_desc(sG0 + 8192 + s * 2048, 16384), ID_N128_MN, 1);
+        const uint64_t dG0 = pair_desc(sG0, 16384), dG1 = pair_desc(sG0 + 8192, 16384);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 8 * s, dG0 + 128 * s, ID_N128_MN, s > 0);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) mma_ts(tD0, tA0 + 32 + 8 * s, dG1 + 128 * s, ID_N128_MN, 1);
         mma_commit(bar_mma);
       }
       __syncwarp();
@@ -431,10 +446,14 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
     if (lead_warp) {
       tc_fence_after();
       if (elect_one()) {
-        for (int s = 0; s < 8; ++s) mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, s > 0);
+        const uint64_t dYr = tile_desc(sX), dYi = tile_desc(sX + kTileBytes);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_ts(tD0, tC0 + 8 * s, dYr + 128 * s, ID_N128_MN, s > 0);
         // D[:,0:64] += (-S) * Yi ;  D[:,64:128] += S * Yr       (conj F = C + iS)
-        for (int s = 0; s < 8; ++s) mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), ID_N64_MN_NEG, 1);
-        for (int s = 0; s < 8; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), ID_N64_MN, 1);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_ts(tD0, tS0 + 8 * s, dYi + 128 * s, ID_N64_MN_NEG, 1);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, dYr + 128 * s, ID_N64_MN, 1);
         mma_commit(bar_mma);
       }
       __syncwarp();

@@ -54,7 +54,7 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
 
   const int tid = threadIdx.x;
-  const int pipe = tid >> 8;
+  const int pipe = __shfl_sync(0xffffffffu, tid >> 8, 0);   // warp-uniform for the compiler (uniform-register MMA issue)
   const int half = (tid >> 7) & 1;
   const int lane = tid & 127;
   const int warp_q = (tid >> 5) & 3;
@@ -229,12 +229,20 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
       tc_fence_after();
       if (elect_one()) {
         const int ks = kInverse ? 8 : p.ksteps;
-        for (int s = 0; s < ks; ++s) mma_ts(tD0, tC0 + 8 * s, tile_desc(sX + s * 2048), ID_N128_MN, s > 0);
+        const uint64_t dXr = tile_desc(sX), dXi = tile_desc(sX + kTileBytes);   // a K step = +(2048 >> 4) in the address field
         // forward F = C - iS: D[:,0:64] += S*Xi, D[:,64:128] -= S*Xr ; inverse conj F: signs swapped
-        for (int s = 0; s < ks; ++s)
-          mma_ts(tD0, tS0 + 8 * s, tile_desc(sX + kTileBytes + s * 2048), kInverse ? ID_N64_MN_NEG : ID_N64_MN, 1);
-        for (int s = 0; s < ks; ++s)
-          mma_ts(tD0 + 64, tS0 + 8 * s, tile_desc(sX + s * 2048), kInverse ? ID_N64_MN : ID_N64_MN_NEG, 1);
+        if (ks == 8) {
+#pragma unroll
+          for (int s = 0; s < 8; ++s) mma_ts(tD0, tC0 + 8 * s, dXr + 128 * s, ID_N128_MN, s > 0);
+#pragma unroll
+          for (int s = 0; s < 8; ++s) mma_ts(tD0, tS0 + 8 * s, dXi + 128 * s, kInverse ? ID_N64_MN_NEG : ID_N64_MN, 1);
+#pragma unroll
+          for (int s = 0; s < 8; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, dXr + 128 * s, kInverse ? ID_N64_MN : ID_N64_MN_NEG, 1);
+        } else {
+          for (int s = 0; s < ks; ++s) mma_ts(tD0, tC0 + 8 * s, dXr + 128 * s, ID_N128_MN, s > 0);
+          for (int s = 0; s < ks; ++s) mma_ts(tD0, tS0 + 8 * s, dXi + 128 * s, kInverse ? ID_N64_MN_NEG : ID_N64_MN, 1);
+          for (int s = 0; s < ks; ++s) mma_ts(tD0 + 64, tS0 + 8 * s, dXr + 128 * s, kInverse ? ID_N64_MN : ID_N64_MN_NEG, 1);
+        }
         mma_commit(bar_mma);
         // next unit -> next ring slot (ungated: its last reader, a TMA store, was issued two units ago)
         if (unit + 1 < u_end) {
