@@ -622,8 +622,15 @@ static void fill_step(bffc::outer::OuterParams& op, double n_level) {
 }
 
 template <int R, int F>
-static void launch_cc(bool inverse, bool gated, bool planes, const bffc::outer::OuterParams& op, int rows, cudaStream_t st) {
+static void launch_cc(bool inverse, bool gated, bool planes, const bffc::outer::OuterParams& op_in, int rows, cudaStream_t st) {
   using namespace bffc::outer;
+  OuterParams op = op_in;
+  // read-ahead distance = the number of resident blocks (one residency period ahead; measured optimum at C3:
+  // 0 -> 0.827 ms, 296 -> 0.690, 592 -> 0.693, 1184 -> 0.725, 2368 -> 0.985 ms for the three kernels)
+  static const int la_env = getenv("BFFC_LOOKAHEAD") ? atoi(getenv("BFFC_LOOKAHEAD")) : -1;
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  op.lookahead = la_env >= 0 ? la_env : sms * (R <= 4 ? 4 : 2);
   const int cb = op.M / (kVec * 128);
   if (planes) {
     dim3 grid(rows, cb, 1);
