@@ -12,6 +12,7 @@
 #include "fwd_r128.cuh"
 #include "fwd3_r128.cuh"
 #include "dkf_r128.cuh"
+#include "dkf3_r128.cuh"
 #include "outer_cuda.cuh"
 #include "outer_r128.cuh"
 #include "filter_fft.cuh"
@@ -202,6 +203,15 @@ __global__ void kf_pack_tiled_kernel(const float2* __restrict__ kf_nat, uint2* _
 constexpr int kInner = 8192;   // the fused tcgen05 kernel's size
 
 // BFFC_FWD3=0 selects the two-pipeline kernel (fwd_r128.cuh) for the ungated forward; default: three-pipeline variant
+bool use_dkf3() {   // warp-specialised dk_f kernel (dkf3_r128.cuh): EXPERIMENTAL, off unless BFFC_DKF3=1 — its first GPU
+  static int v = -1;   // run did not terminate (hand-over protocol not yet validated); dkf_r128.cuh is the product path
+  if (v < 0) {
+    const char* e = getenv("BFFC_DKF3");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 bool use_fwd3() {
   static int v = -1;
   if (v < 0) {
@@ -337,6 +347,8 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
     CUDA_TRY(cudaFuncSetAttribute(fwd3_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal3));
     CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf));
     CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkfGated));
+    CUDA_TRY(cudaFuncSetAttribute(dkf3_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf3));
+    CUDA_TRY(cudaFuncSetAttribute(dkf3_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf3));
     CUDA_TRY(cudaFuncSetAttribute(outer_tc_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOuterGated));
     CUDA_TRY(cudaFuncSetAttribute(outer_tc_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOuter));
     CUDA_TRY(cudaFuncSetAttribute(bffc::ffft::kf_from_filter_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, bffc::ffft::kSmemBytes));
@@ -880,7 +892,11 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
     prm.kmask = sg.kmask; prm.nseg = sg.S; prm.seg_bytes = sg.seg_rows * 128;
     prm.gated = gated ? 1 : 0;
     int grid = H < p->num_sms ? H : p->num_sms;
-    FMT_SWITCH(p->dtype, (dkf_kernel<false, F><<<grid, kThreads, gated ? kSmemTotalDkfGated : kSmemTotalDkf, st>>>(tm_u, tm_d, tm_p, tm_q, prm)););
+    if (!gated && use_dkf3()) {
+      FMT_SWITCH(p->dtype, (dkf3_kernel<false, F><<<grid, kThreadsDkf3, kSmemTotalDkf3, st>>>(tm_u, tm_d, tm_p, tm_q, prm)););
+    } else {
+      FMT_SWITCH(p->dtype, (dkf_kernel<false, F><<<grid, kThreads, gated ? kSmemTotalDkfGated : kSmemTotalDkf, st>>>(tm_u, tm_d, tm_p, tm_q, prm)););
+    }
     CUDA_TRY(cudaGetLastError());
     launches += 1;
   } else {
@@ -905,7 +921,11 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
     prm.kmask = 0xff; prm.nseg = 1; prm.seg_bytes = 16384;
     prm.gated = 0;
     int grid = rows < p->num_sms ? rows : p->num_sms;
-    FMT_SWITCH(p->dtype, (dkf_kernel<true, F><<<grid, kThreads, kSmemTotalDkf, st>>>(tur, tdr, tui, tdi, prm)););
+    if (use_dkf3()) {
+      FMT_SWITCH(p->dtype, (dkf3_kernel<true, F><<<grid, kThreadsDkf3, kSmemTotalDkf3, st>>>(tur, tdr, tui, tdi, prm)););
+    } else {
+      FMT_SWITCH(p->dtype, (dkf_kernel<true, F><<<grid, kThreads, kSmemTotalDkf, st>>>(tur, tdr, tui, tdi, prm)););
+    }
     CUDA_TRY(cudaGetLastError());
     launches += 1;
   }

@@ -19,12 +19,25 @@ DEVINL void mbar_init(uint32_t bar, uint32_t count) {
 DEVINL void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+DEVINL void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// register re-allocation between warpgroups (all warps of the warpgroup execute it)
+template <int kRegs> DEVINL void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> DEVINL void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 DEVINL void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// Bounded spin: a protocol bug must not hang the GPU box (it traps instead; host sees an error).
+// Bounded wait: a protocol bug must not hang the GPU box (it traps instead; the host sees a launch error).  The bound
+// is wall-clock (%globaltimer, checked every 4096 polls): ~4 s, far beyond any legitimate wait in these kernels.
+DEVINL unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
-  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+  unsigned long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -33,6 +46,11 @@ DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return;
+    if ((spin & 4095u) == 4095u) {
+      const unsigned long long t = global_timer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ull) break;
+    }
   }
   __trap();
 }
