@@ -128,7 +128,6 @@ dkf3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 
   if (!compute) {
     // ======================================================================================= issuer warpgroup
-    setmaxnreg_dec<40>();
     if (!issuer_warp || n_units == 0) return;
     const uint32_t tC0 = tmem_base + kColC, tS0 = tmem_base + kColS;
     // stage 1 (TS): D = F128 * X, X = the two tiles of a slot
@@ -217,7 +216,6 @@ dkf3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   }
 
   // ========================================================================================= compute warpgroups
-  setmaxnreg_inc<112>();
   // twiddles W_8192^{k1 j} of this thread's 16 columns j = 16 wg + (0..15), as 8 packed pairs (cos, sin), scaled
   __half2 twc[8], tws[8];
 #pragma unroll

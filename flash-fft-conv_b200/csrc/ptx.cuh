@@ -22,9 +22,6 @@ DEVINL void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 DEVINL void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// register re-allocation between warpgroups (all warps of the warpgroup execute it)
-template <int kRegs> DEVINL void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
-template <int kRegs> DEVINL void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 DEVINL void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // Bounded wait: a protocol bug must not hang the GPU box (it traps instead; the host sees a launch error).  The bound
