@@ -203,12 +203,11 @@ __global__ void kf_pack_tiled_kernel(const float2* __restrict__ kf_nat, uint2* _
 constexpr int kInner = 8192;   // the fused tcgen05 kernel's size
 
 // BFFC_FWD3=0 selects the two-pipeline kernel (fwd_r128.cuh) for the ungated forward; default: three-pipeline variant
-bool use_dkf3() {   // warp-specialised dk_f kernel (dkf3_r128.cuh): EXPERIMENTAL, off unless BFFC_DKF3=1.  Its first GPU
-  static int v = -1;   // run hung on a setmaxnreg.inc that could never be satisfied (since removed); the fixed version has
-                       // not been validated on the GPU yet, so dkf_r128.cuh stays the product path
+bool use_dkf3() {   // warp-specialised dk_f kernel (dkf3_r128.cuh, ungated); BFFC_DKF3=0 selects dkf_r128.cuh for A/B runs
+  static int v = -1;
   if (v < 0) {
     const char* e = getenv("BFFC_DKF3");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
 }
