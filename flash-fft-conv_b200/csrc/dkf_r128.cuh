@@ -53,7 +53,7 @@ dkf_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
 
   const int tid = threadIdx.x;
-  const int pipe = __shfl_sync(0xffffffffu, tid >> 8, 0);   // warp-uniform for the compiler (uniform-register MMA issue)           // 0: u, 1: dout
+  const int pipe = __shfl_sync(0xffffffffu, tid >> 8, 0);   // 0: u, 1: dout; warp-uniform for the compiler (uniform-register MMA issue)
   const int half = (tid >> 7) & 1;
   const int lane = tid & 127;
   const int warp_q = (tid >> 5) & 3;

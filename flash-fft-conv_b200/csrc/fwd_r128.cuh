@@ -119,7 +119,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));  // generic pointer to aligned base
 
   const int tid = threadIdx.x;
-  const int pipe = __shfl_sync(0xffffffffu, tid >> 8, 0);   // warp-uniform for the compiler (uniform-register MMA issue)           // pipeline = pair of warpgroups
+  const int pipe = __shfl_sync(0xffffffffu, tid >> 8, 0);   // pipeline = pair of warpgroups; warp-uniform for the compiler
   const int half = (tid >> 7) & 1;     // which 32-column half of every pass this warpgroup handles
   const int lane = tid & 127;          // TMEM lane owned by this thread (= k1, later = i)
   const int warp_q = (tid >> 5) & 3;   // TMEM sub-partition of this warp
