@@ -133,7 +133,8 @@ int bffc_bwd(const bffc_plan* plan, const void* dout, const void* u, const void*
  * internal streams (both PCIe directions busy), all
  * ordered after the work already enqueued on `stream` and joined back into `stream` before the call returns (the
  * call itself is asynchronous like every other entry point).  dev_workspace: device scratch of
- * bffc_host_workspace_bytes() bytes (two staging slots of inputs, output and conv workspace).
+ * bffc_host_workspace_bytes() bytes (two staging slots of inputs, output and conv workspace).  The internal streams
+ * and events belong to the plan: calls on the same plan must not overlap in time on different caller streams.
  */
 int bffc_host_chunk_batch(const bffc_plan* plan, int B, int H, int L);
 size_t bffc_host_workspace_bytes(const bffc_plan* plan, int B, int H, int L, int gated);
