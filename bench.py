@@ -5,10 +5,15 @@
   python bench.py --impl reference --gpus N --steps K ...  # reference arm: the reference's CPU path
                                                            # (tests/test_flashfftconv.py:5-13 oracle port)
 
-One "step" = one pass of the hot path over one synthetic batch of BASELINE.json's configs[1]
-(N=8192, B=16, H=768, bf16, ungated, L=N) per GPU.  Prints ONE JSON line (rank 0).  Multi-GPU runs shard
-B x H with no data-path collective (every (b,h) convolution is independent): each rank owns its own H=768
-channel block (weak scaling); NCCL is used only for the barrier / max-over-ranks timing.
+Headline: one "step" = one pass of the hot path over one synthetic batch of BASELINE.json's configs[1]
+(C2: N=8192, B=16, H=768, bf16, ungated, L=N) per GPU; weak scaling (every rank owns a full C2 channel block, B x H
+sharded, no data-path collective; NCCL only for the barrier / max-over-ranks timing).
+
+With no --workload the same run also measures the other BASELINE configs (C3 gated + padded 32K, C4 1M, C5 4M) —
+forward step, conv kernels alone, forward+backward, host-buffer end to end — and reports them per config under
+`roofline.configs` (the driver keeps the `roofline` and `config` objects whole).  At --gpus N > 1 the long configs run as
+the STRONG-scaling shards BASELINE.json names (C4: H = 128/N, C5: H = 64/N per rank); their aggregate is the total
+conv count over the max-over-ranks time.  Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -30,21 +35,42 @@ WORKLOADS = {
     # name: (N, B, H, L, gated)
     'c2': (8192, 16, 768, 8192, False),       # BASELINE.json configs[1]: M2-BERT dims, the metric's config
     'c3': (32768, 8, 1024, 16384, True),      # configs[2]: Hyena-style, gated, implicit 2x causal padding
-    'c4': (1048576, 2, 128, 1048576, False),  # configs[3]: HyenaDNA long range (per GPU here; see config.sharding)
-    'c5': (4194304, 8, 8, 4194304, False),    # configs[4] per-GPU shard: B=8, H=64/8
+    'c4': (1048576, 2, 128, 1048576, False),  # configs[3]: HyenaDNA long range, B x H shard over 1..4 GPUs
+    'c5': (4194304, 8, 64, 4194304, False),   # configs[4]: 8 x B200 B x H shard (H = 64 / n_gpus per rank)
 }
+STRONG = ('c4', 'c5')          # sharded over ranks (strong scaling); c2 / c3 are per-rank (weak)
 
 
-def algorithmic_bytes(N, B, H, L, gated):
+def shard_shape(name, world):
+    N, B, H, L, gated = WORKLOADS[name]
+    if name in STRONG:
+        H = max(1, H // world)
+    if name == 'c5' and world == 1:
+        H = 8                  # one GPU measures the per-GPU shard of the 8-GPU configuration (the full H=64 needs
+                               # 8 x the work the config assigns to one device)
+    return N, B, H, L, gated
+
+
+def workload_string(name, world=1):
+    N, B, H, L, gated = shard_shape(name, world)
+    return (f'{name}: FlashFFTConv({N}, bf16), B={B} H={H} L={L} {"gated" if gated else "ungated"} per GPU '
+            f'(BASELINE.json configs)')
+
+
+def fwd_bytes(N, B, H, L, gated):
     """fwd ungated 4L per conv (+4L gates when gated) plus k_f once per channel (4N)."""
     return (8 if gated else 4) * L * B * H + 4 * N * H
+
+
+def bwd_bytes(N, B, H, L, gated):
+    """bwd ungated 6L per conv + 8N per channel (dk_f fp32); gated 14L per conv."""
+    return (14 if gated else 6) * L * B * H + 8 * N * H
 
 
 def issued_tensor_flops(N, B, H):
     """Matmul flops the inner 8192-point kernel issues: 25.2 MFLOP per unit (a pair of sequences of one
     channel; an odd batch still runs a full unit), N/8192 units per pair for the composite sizes; the outer radix-128
-    stage of the 1M+ sizes adds 2 x 128 x 256 x 2 flops per complex column.  Sizes below 8192 share one unit between
-    4096/N batch pairs."""
+    stage of the 1M+ sizes adds 2 x 128 x 256 x 2 flops per complex column."""
     unit = 2.0 * 128 * 128 * (2 * 256 + 2 * 128)
     ne = max(N, 8192)
     seg = 4096 // N if N < 8192 else 1
@@ -113,9 +139,10 @@ def sample_shape(N):
     return (4, n // 4) if n >= 8 else (2, n // 2)
 
 
-def cpu_baseline(N, L, gated, budget_s=12.0):
-    """The reference's CPU path (oracle port of tests/test_flashfftconv.py:5-13) on the host cores,
-    on a bounded sample of the same workload: S convolutions of the true N / L, all threads."""
+def cpu_reference(N, L, gated, steps=None, warmup=5, budget_s=8.0):
+    """The reference's CPU path (oracle port of tests/test_flashfftconv.py:5-13, :208) on the host cores, on a bounded
+    sample of the same workload: S convolutions of the true N / L, all threads.  Returns (convs/s, seconds per call,
+    sample description)."""
     from oracle.fftconv_oracle import ref_fft_conv, ref_fft_conv_gated
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -129,19 +156,20 @@ def cpu_baseline(N, L, gated, budget_s=12.0):
         fn = lambda: ref_fft_conv_gated(u, k, pg, qg, N)
     else:
         fn = lambda: ref_fft_conv(u, k, N)
-    for _ in range(5):          # thread pool / FFT plan warm-up (first calls are 10x slower)
+    for _ in range(warmup):          # thread pool / FFT plan warm-up (first calls are 10x slower)
         fn()
     t0 = time.perf_counter(); n = 0
     while True:
         fn(); n += 1
         dt = time.perf_counter() - t0
-        if dt > budget_s or n >= 200:
+        if (steps is not None and n >= steps) or (steps is None and (dt > budget_s or n >= 200)):
             break
-    return {'value': Bs * Hs * n / dt, 'unit': 'convs/s', 'cores': cores, 'kind': 'port',
-            'sample': f'{n} calls x {Bs * Hs} convs (B={Bs},H={Hs}) at N={N}, L={L}, fp32 torch.fft on CPU'}
+    sample = (f'{n} calls x {Bs * Hs} convs (B={Bs},H={Hs}) at N={N}, L={L}, {"gated, " if gated else ""}'
+              f'fp32 torch.fft on CPU, {cores} threads')
+    return Bs * Hs * n / dt, dt / n, sample, cores
 
 
-def dist_setup(n_gpus):
+def dist_setup():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -156,48 +184,158 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    N, B, H, L, gated = WORKLOADS[args.workload]
-    from oracle.fftconv_oracle import ref_fft_conv
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    Bs, Hs = sample_shape(N)
-    g = torch.Generator().manual_seed(0)
-    u = torch.randn(Bs, Hs, L, generator=g).to(torch.bfloat16)
-    k = torch.randn(Hs, L, generator=g) / L ** 0.5
-    for _ in range(args.warmup):
-        ref_fft_conv(u, k, N)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ref_fft_conv(u, k, N)
-    dt = time.perf_counter() - t0
-    val = Bs * Hs * args.steps / dt
-    sample = f'each step = {Bs * Hs} convs (B={Bs},H={Hs}) of the N={N}, L={L} workload; fp32 torch.fft, {cores} threads'
+    name = args.workload or 'c2'
+    N, B, H, L, gated = shard_shape(name, 1)
+    val, spc, sample, cores = cpu_reference(N, L, gated, steps=args.steps, warmup=max(args.warmup, 1))
     emit(json.dumps({
         'impl': 'reference', 'metric': 'fftconv_fwd_convs_per_sec', 'value': val, 'unit': 'convs/s',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': spc * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'{args.workload}: N={N} B={B} H={H} L={L} ungated (bounded CPU sample)'},
+        'config': {'workload': workload_string(name, 1),
+                   'note': 'each CPU step is a bounded sample of the workload (cpu_baseline.sample); value is per convolution'},
         'cpu_baseline': {'value': val, 'unit': 'convs/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': val, 'unit': 'convs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}), _OUT_FD)
 
 
-def run_ours(args):
-    rank, world, local = dist_setup(args.gpus)
-    import __graft_entry__ as ge
-    ge.build()
+class Ctx:
+    pass
+
+
+def measure(cx, name, steps, warmup, headline=False):
+    """One BASELINE config on this rank's GPU: whole forward step through the public module, the conv kernels alone
+    (k_f pre-packed; CUDA events on the launching stream), autograd forward+backward, host-buffer end to end."""
     from flashfftconv import FlashFFTConv, _lib
     from flashfftconv.conv import _pack_kf, _ptr, _stream
-    dev = torch.device('cuda', local)
-    torch.cuda.set_device(dev)
-    N, B, H, L, gated = WORKLOADS[args.workload]
-    torch.manual_seed(1234 + rank)
+    dev, world = cx.dev, cx.world
+    N, B, H, L, gated = shard_shape(name, world)
+    torch.manual_seed(1234 + cx.rank)
     conv = FlashFFTConv(N, dtype=torch.bfloat16).to(dev)
     plan = conv.plan(dev)
     u = torch.randn(B, H, L, device=dev).to(torch.bfloat16)
     k = torch.randn(H, L, device=dev) / L ** 0.5
     gates = [torch.randn(B, H, L, device=dev).to(torch.bfloat16) for _ in range(2)] if gated else []
-    convs_per_step = B * H
+    convs = B * H
+    torch.cuda.reset_peak_memory_stats(dev)
+    base_mem = torch.cuda.memory_allocated(dev)
+
+    def timed(fn, n, sync_ranks=True):
+        cx.barrier() if sync_ranks else torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        cx.barrier() if sync_ranks else torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        return cx.max_over_ranks(ms) if sync_ranks else ms
+
+    # ---- (1) device-resident whole step through the public forward (k -> k_f -> conv kernels)
+    launches = [0]
+
+    def step():
+        conv(u, k, *gates)
+        launches[0] += conv.last_launches
+    for _ in range(warmup):
+        step()
+    t_load0 = time.time()
+    launches[0] = 0
+    step_ms = timed(step, steps)
+    step_launches = launches[0]
+    fwd_peak = torch.cuda.max_memory_allocated(dev) - base_mem
+
+    # ---- (2) conv kernels alone (k_f pre-packed) -> roofline
+    kf = _pack_kf(conv, plan, k, 0)
+    yk = torch.empty_like(u)
+    ws_bytes = _lib.lib().bffc_workspace_bytes(plan.handle, B, H, L)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+    g0 = _ptr(gates[0]) if gated else None
+    g1 = _ptr(gates[1]) if gated else None
+
+    def kern():
+        _lib.check(_lib.lib().bffc_fwd(plan.handle, _ptr(u), _ptr(kf), g0, g1, _ptr(yk), B, H, L, _ptr(ws), ws_bytes,
+                                       _stream()))
+    for _ in range(3):
+        kern()
+    kern_ms = timed(kern, steps, sync_ranks=False)
+    if headline and cx.sampler:
+        # the timed regions last milliseconds; keep the identical kernel running ~1.5 s more so that
+        # nvidia-smi (100 ms period) sees clocks and throttle reasons under this load
+        t_end = time.time() + 1.5
+        while time.time() < t_end:
+            for _ in range(50):
+                kern()
+            torch.cuda.synchronize()
+        cx.sampler.windows.append((t_load0, time.time()))
+    del yk, ws
+
+    # ---- (3) forward + backward through autograd (du, dk, gate gradients), device resident
+    ug = u.clone().requires_grad_(True); kg = k.clone().requires_grad_(True)
+    gg = [g.clone().requires_grad_(True) for g in gates]
+    dout = torch.randn_like(u)
+    torch.cuda.reset_peak_memory_stats(dev)
+
+    def fb():
+        ug.grad = None; kg.grad = None
+        for g in gg:
+            g.grad = None
+        conv(ug, kg, *gg).backward(dout)
+    for _ in range(2):
+        fb()
+    fb_ms = timed(fb, max(2, steps // 2))
+    fb_peak = torch.cuda.max_memory_allocated(dev) - base_mem
+    del ug, kg, gg, dout
+
+    # ---- (4) end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    cx.bind_host()
+    u_h = torch.empty(u.shape, dtype=u.dtype).pin_memory(); u_h.copy_(u)
+    k_h = k.cpu().pin_memory()
+    g_h = []
+    for g in gates:
+        t = torch.empty(g.shape, dtype=g.dtype).pin_memory(); t.copy_(g); g_h.append(t)
+    y_h = torch.empty(u.shape, dtype=u.dtype).pin_memory()
+
+    def e2e_step():
+        # public host-buffer call: k -> device, k_f, then u (and gates) host -> device, conv, y device -> host,
+        # pipelined over batch chunks inside bffc_fwd_host (include/bffc.h)
+        conv.forward_host(u_h, k_h, *g_h, out=y_h, device=dev)
+    e2e_step()
+    e2e_ms = timed(e2e_step, max(2, min(steps, 5)))
+
+    fb_bytes = fwd_bytes(N, B, H, L, gated) + bwd_bytes(N, B, H, L, gated)
+    ab = fwd_bytes(N, B, H, L, gated)
+    tot = convs * (world if True else 1)
+    res = {
+        'workload': workload_string(name, world),
+        'scaling': 'strong (B x H shard of the config over ranks)' if name in STRONG and world > 1 else 'weak',
+        'convs_per_rank': convs,
+        'fwd': {'ms_per_step': step_ms, 'convs_per_sec': tot / (step_ms * 1e-3), 'launches_per_step': step_launches / steps},
+        'kernels': {'ms': kern_ms, 'algorithmic_bytes': ab, 'gbs': ab / (kern_ms * 1e-3) / 1e9,
+                    'frac': ab / (kern_ms * 1e-3) / 1e9 / cx.hbm_peak,
+                    'convs_per_sec_per_gpu': convs / (kern_ms * 1e-3),
+                    'tensor_issued_tflops': issued_tensor_flops(N, B, H) / (kern_ms * 1e-3) / 1e12},
+        'fwd_bwd': {'ms_per_step': fb_ms, 'convs_per_sec': tot / (fb_ms * 1e-3), 'algorithmic_bytes': fb_bytes,
+                    'gbs': fb_bytes / (fb_ms * 1e-3) / 1e9, 'frac': fb_bytes / (fb_ms * 1e-3) / 1e9 / cx.hbm_peak,
+                    'ratio_to_fwd': fb_ms / step_ms},
+        'e2e': {'ms_per_step': e2e_ms, 'convs_per_sec': tot / (e2e_ms * 1e-3),
+                'h2d_bytes_per_step': u_h.numel() * 2 * (3 if gated else 1) + k_h.numel() * 4,
+                'd2h_bytes_per_step': y_h.numel() * 2},
+        'peak_mem_mb': {'fwd': fwd_peak / 2 ** 20, 'fwd_bwd': fb_peak / 2 ** 20,
+                        'inputs': (u.numel() * 2 * (3 if gated else 1) + k.numel() * 4) / 2 ** 20,
+                        'note': 'torch.cuda.max_memory_allocated above the resident inputs (reference metric: '
+                                'benchmarks/benchmark.py:137-147)'},
+    }
+    return res
+
+
+def run_ours(args):
+    rank, world, local = dist_setup()
+    import __graft_entry__ as ge
+    ge.build()
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    cx = Ctx()
+    cx.rank, cx.world, cx.dev = rank, world, dev
 
     def barrier():
         if world > 1:
@@ -213,149 +351,87 @@ def run_ours(args):
             return float(t.item())
         return x
 
-    # ---- (1) device-resident whole step through the public forward (k -> k_f -> fused conv)
-    for _ in range(args.warmup):
-        y = conv(u, k, *gates)
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.3)
-    t_load0 = time.time()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    launches = 0
-    e0.record()
-    for _ in range(args.steps):
-        y = conv(u, k, *gates)
-        launches += 1 + _lib.lib().bffc_last_launch_count()          # kf_pack + conv kernels (our kernels only)
-    e1.record()
-    barrier()
-    step_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    bound = [False]
 
-    # ---- (2) dominant kernel alone (k_f pre-packed), CUDA events on the launching stream -> roofline
-    kf = _pack_kf(conv, plan, k, 0)
-    yk = torch.empty_like(u)
-    ws_bytes = _lib.lib().bffc_workspace_bytes(plan.handle, B, H, L)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
-    g0 = _ptr(gates[0]) if gated else None
-    g1 = _ptr(gates[1]) if gated else None
+    def bind_host():
+        # pinned staging buffers should live on the GPU's NUMA node: bind this process's CPU affinity (and with it the
+        # first-touch placement of later allocations) to the cores local to the device before allocating them
+        if not bound[0]:
+            bound[0] = True
+            try:
+                from flashfftconv.parallel import bind_to_gpu_numa_node
+                cx.numa = bind_to_gpu_numa_node(local)
+            except Exception as e:            # measurement aid only
+                cx.numa = f'not bound: {e}'
+    cx.barrier, cx.max_over_ranks, cx.bind_host, cx.numa = barrier, max_over_ranks, bind_host, None
 
-    def kern():
-        _lib.check(_lib.lib().bffc_fwd(plan.handle, _ptr(u), _ptr(kf), g0, g1, _ptr(yk), B, H, L, _ptr(ws), ws_bytes,
-                                       _stream()))
-    for _ in range(max(3, args.warmup)):
-        kern()
-    torch.cuda.synchronize()
-    k0 = torch.cuda.Event(enable_timing=True); k1 = torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(args.steps):
-        kern()
-    k1.record(); torch.cuda.synchronize()
-    kern_ms = k0.elapsed_time(k1) / args.steps
-    if sampler:
-        # the timed regions last milliseconds; keep the identical kernel running ~1.5 s more so that
-        # nvidia-smi (100 ms period) sees clocks and throttle reasons under this load
-        t_end = time.time() + 1.5
-        while time.time() < t_end:
-            for _ in range(50):
-                kern()
-            torch.cuda.synchronize()
-        sampler.windows.append((t_load0, time.time()))
-        time.sleep(0.15)
-        sampler.stop()
-
-    # ---- (2b) forward + backward through autograd (du, dk), device resident
-    ug = u.clone().requires_grad_(True); kg = k.clone().requires_grad_(True)
-    gg = [g.clone().requires_grad_(True) for g in gates]
-    dout = torch.randn_like(u)
-    def fb():
-        ug.grad = None; kg.grad = None
-        for g in gg:
-            g.grad = None
-        conv(ug, kg, *gg).backward(dout)
-    for _ in range(3):
-        fb()
-    barrier()
-    f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
-        fb()
-    f1.record()
-    barrier()
-    fb_ms = max_over_ranks(f0.elapsed_time(f1) / args.steps)
-
-    # ---- (3) end to end through the public API with HOST buffers (pinned), copies inside the timed region
-    u_h = u.cpu().pin_memory(); k_h = k.cpu().pin_memory()
-    g_h = [g.cpu().pin_memory() for g in gates]
-    y_h = torch.empty_like(u_h).pin_memory()
-    e2e_steps = max(2, min(args.steps, 5))
-
-    def e2e_step():
-        # public host-buffer call: k -> device, k_f, then u (and gates) host -> device, conv, y device -> host,
-        # pipelined over batch chunks inside bffc_fwd_host (include/bffc.h)
-        conv.forward_host(u_h, k_h, *g_h, out=y_h, device=dev)
-    e2e_step()
-    barrier()
-    s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
-    s0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    s1.record()
-    barrier()
-    e2e_ms = max_over_ranks(s0.elapsed_time(s1) / e2e_steps)
-
-    if rank != 0:
-        return
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
     except Exception:
         pass
-    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-    bf16_peak = float(peaks.get('bf16_tflops', peaks.get('bf16_tfs', 0)) or 0)
-    if not bf16_peak:
-        bf16_peak = next((float(v) for k_, v in peaks.items() if 'bf16' in k_.lower() and isinstance(v, (int, float))), 1640.0)
-    tflops_issued = issued_tensor_flops(N, B, H)
-    ref_flops = reference_tensor_flops(N, B, H)
+    cx.hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    bf16_peak = float(peaks.get('bf16_tflops', 0) or 1590.0)
     peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s'
-    abytes = algorithmic_bytes(N, B, H, L, gated)
-    achieved = abytes / (kern_ms * 1e-3) / 1e9
+
+    cx.sampler = ClockSampler(local) if rank == 0 else None
+    if cx.sampler:
+        cx.sampler.start()
+        time.sleep(0.3)
+    head_name = args.workload or 'c2'
+    head = measure(cx, head_name, args.steps, args.warmup, headline=True)
+    if cx.sampler:
+        time.sleep(0.15)
+        cx.sampler.stop()
+    configs = {head_name: head}
+    if args.workload is None:
+        for name in ('c3', 'c4', 'c5'):
+            torch.cuda.empty_cache()
+            try:
+                configs[name] = measure(cx, name, max(3, min(args.steps, 5)), 3)
+            except Exception as e:        # a side config must never take the headline line down
+                configs[name] = {'error': f'{type(e).__name__}: {e}'[:300]}
+    if rank != 0:
+        return
+    N, B, H, L, gated = shard_shape(head_name, world)
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json'))).get(args.workload)
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json'))).get(head_name)
     except Exception:
         pass
+    kern = head['kernels']
     out = {
-        'metric': 'fftconv_fwd_convs_per_sec', 'value': convs_per_step * world / (step_ms * 1e-3), 'unit': 'convs/s',
-        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_ms,
+        'metric': 'fftconv_fwd_convs_per_sec', 'value': head['fwd']['convs_per_sec'], 'unit': 'convs/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': head['fwd']['ms_per_step'],
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-        'config': {'workload': f'{args.workload}: FlashFFTConv({N}, bf16) fwd, B={B} H={H} L={L} '
-                               f'{"gated" if gated else "ungated"} per GPU (BASELINE.json configs); '
-                               f'step = k->k_f (bffc_kf_from_filter for seqlen <= 8192, else torch.fft.rfft + bffc_kf_pack_rfft) + conv kernels',
-                   'l2': f'inputs+outputs {abytes / 1e6:.0f} MB per step exceed the 126 MB L2 (no flush needed)',
-                   'sharding': 'B x H sharded over ranks, no data-path collective'},
-        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
+        'config': {'workload': workload_string(head_name, world),
+                   'step': 'k -> k_f (one library launch; cached while k is unchanged only in eval mode) + conv kernels',
+                   'l2': f'inputs+outputs {kern["algorithmic_bytes"] / 1e6:.0f} MB per step exceed the 126 MB L2 (no flush needed)',
+                   'sharding': 'B x H sharded over ranks, no data-path collective',
+                   'fwd_bwd_convs_per_sec': head['fwd_bwd']['convs_per_sec'], 'fwd_bwd_ms_per_step': head['fwd_bwd']['ms_per_step'],
+                   'host_numa_binding': cx.numa},
+        'roofline': {'bound': 'hbm', 'achieved': kern['gbs'], 'peak': cx.hbm_peak, 'unit': 'GB/s', 'frac': kern['frac'],
                      'traffic': traffic,
-                     'kernel': 'bffc::r128::fwd3_kernel' if N == 8192 and not gated else 'bffc_fwd native path (outer stages / fold + bffc::r128 fused kernel)',
-                     'kernel_ms': kern_ms,
-                     'algorithmic_bytes': abytes, 'peak_source': peak_src,
-                     'kernel_convs_per_sec': convs_per_step / (kern_ms * 1e-3)},
-        # the tighter roofline at 8192 under this factorisation (report both): flops actually issued
-        # to the tensor pipe per launch vs the measured dense bf16 peak (itself power limited on this board)
-        'roofline_tensor': {'bound': 'tensor', 'achieved': tflops_issued / (kern_ms * 1e-3) / 1e12, 'peak': bf16_peak,
-                            'unit': 'TFLOP/s', 'frac': tflops_issued / (kern_ms * 1e-3) / 1e12 / bf16_peak,
-                            'issued_flops': tflops_issued, 'reference_factorisation_flops': ref_flops,
-                            'note': 'radix 128 x 64 issues 2x the matmul flops of the reference split (DESIGN.md §6)'},
-        'e2e': {'value': convs_per_step * world / (e2e_ms * 1e-3), 'unit': 'convs/s',
-                'h2d_bytes_per_step': u_h.numel() * 2 * (3 if gated else 1) + k_h.numel() * 4,
-                'd2h_bytes_per_step': y_h.numel() * 2,
-                'ms_per_step': e2e_ms},
-        'fwd_bwd': {'value': convs_per_step * world / (fb_ms * 1e-3), 'unit': 'convs/s', 'ms_per_step': fb_ms,
-                    'note': 'autograd fwd+bwd (du, dk) through FlashFFTConv, inputs resident'},
-        'gpu_launches': launches,
-        'clocks': sampler.summary() if sampler else None,
+                     'traffic_source': 'ncu --set full capture of this kernel, profiles/ (not re-measured by this run)',
+                     'kernel': 'bffc forward conv kernels of the headline config (k_f pre-packed)',
+                     'kernel_ms': kern['ms'], 'algorithmic_bytes': kern['algorithmic_bytes'], 'peak_source': peak_src,
+                     'kernel_convs_per_sec': kern['convs_per_sec_per_gpu'],
+                     'tensor': {'issued_tflops': kern['tensor_issued_tflops'], 'peak_tflops': bf16_peak,
+                                'frac_issued': kern['tensor_issued_tflops'] / bf16_peak,
+                                'reference_factorisation_flops': reference_tensor_flops(N, B, H)},
+                     'fwd_bwd': head['fwd_bwd'],
+                     'configs': configs},
+        'e2e': {'value': head['e2e']['convs_per_sec'], 'unit': 'convs/s',
+                'h2d_bytes_per_step': head['e2e']['h2d_bytes_per_step'],
+                'd2h_bytes_per_step': head['e2e']['d2h_bytes_per_step'], 'ms_per_step': head['e2e']['ms_per_step']},
+        'gpu_launches': int(round(head['fwd']['launches_per_step'] * args.steps)),
+        'clocks': cx.sampler.summary() if cx.sampler else None,
     }
-    out['cpu_baseline'] = cpu_baseline(N, L, gated) if world == 1 else None
+    if world == 1:
+        val, _, sample, cores = cpu_reference(N, L, gated)
+        out['cpu_baseline'] = {'value': val, 'unit': 'convs/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+    else:
+        out['cpu_baseline'] = None
     emit(json.dumps(out), _OUT_FD)
 
 
@@ -384,7 +460,8 @@ def _main(saved_fd):
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default=None, choices=sorted(WORKLOADS),
+                    help='measure only this config (default: headline c2 + c3, c4, c5 under roofline.configs)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':

@@ -11,7 +11,6 @@
 #include "bffc.h"
 #include "fwd_r128.cuh"
 #include "fwd3_r128.cuh"
-#include "dkf_r128.cuh"
 #include "dkf3_r128.cuh"
 #include "outer_cuda.cuh"
 #include "outer_r128.cuh"
@@ -138,6 +137,7 @@ constexpr int kInnerWords = 8192;
 // scratch row = 2*(h*G + g) + (b & 1), segment s = (b >> 1) % S starting at s*2N, g = b / (2S).  8 elements per thread.
 template <int kFmt>
 __global__ void fold_kernel(const uint4* __restrict__ t, const uint4* __restrict__ postgate, uint4* __restrict__ y,
+                            const uint4* __restrict__ postgate2, uint4* __restrict__ y2,
                             int L, int N, int S, int G, int H, int off, size_t rows) {
   const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int per = L / 8;
@@ -158,6 +158,11 @@ __global__ void fold_kernel(const uint4* __restrict__ t, const uint4* __restrict
     bffc::upk2(bffc::Num<kFmt>::unpack(bw[i]), b0, b1);
     o[i] = bffc::Num<kFmt>::pack(a0 + b0, a1 + b1);
   }
+  if (y2) {
+    const uint4 g = postgate2[r * per + v];
+    y2[r * per + v] = make_uint4(bffc::Num<kFmt>::hmul2(o[0], g.x), bffc::Num<kFmt>::hmul2(o[1], g.y),
+                                 bffc::Num<kFmt>::hmul2(o[2], g.z), bffc::Num<kFmt>::hmul2(o[3], g.w));
+  }
   if (postgate) {
     const uint4 g = postgate[r * per + v];
     const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
@@ -165,6 +170,18 @@ __global__ void fold_kernel(const uint4* __restrict__ t, const uint4* __restrict
     for (int i = 0; i < 4; ++i) o[i] = bffc::Num<kFmt>::hmul2(o[i], gw[i]);
   }
   y[r * per + v] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// o0 = a0 * g0, o1 = a1 * g1 elementwise in the 16-bit format (gated loads of the dk_f kernel, seqlen <= 8192)
+template <int kFmt>
+__global__ void gate_mul2_kernel(const uint4* __restrict__ a0, const uint4* __restrict__ g0, uint4* __restrict__ o0,
+                                 const uint4* __restrict__ a1, const uint4* __restrict__ g1, uint4* __restrict__ o1, size_t nvec) {
+  using NT = bffc::Num<kFmt>;
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  const uint4 x = a0[i], g = g0[i], y = a1[i], q = g1[i];
+  o0[i] = make_uint4(NT::hmul2(x.x, g.x), NT::hmul2(x.y, g.y), NT::hmul2(x.z, g.z), NT::hmul2(x.w, g.w));
+  o1[i] = make_uint4(NT::hmul2(y.x, q.x), NT::hmul2(y.y, q.y), NT::hmul2(y.z, q.z), NT::hmul2(y.w, q.w));
 }
 
 template <bool kHalf, int kFmt>
@@ -202,25 +219,6 @@ __global__ void kf_pack_tiled_kernel(const float2* __restrict__ kf_nat, uint2* _
 
 constexpr int kInner = 8192;   // the fused tcgen05 kernel's size
 
-// BFFC_FWD3=0 selects the two-pipeline kernel (fwd_r128.cuh) for the ungated forward; default: three-pipeline variant
-bool use_dkf3() {   // warp-specialised dk_f kernel (dkf3_r128.cuh, ungated); BFFC_DKF3=0 selects dkf_r128.cuh for A/B runs
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("BFFC_DKF3");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
-
-bool use_fwd3() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("BFFC_FWD3");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
-
 }  // namespace
 
 struct bffc_level { int tc; int R; };   // tc = 1: tcgen05 radix-128 stage (outer_r128.cuh); 0: CUDA-core radix 2/4/8
@@ -239,9 +237,9 @@ struct bffc_plan {
   uint8_t* gtiles = nullptr;
   float2* tw8192 = nullptr;   // e^{-2 pi i t / 8192}, t < 8192: twiddles of the fp32 filter-side FFTs (filter_fft.cuh)
   int num_sms = 0;
-  // bffc_fwd_host: copy-in / compute / copy-out streams and the per-slot events, created on first use
-  mutable cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
-  mutable cudaEvent_t hev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // bffc_fwd_host: copy-in / compute / copy-out streams and the per-slot events (created with the plan)
+  cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t hev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 extern "C" {
@@ -267,6 +265,8 @@ static int levels_for(int N, bffc_level* lev) {
   }
 }
 
+int bffc_plan_destroy(bffc_plan* p);
+
 int bffc_supported(int seqlen, int dtype) {
   if (dtype != BFFC_DTYPE_BF16 && dtype != BFFC_DTYPE_FP16) return 0;
   bffc_level lev[2];
@@ -283,13 +283,22 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   if (int rc = get_encode()) return rc;
 
   bffc_plan* p = new bffc_plan();
+  // every failure below releases what was created so far (bffc_plan_destroy accepts a partially built plan)
+#define PLAN_TRY(expr)                                                                               \
+  do {                                                                                               \
+    cudaError_t e_ = (expr);                                                                         \
+    if (e_ != cudaSuccess) {                                                                         \
+      bffc_plan_destroy(p);                                                                          \
+      return fail(BFFC_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));                    \
+    }                                                                                                \
+  } while (0)
   p->N = seqlen;
   p->NE = seqlen < kInner ? kInner : seqlen;
   p->R = p->NE / kInner;
   p->nlev = levels_for(seqlen, p->lev);
   p->dtype = dtype;
-  CUDA_TRY(cudaGetDevice(&p->device));
-  CUDA_TRY(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
+  PLAN_TRY(cudaGetDevice(&p->device));
+  PLAN_TRY(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
 
   const double PI = 3.14159265358979323846;
   // outer radix-128 DFT of the fused kernel, cos / sin planes (symmetric, K-major rows)
@@ -300,10 +309,10 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
       c[m * 128 + k] = f2h16(cos(ang), dtype);
       s[m * 128 + k] = f2h16(sin(ang), dtype);
     }
-  CUDA_TRY(cudaMalloc(&p->dftC, c.size() * 2));
-  CUDA_TRY(cudaMalloc(&p->dftS, s.size() * 2));
-  CUDA_TRY(cudaMemcpy(p->dftC, c.data(), c.size() * 2, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(p->dftS, s.data(), s.size() * 2, cudaMemcpyHostToDevice));
+  PLAN_TRY(cudaMalloc(&p->dftC, c.size() * 2));
+  PLAN_TRY(cudaMalloc(&p->dftS, s.size() * 2));
+  PLAN_TRY(cudaMemcpy(p->dftC, c.data(), c.size() * 2, cudaMemcpyHostToDevice));
+  PLAN_TRY(cudaMemcpy(p->dftS, s.data(), s.size() * 2, cudaMemcpyHostToDevice));
 
   // DFT-64 planes for the row-local stage: G = exp(-2 pi i k n / 64) = Gr + i Gi.  Stored as the MN-major
   // B operand image: row k (K index) = 64 bf16 = 128 B, 16-byte chunk c of row k at chunk position c ^ (k & 7)
@@ -320,8 +329,8 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
       memcpy(gt.data() + 2 * T + off, &ngi, 2);
       memcpy(gt.data() + 3 * T + off, &gr, 2);
     }
-  CUDA_TRY(cudaMalloc(&p->gtiles, gt.size()));
-  CUDA_TRY(cudaMemcpy(p->gtiles, gt.data(), gt.size(), cudaMemcpyHostToDevice));
+  PLAN_TRY(cudaMalloc(&p->gtiles, gt.size()));
+  PLAN_TRY(cudaMemcpy(p->gtiles, gt.data(), gt.size(), cudaMemcpyHostToDevice));
 
   if (p->NE == kInner) {
     std::vector<float2> tw(kInner);
@@ -329,8 +338,8 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
       const double a = -2.0 * M_PI * double(t) / double(kInner);
       tw[t] = make_float2(float(cos(a)), float(sin(a)));
     }
-    CUDA_TRY(cudaMalloc(&p->tw8192, tw.size() * sizeof(float2)));
-    CUDA_TRY(cudaMemcpy(p->tw8192, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    PLAN_TRY(cudaMalloc(&p->tw8192, tw.size() * sizeof(float2)));
+    PLAN_TRY(cudaMemcpy(p->tw8192, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
   }
 
   // engine order of k_f (32-bit words), per channel h: R rows of 8192 words, row = c0*R1 + c1 (outer digits); inside a
@@ -339,21 +348,23 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
 
   using namespace bffc::r128;
   FMT_SWITCH(dtype,
-    CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<false, false, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<true, false, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<false, true, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalGated));
-    CUDA_TRY(cudaFuncSetAttribute(fwd_kernel<false, false, true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    CUDA_TRY(cudaFuncSetAttribute(fwd3_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal3));
-    CUDA_TRY(cudaFuncSetAttribute(fwd3_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal3));
-    CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf));
-    CUDA_TRY(cudaFuncSetAttribute(dkf_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkfGated));
-    CUDA_TRY(cudaFuncSetAttribute(dkf3_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf3));
-    CUDA_TRY(cudaFuncSetAttribute(dkf3_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf3));
-    CUDA_TRY(cudaFuncSetAttribute(outer_tc_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOuterGated));
-    CUDA_TRY(cudaFuncSetAttribute(outer_tc_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOuter));
-    CUDA_TRY(cudaFuncSetAttribute(bffc::ffft::kf_from_filter_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, bffc::ffft::kSmemBytes));
+    PLAN_TRY(cudaFuncSetAttribute(fwd_kernel<false, false, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    PLAN_TRY(cudaFuncSetAttribute(fwd_kernel<true, false, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    PLAN_TRY(cudaFuncSetAttribute(fwd_kernel<false, true, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalGated));
+    PLAN_TRY(cudaFuncSetAttribute(fwd_kernel<false, false, true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    PLAN_TRY(cudaFuncSetAttribute(fwd3_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal3));
+    PLAN_TRY(cudaFuncSetAttribute(fwd3_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal3));
+    PLAN_TRY(cudaFuncSetAttribute(dkf3_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf3));
+    PLAN_TRY(cudaFuncSetAttribute(dkf3_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf3));
+    PLAN_TRY(cudaFuncSetAttribute(outer_tc_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOuterGated));
+    PLAN_TRY(cudaFuncSetAttribute(outer_tc_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOuter));
+    PLAN_TRY(cudaFuncSetAttribute(bffc::ffft::kf_from_filter_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, bffc::ffft::kSmemBytes));
   );
-  CUDA_TRY(cudaFuncSetAttribute(bffc::ffft::dk_from_dkf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bffc::ffft::kSmemBytes));
+  PLAN_TRY(cudaFuncSetAttribute(bffc::ffft::dk_from_dkf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bffc::ffft::kSmemBytes));
+  // streams / events of bffc_fwd_host (copy-in, compute, copy-out; per-slot events)
+  for (auto& st : p->hs) PLAN_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  for (auto& ev : p->hev) PLAN_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+#undef PLAN_TRY
   *out = p;
   return BFFC_OK;
 }
@@ -458,31 +469,36 @@ int bffc_dkf_unpack(const bffc_plan* p, const void* dkf_engine, void* dkf_natura
 // Composite sizes keep the outer stage's output as two bf16 planes (real, imaginary) of pairs*H*N elements.
 static size_t plane_bytes(const bffc_plan* p, int B, int H) { return size_t((B + 1) / 2) * H * p->N * 2; }
 
-extern "C" size_t bffc_workspace_bytes(const bffc_plan* p, int B, int H, int L) {
-  (void)L;
+// u*pregate and dout*postgate for the dk_f kernel of a gated backward at seqlen <= 8192 (two (B,H,L) tensors)
+static size_t gate_scratch_bytes(int B, int H, int L) { return 2 * ((size_t(B) * H * L * 2 + 255) & ~size_t(255)); }
+
+extern "C" size_t bffc_workspace_bytes_ex(const bffc_plan* p, int B, int H, int L, int gated, int backward) {
   if (!p) return 0;
   if (p->N < kInner) {   // small sizes: S = 4096/N batch members share one 8192-point slot; scratch of full output tiles
     const int S = 4096 / p->N, G = (B + 2 * S - 1) / (2 * S);
-    return size_t(H) * G * 2 * kInner * 2;
+    return size_t(H) * G * 2 * kInner * 2 + ((gated && backward) ? gate_scratch_bytes(B, H, L) : 0);
   }
-  if (p->nlev == 0) return 0;
+  if (p->nlev == 0) return (gated && backward) ? gate_scratch_bytes(B, H, L) : 0;
   // plane sets (real + imaginary plane each): forward nlev sets; backward nlev + 1 (transformed u and dout)
-  return size_t(2 * (p->nlev + 1)) * plane_bytes(p, B, H);
+  return size_t(2 * (backward ? p->nlev + 1 : p->nlev)) * plane_bytes(p, B, H);
 }
 
-static thread_local CUtensorMapDataType g_tm_dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-static void set_map_dtype(const bffc_plan* p) {
-  g_tm_dtype = p->dtype == BFFC_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+extern "C" size_t bffc_workspace_bytes(const bffc_plan* p, int B, int H, int L) {
+  return bffc_workspace_bytes_ex(p, B, H, L, 1, 1);     // enough for every call with these shapes
 }
 
-static int make_map(CUtensorMap* map, const void* base, int rows, int L, int box_rows = 128) {
+static CUtensorMapDataType map_dtype(const bffc_plan* p) {
+  return p->dtype == BFFC_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+}
+
+static int make_map(const bffc_plan* p, CUtensorMap* map, const void* base, int rows, int L, int box_rows = 128) {
   // (rows, L) bf16 viewed as [row][L/64][64]; box = one (128 x 64) tile, 128B swizzle;
   // tile rows >= L/64 are out of bounds: zero-filled on load (implicit padding), dropped on store.
   cuuint64_t dims[3] = {64, cuuint64_t(L / 64), cuuint64_t(rows)};
   cuuint64_t strides[2] = {128, cuuint64_t(L) * 2};
   cuuint32_t box[3] = {64, cuuint32_t(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(map, g_tm_dtype, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = g_encode(map, map_dtype(p), 3, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(BFFC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
@@ -502,12 +518,17 @@ static void fill_params(const bffc_plan* p, bffc::FwdParams& prm, const void* kf
   prm.tw_scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 0.08838834764831845f;
   prm.pregate = nullptr;
   prm.postgate = nullptr;
+  prm.postgate2 = nullptr;
+  prm.y2 = nullptr;
+  prm.kf_conj_mask = 0;
   prm.dbg = nullptr;
   prm.dbg_stages = 0;
   prm.trace = nullptr;
 }
 
-// bring-up: BFFC_TRACE=<file> makes every ungated fused launch record the phase timeline of CTA 0 (tools/trace_fwd3.py)
+#ifdef BFFC_BRINGUP
+// bring-up builds only (nvcc -DBFFC_BRINGUP): BFFC_TRACE=<file> makes every ungated fused launch record the phase
+// timeline of CTA 0 (tools/trace_fwd3.py).  Not compiled into the product library.
 static long long* g_trace = nullptr;
 static long long* trace_buffer() {
   static bool init = false;
@@ -524,6 +545,7 @@ static void trace_dump(cudaStream_t st) {
   cudaMemcpy(h.data(), g_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
   if (FILE* f = fopen(getenv("BFFC_TRACE"), "wb")) { fwrite(h.data(), sizeof(long long), h.size(), f); fclose(f); }
 }
+#endif
 
 // Segment geometry of the input tiles: S = 4096/N batch members per 8192-point slot for the small sizes, else 1.
 struct SegGeom { int S, seg_rows, groups, kmask; };
@@ -539,21 +561,33 @@ static SegGeom seg_geom(const bffc_plan* p, int B, int L) {
   return g;
 }
 
+// optional extras of one pass of the forward path
+struct PassOpts {
+  int corr = 0;                     // 1: correlation (the du path of the backward): fold offset of the small sizes
+  int conj = 0;                     // 1: conjugate k_f inside the kernel's pointwise multiply (else kf is pre-conjugated)
+  const void* postgate2 = nullptr;  // second gated output y2 = postgate2 * conv(...) from the same pass
+  void* y2 = nullptr;
+};
+
 // fused 8192-point kernel on (B, H, L) real sequences.  Small sizes (p->N < 8192): `y` is the fold scratch.
 static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const void* pregate, const void* postgate,
-                        void* y, int B, int H, int L, float* dbg, int dbg_stages, int max_units, cudaStream_t st) {
+                        void* y, int B, int H, int L, float* dbg, int dbg_stages, int max_units, cudaStream_t st,
+                        const PassOpts& po = PassOpts()) {
   if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen <= 8192 in this build", L);
   const bool small = p->N < kInner;
   const SegGeom sg = seg_geom(p, B, L);
   CUtensorMap tm_u, tm_y, tm_g;
-  if (int rc = make_map(&tm_u, u, B * H, L, sg.seg_rows)) return rc;
-  if (small) { if (int rc = make_map(&tm_y, y, H * sg.groups * 2, kInner)) return rc; }
-  else if (int rc = make_map(&tm_y, y, B * H, L)) return rc;
-  if (int rc = make_map(&tm_g, pregate ? pregate : u, B * H, L, sg.seg_rows)) return rc;
+  if (int rc = make_map(p, &tm_u, u, B * H, L, sg.seg_rows)) return rc;
+  if (small) { if (int rc = make_map(p, &tm_y, y, H * sg.groups * 2, kInner)) return rc; }
+  else if (int rc = make_map(p, &tm_y, y, B * H, L)) return rc;
+  if (int rc = make_map(p, &tm_g, pregate ? pregate : u, B * H, L, sg.seg_rows)) return rc;
   bffc::FwdParams prm;
   fill_params(p, prm, kf);
   prm.pregate = static_cast<const uint32_t*>(pregate);
   prm.postgate = static_cast<const uint32_t*>(postgate);
+  prm.postgate2 = small ? nullptr : static_cast<const uint32_t*>(po.postgate2);   // small sizes: applied by the fold
+  prm.y2 = small ? nullptr : static_cast<uint32_t*>(po.y2);
+  prm.kf_conj_mask = po.conj ? 0x80008000u : 0u;
   prm.B = B; prm.H = H; prm.L = L;
   prm.pairs = sg.groups;
   prm.kmask = sg.kmask;
@@ -570,54 +604,53 @@ static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const
   FMT_SWITCH(p->dtype,
     if (dbg)
       fwd_kernel<true, false, false, F><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
-    else if (pregate || postgate)
+    else if (pregate || postgate || prm.y2)
       fwd_kernel<false, true, false, F><<<grid, kThreads, kSmemTotalGated, st>>>(tm_u, tm_y, tm_g, prm);
-    else if (use_fwd3()) {
+    else {
       int g3 = (prm.units + kPipes3 - 1) / kPipes3;
       if (g3 > p->num_sms) g3 = p->num_sms;
+#ifdef BFFC_BRINGUP
       prm.trace = trace_buffer();
+#endif
       fwd3_kernel<false, F><<<g3, kThreads3, kSmemTotal3, st>>>(tm_u, tm_y, tm_g, prm);
+#ifdef BFFC_BRINGUP
       if (prm.trace) trace_dump(st);
-    } else
-      fwd_kernel<false, false, false, F><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
+#endif
+    }
   );
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
 
 // fused kernel on complex rows held in two planes (in place); rows = pairs * kf_rows
-static int launch_planes(const bffc_plan* p, void* pre, void* pim, const void* kf, int pairs, int kf_rows, cudaStream_t st) {
+static int launch_planes(const bffc_plan* p, void* pre, void* pim, const void* kf, int pairs, int kf_rows, cudaStream_t st,
+                         int conj = 0) {
   CUtensorMap tm_r, tm_i;
-  if (int rc = make_map(&tm_r, pre, pairs * kf_rows, kInner)) return rc;
-  if (int rc = make_map(&tm_i, pim, pairs * kf_rows, kInner)) return rc;
+  if (int rc = make_map(p, &tm_r, pre, pairs * kf_rows, kInner)) return rc;
+  if (int rc = make_map(p, &tm_i, pim, pairs * kf_rows, kInner)) return rc;
   bffc::FwdParams prm;
   fill_params(p, prm, kf);
   prm.B = 2 * pairs; prm.H = kf_rows; prm.L = kInner;
   prm.pairs = pairs;
   prm.kmask = 0xff; prm.nseg = 1; prm.seg_bytes = 16384; prm.small_out = 0;
   prm.units = kf_rows * pairs;
-  int grid = (prm.units + 1) / 2;
-  if (grid > p->num_sms) grid = p->num_sms;
+  prm.kf_conj_mask = conj ? 0x80008000u : 0u;
   using namespace bffc::r128;
-  if (use_fwd3()) {
-    int g3 = (prm.units + kPipes3 - 1) / kPipes3;
-    if (g3 > p->num_sms) g3 = p->num_sms;
-    FMT_SWITCH(p->dtype, (fwd3_kernel<true, F><<<g3, kThreads3, kSmemTotal3, st>>>(tm_r, tm_r, tm_i, prm)););
-  } else {
-    FMT_SWITCH(p->dtype, (fwd_kernel<false, false, true, F><<<grid, kThreads, kSmemTotal, st>>>(tm_r, tm_r, tm_i, prm)););
-  }
+  int g3 = (prm.units + kPipes3 - 1) / kPipes3;
+  if (g3 > p->num_sms) g3 = p->num_sms;
+  FMT_SWITCH(p->dtype, (fwd3_kernel<true, F><<<g3, kThreads3, kSmemTotal3, st>>>(tm_r, tm_r, tm_i, prm)););
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
 
-static int make_map4(CUtensorMap* map, const void* base, int chunks, int rows, int seqs, size_t row_stride_bytes,
-                     size_t seq_stride_bytes) {
+static int make_map4(const bffc_plan* p, CUtensorMap* map, const void* base, int chunks, int rows, int seqs,
+                     size_t row_stride_bytes, size_t seq_stride_bytes) {
   // [seq][row][chunk][64] bf16 view of a strided matrix; box = 128 rows x 64 columns of one chunk, 128B swizzle.
   cuuint64_t dims[4] = {64, cuuint64_t(chunks), cuuint64_t(rows), cuuint64_t(seqs)};
   cuuint64_t strides[3] = {128, cuuint64_t(row_stride_bytes), cuuint64_t(seq_stride_bytes)};
   cuuint32_t box[4] = {64, 1, 128, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = g_encode(map, g_tm_dtype, 4, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = g_encode(map, map_dtype(p), 4, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(BFFC_ERR_CUDA, "cuTensorMapEncodeTiled (4d) failed (%d)", int(r));
@@ -634,15 +667,13 @@ static void fill_step(bffc::outer::OuterParams& op, double n_level) {
 }
 
 template <int R, int F>
-static void launch_cc(bool inverse, bool gated, bool planes, const bffc::outer::OuterParams& op_in, int rows, cudaStream_t st) {
+static void launch_cc(const bffc_plan* p, bool inverse, bool gated, bool planes, const bffc::outer::OuterParams& op_in,
+                      int rows, cudaStream_t st) {
   using namespace bffc::outer;
   OuterParams op = op_in;
   // read-ahead distance = the number of resident blocks (one residency period ahead; measured optimum at C3:
   // 0 -> 0.827 ms, 296 -> 0.690, 592 -> 0.693, 1184 -> 0.725, 2368 -> 0.985 ms for the three kernels)
-  static const int la_env = getenv("BFFC_LOOKAHEAD") ? atoi(getenv("BFFC_LOOKAHEAD")) : -1;
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  op.lookahead = la_env >= 0 ? la_env : sms * (R <= 4 ? 4 : 2);
+  op.lookahead = p->num_sms * (R <= 4 ? 4 : 2);
   const int cb = op.M / (kVec * 128);
   if (planes) {
     dim3 grid(rows, cb, 1);
@@ -659,13 +690,12 @@ static void launch_cc(bool inverse, bool gated, bool planes, const bffc::outer::
     }
   }
 }
-static thread_local int g_cur_dtype = BFFC_DTYPE_BF16;
-static int cc_stage(int R, bool inverse, bool gated, bool planes, const bffc::outer::OuterParams& op, int rows,
+static int cc_stage(const bffc_plan* p, int R, bool inverse, bool gated, bool planes, const bffc::outer::OuterParams& op, int rows,
                     cudaStream_t st) {
   switch (R) {
-    case 2: FMT_SWITCH(g_cur_dtype, (launch_cc<2, F>(inverse, gated, planes, op, rows, st));); break;
-    case 4: FMT_SWITCH(g_cur_dtype, (launch_cc<4, F>(inverse, gated, planes, op, rows, st));); break;
-    case 8: FMT_SWITCH(g_cur_dtype, (launch_cc<8, F>(inverse, gated, planes, op, rows, st));); break;
+    case 2: FMT_SWITCH(p->dtype, (launch_cc<2, F>(p, inverse, gated, planes, op, rows, st));); break;
+    case 4: FMT_SWITCH(p->dtype, (launch_cc<4, F>(p, inverse, gated, planes, op, rows, st));); break;
+    case 8: FMT_SWITCH(p->dtype, (launch_cc<8, F>(p, inverse, gated, planes, op, rows, st));); break;
     default: return fail(BFFC_ERR_UNSUPPORTED, "outer radix %d not supported", R);
   }
   CUDA_TRY(cudaGetLastError());
@@ -674,17 +704,19 @@ static int cc_stage(int R, bool inverse, bool gated, bool planes, const bffc::ou
 
 // tcgen05 radix-128 level 0: real endpoint x (u or y), gate g (pregate fwd / postgate inv), planes set A
 static int tc_stage(const bffc_plan* p, bool inverse, const void* x, const void* gate, PlaneSet A, int B, int H, int L,
-                    cudaStream_t st) {
+                    cudaStream_t st, const void* gate2 = nullptr, void* x2 = nullptr) {
   const int M = p->N / 128, chunks = M / 64, pairs = (B + 1) / 2;
   if (L % M != 0) return fail(BFFC_ERR_UNSUPPORTED, "seqlen %d needs L to be a multiple of %d in this build (L=%d)", p->N, M, L);
   CUtensorMap tm_x, tm_pr, tm_pi, tm_g;
-  if (int rc = make_map4(&tm_x, x, chunks, L / M, B * H, size_t(M) * 2, size_t(L) * 2)) return rc;
-  if (int rc = make_map4(&tm_pr, A.re, chunks, 128, pairs * H, size_t(M) * 2, size_t(p->N) * 2)) return rc;
-  if (int rc = make_map4(&tm_pi, A.im, chunks, 128, pairs * H, size_t(M) * 2, size_t(p->N) * 2)) return rc;
-  if (int rc = make_map4(&tm_g, (!inverse && gate) ? gate : x, chunks, L / M, B * H, size_t(M) * 2, size_t(L) * 2)) return rc;
+  if (int rc = make_map4(p, &tm_x, x, chunks, L / M, B * H, size_t(M) * 2, size_t(L) * 2)) return rc;
+  if (int rc = make_map4(p, &tm_pr, A.re, chunks, 128, pairs * H, size_t(M) * 2, size_t(p->N) * 2)) return rc;
+  if (int rc = make_map4(p, &tm_pi, A.im, chunks, 128, pairs * H, size_t(M) * 2, size_t(p->N) * 2)) return rc;
+  if (int rc = make_map4(p, &tm_g, (!inverse && gate) ? gate : x, chunks, L / M, B * H, size_t(M) * 2, size_t(L) * 2)) return rc;
   bffc::OuterTcParams prm;
   prm.dftC = p->dftC; prm.dftS = p->dftS;
   prm.postgate = inverse ? static_cast<const uint32_t*>(gate) : nullptr;
+  prm.postgate2 = inverse ? static_cast<const uint32_t*>(gate2) : nullptr;
+  prm.y2 = inverse ? static_cast<uint32_t*>(x2) : nullptr;
   prm.has_pregate = (!inverse && gate) ? 1 : 0;
   prm.tw_scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 0.08838834764831845f;
   prm.B = B; prm.H = H; prm.L = L; prm.pairs = pairs;
@@ -725,7 +757,7 @@ static int transform_fwd(const bffc_plan* p, const void* x, const void* pregate,
     op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / l0.R;
     op.scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 1.0f / sqrtf(float(l0.R));
     fill_step(op, double(p->N));
-    if (int rc = cc_stage(l0.R, false, pregate != nullptr, false, op, 0, st)) return rc;
+    if (int rc = cc_stage(p, l0.R, false, pregate != nullptr, false, op, 0, st)) return rc;
   }
   *launches += 1;
   *out = s0;
@@ -737,7 +769,7 @@ static int transform_fwd(const bffc_plan* p, const void* x, const void* pregate,
     op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / (l0.R * l1.R);
     op.scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 1.0f / sqrtf(float(l1.R));
     fill_step(op, double(p->N) / l0.R);
-    if (int rc = cc_stage(l1.R, false, false, true, op, pairs * H * l0.R, st)) return rc;
+    if (int rc = cc_stage(p, l1.R, false, false, true, op, pairs * H * l0.R, st)) return rc;
     *launches += 1;
     *out = s1;
   }
@@ -746,7 +778,7 @@ static int transform_fwd(const bffc_plan* p, const void* x, const void* pregate,
 
 // all outer levels, inverse: rows in `rows` (set s1 if two levels, else s0) -> real y (* postgate)
 static int transform_inv(const bffc_plan* p, void* y, const void* postgate, int B, int H, int L, PlaneSet s0, PlaneSet s1,
-                         cudaStream_t st, int* launches) {
+                         cudaStream_t st, int* launches, const void* postgate2 = nullptr, void* y2 = nullptr) {
   const int pairs = (B + 1) / 2;
   const bffc_level l0 = p->lev[0];
   if (p->nlev == 2) {
@@ -757,20 +789,22 @@ static int transform_inv(const bffc_plan* p, void* y, const void* postgate, int 
     op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / (l0.R * l1.R);
     op.scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 1.0f / sqrtf(float(l1.R));
     fill_step(op, double(p->N) / l0.R);
-    if (int rc = cc_stage(l1.R, true, false, true, op, pairs * H * l0.R, st)) return rc;
+    if (int rc = cc_stage(p, l1.R, true, false, true, op, pairs * H * l0.R, st)) return rc;
     *launches += 1;
   }
   if (l0.tc) {
-    if (int rc = tc_stage(p, true, y, postgate, s0, B, H, L, st)) return rc;
+    if (int rc = tc_stage(p, true, y, postgate, s0, B, H, L, st, postgate2, y2)) return rc;
   } else {
     bffc::outer::OuterParams op{};
     op.y = static_cast<uint4*>(y);
     op.postgate = static_cast<const uint4*>(postgate);
+    op.postgate2 = static_cast<const uint4*>(postgate2);
+    op.y2 = static_cast<uint4*>(y2);
     op.pre = reinterpret_cast<uint4*>(s0.re); op.pim = reinterpret_cast<uint4*>(s0.im);
     op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / l0.R;
     op.scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 1.0f / sqrtf(float(l0.R));
     fill_step(op, double(p->N));
-    if (int rc = cc_stage(l0.R, true, postgate != nullptr, false, op, 0, st)) return rc;
+    if (int rc = cc_stage(p, l0.R, true, postgate != nullptr, false, op, 0, st)) return rc;
   }
   *launches += 1;
   return BFFC_OK;
@@ -787,7 +821,9 @@ static int check_common(const bffc_plan* p, int B, int H, int L, const void* a, 
 
 // y = postgate * conv(u * pregate, k) for any supported size.  `ws`: workspace (plane sets 0 and 1) for composite sizes.
 static int conv_forward(const bffc_plan* p, const void* u, const void* kf, const void* pregate, const void* postgate,
-                        void* y, int B, int H, int L, void* ws, cudaStream_t st, int* launches, int corr = 0) {
+                        void* y, int B, int H, int L, void* ws, cudaStream_t st, int* launches,
+                        const PassOpts& po = PassOpts()) {
+  const int corr = po.corr;
   if (p->N < kInner) {
     // small sizes (reference: the 2-stage / r2r kernels for 256..2048 and 16_16_16 for 4096, conv.py:78-131): zero-padded
     // operands make the 8192-point circular result a LINEAR (corr = 0) convolution or correlation (corr = 1, du path)
@@ -795,25 +831,25 @@ static int conv_forward(const bffc_plan* p, const void* u, const void* kf, const
     // S = 4096/N batch members of a channel share one 8192-point slot (spacing 2N), so a unit carries 2S sequences.
     const int off = corr ? kInner - p->N : p->N;
     const SegGeom sg = seg_geom(p, B, L);
-    if (int rc = launch_fused(p, u, kf, pregate, nullptr, ws, B, H, L, nullptr, 0, 0, st)) return rc;
+    if (int rc = launch_fused(p, u, kf, pregate, nullptr, ws, B, H, L, nullptr, 0, 0, st, po)) return rc;
     const size_t rows = size_t(B) * H, total = rows * (L / 8);
     FMT_SWITCH(p->dtype, (fold_kernel<F><<<unsigned((total + 255) / 256), 256, 0, st>>>(
-        static_cast<const uint4*>(ws), static_cast<const uint4*>(postgate), static_cast<uint4*>(y), L, p->N, sg.S,
-        sg.groups, H, off, rows)););
+        static_cast<const uint4*>(ws), static_cast<const uint4*>(postgate), static_cast<uint4*>(y),
+        static_cast<const uint4*>(po.postgate2), static_cast<uint4*>(po.y2), L, p->N, sg.S, sg.groups, H, off, rows)););
     CUDA_TRY(cudaGetLastError());
     *launches += 2;
     return BFFC_OK;
   }
   if (p->nlev == 0) {
     *launches += 1;
-    return launch_fused(p, u, kf, pregate, postgate, y, B, H, L, nullptr, 0, 0, st);
+    return launch_fused(p, u, kf, pregate, postgate, y, B, H, L, nullptr, 0, 0, st, po);
   }
   const int pairs = (B + 1) / 2;
   PlaneSet s0 = plane_set(p, ws, 0, B, H), s1 = plane_set(p, ws, p->nlev == 2 ? 1 : 0, B, H), rows;
   if (int rc = transform_fwd(p, u, pregate, B, H, L, s0, s1, &rows, st, launches)) return rc;
-  if (int rc = launch_planes(p, rows.re, rows.im, kf, pairs, H * p->R, st)) return rc;
+  if (int rc = launch_planes(p, rows.re, rows.im, kf, pairs, H * p->R, st, po.conj)) return rc;
   *launches += 1;
-  return transform_inv(p, y, postgate, B, H, L, s0, s1, st, launches);
+  return transform_inv(p, y, postgate, B, H, L, s0, s1, st, launches, po.postgate2, po.y2);
 }
 
 extern "C" {
@@ -824,14 +860,13 @@ int bffc_fwd(const bffc_plan* p, const void* u, const void* kf, const void* preg
     return fail(BFFC_ERR_INVALID, "bffc_fwd: pregate and postgate must both be given or both be null");
   if (!u || !kf || !y) return fail(BFFC_ERR_INVALID, "bffc_fwd: null pointer");
   if (int rc = check_common(p, B, H, L, u, y, kf)) return rc;
-  set_map_dtype(p); g_cur_dtype = p->dtype;
   if ((reinterpret_cast<uintptr_t>(pregate) | reinterpret_cast<uintptr_t>(postgate) | reinterpret_cast<uintptr_t>(workspace)) & 15)
     return fail(BFFC_ERR_INVALID, "bffc_fwd: gates / workspace must be 16-byte aligned");
-  if (p->N < kInner) {
-    if (!workspace || workspace_bytes < bffc_workspace_bytes(p, B, H, L))
-      return fail(BFFC_ERR_INVALID, "bffc_fwd: workspace of %zu bytes required", bffc_workspace_bytes(p, B, H, L));
-  } else if (p->nlev > 0 && (!workspace || workspace_bytes < size_t(2 * p->nlev) * plane_bytes(p, B, H)))
-    return fail(BFFC_ERR_INVALID, "bffc_fwd: workspace of %zu bytes required", size_t(2 * p->nlev) * plane_bytes(p, B, H));
+  {
+    const size_t need = bffc_workspace_bytes_ex(p, B, H, L, pregate != nullptr, 0);
+    if (need && (!workspace || workspace_bytes < need))
+      return fail(BFFC_ERR_INVALID, "bffc_fwd: workspace of %zu bytes required", need);
+  }
   int launches = 0;
   int rc = conv_forward(p, u, kf, pregate, postgate, y, B, H, L, workspace, static_cast<cudaStream_t>(stream), &launches);
   g_launches = launches;
@@ -844,32 +879,42 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
   if ((pregate == nullptr) != (postgate == nullptr))
     return fail(BFFC_ERR_INVALID, "bffc_bwd: pregate and postgate must both be given or both be null");
   const bool gated = pregate != nullptr;
-  if (!dout || !u || !kf_conj || !du || !dkf) return fail(BFFC_ERR_INVALID, "bffc_bwd: null pointer");
+  if (!dout || !u || (!kf && !kf_conj) || !du || !dkf) return fail(BFFC_ERR_INVALID, "bffc_bwd: null pointer");
   if (gated && (!kf || !dpregate || !dpostgate)) return fail(BFFC_ERR_INVALID, "bffc_bwd: gated backward needs kf, dpregate, dpostgate");
   if ((reinterpret_cast<uintptr_t>(pregate) | reinterpret_cast<uintptr_t>(postgate) | reinterpret_cast<uintptr_t>(dpregate) |
        reinterpret_cast<uintptr_t>(dpostgate) | reinterpret_cast<uintptr_t>(kf)) & 15)
     return fail(BFFC_ERR_INVALID, "bffc_bwd: gate pointers must be 16-byte aligned");
   if (int rc = check_common(p, B, H, L, u, du, dout)) return rc;
-  set_map_dtype(p); g_cur_dtype = p->dtype;
   if ((reinterpret_cast<uintptr_t>(dkf) | reinterpret_cast<uintptr_t>(kf_conj) | reinterpret_cast<uintptr_t>(workspace)) & 15)
     return fail(BFFC_ERR_INVALID, "bffc_bwd: dkf / kf / workspace must be 16-byte aligned");
-  if ((p->nlev > 0 || p->N < kInner) && (!workspace || workspace_bytes < bffc_workspace_bytes(p, B, H, L)))
-    return fail(BFFC_ERR_INVALID, "bffc_bwd: workspace of %zu bytes required", bffc_workspace_bytes(p, B, H, L));
+  {
+    const size_t need = bffc_workspace_bytes_ex(p, B, H, L, gated, 1);
+    if (need && (!workspace || workspace_bytes < need))
+      return fail(BFFC_ERR_INVALID, "bffc_bwd: workspace of %zu bytes required", need);
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int launches = 0;
-  // du = corr(dout, k) = circular conv with conj(k_f): the forward path on dout
+  // du = corr(dout, k) = circular conv with conj(k_f): the forward path on dout, conjugating k_f in the kernel's
+  // pointwise multiply (a pre-conjugated kf_engine_conj is still accepted)
   // (reference: kernels_bf16/monarch_cuda_32_16_16_bwd_kernel_bf16.h:740-815)
+  PassOpts dx;
+  dx.corr = 1;
+  dx.conj = kf_conj ? 0 : 1;
+  const void* kfc = kf_conj ? kf_conj : kf;
   if (!gated) {
-    if (int rc = conv_forward(p, dout, kf_conj, nullptr, nullptr, du, B, H, L, workspace, st, &launches, 1)) return rc;
+    if (int rc = conv_forward(p, dout, kfc, nullptr, nullptr, du, B, H, L, workspace, st, &launches, dx)) return rc;
   } else {
     // y = q * conv(u*p, k)  (conv.py:3856-3939; kernels_bf16/..._bwd_kernel_bf16.h:836-906; host recompute
     // monarch_cuda_interface_bwd_bf16.cu:798-808).  With dx = corr(dout*q, k):
-    //   dpostgate = dout * conv(u*p, k),  du = p * dx,  dpregate = u * dx     — three passes of the forward path
+    //   dpostgate = dout * conv(u*p, k)                        — one pass of the forward path
+    //   du = p * dx  and  dpregate = u * dx                    — ONE more pass with two gated outputs
     if (int rc = conv_forward(p, u, kf, pregate, dout, dpostgate, B, H, L, workspace, st, &launches)) return rc;
-    if (int rc = conv_forward(p, dout, kf_conj, postgate, pregate, du, B, H, L, workspace, st, &launches, 1)) return rc;
-    if (int rc = conv_forward(p, dout, kf_conj, postgate, u, dpregate, B, H, L, workspace, st, &launches, 1)) return rc;
+    dx.postgate2 = u;
+    dx.y2 = dpregate;
+    if (int rc = conv_forward(p, dout, kfc, postgate, pregate, du, B, H, L, workspace, st, &launches, dx)) return rc;
   }
-  // dk_f = sum_b FFT(dout*q) * conj(FFT(u*p))
+  // dk_f = sum_b FFT(dout*q) * conj(FFT(u*p)), reduced with fp32 atomics into the zeroed gradient
+  CUDA_TRY(cudaMemsetAsync(dkf, 0, size_t(H) * p->NE * sizeof(float2), st));
   const int pairs = (B + 1) / 2;
   bffc::DkfParams prm;
   prm.dftC = p->dftC;
@@ -880,23 +925,31 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
   prm.tw_scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 0.08838834764831845f;
   using namespace bffc::r128;
   if (p->nlev == 0) {
-    if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen 8192 in this build", L);
-    CUtensorMap tm_u, tm_d, tm_p, tm_q;
+    if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen <= 8192 in this build", L);
+    const void *xu = u, *xd = dout;
+    if (gated) {
+      // gated loads: u*pregate and dout*postgate (reference: ..._bwd_kernel_bf16.h:505-509,571-581) from an elementwise
+      // pre-pass into the tail of the workspace
+      uint8_t* g0 = static_cast<uint8_t*>(workspace) + (p->N < kInner ? bffc_workspace_bytes_ex(p, B, H, L, 0, 0) : 0);
+      uint8_t* g1 = g0 + gate_scratch_bytes(B, H, L) / 2;
+      const size_t nvec = size_t(B) * H * L / 8;
+      FMT_SWITCH(p->dtype, (gate_mul2_kernel<F><<<unsigned((nvec + 255) / 256), 256, 0, st>>>(
+          static_cast<const uint4*>(u), static_cast<const uint4*>(pregate), reinterpret_cast<uint4*>(g0),
+          static_cast<const uint4*>(dout), static_cast<const uint4*>(postgate), reinterpret_cast<uint4*>(g1), nvec)););
+      CUDA_TRY(cudaGetLastError());
+      launches += 1;
+      xu = g0; xd = g1;
+    }
+    CUtensorMap tm_u, tm_d;
     const SegGeom sg = seg_geom(p, B, L);
-    if (int rc = make_map(&tm_u, u, B * H, L, sg.seg_rows)) return rc;
-    if (int rc = make_map(&tm_d, dout, B * H, L, sg.seg_rows)) return rc;
-    if (int rc = make_map(&tm_p, gated ? pregate : u, B * H, L, sg.seg_rows)) return rc;
-    if (int rc = make_map(&tm_q, gated ? postgate : dout, B * H, L, sg.seg_rows)) return rc;
+    if (int rc = make_map(p, &tm_u, xu, B * H, L, sg.seg_rows)) return rc;
+    if (int rc = make_map(p, &tm_d, xd, B * H, L, sg.seg_rows)) return rc;
     prm.B = B; prm.H = H; prm.L = L;
     prm.pairs = sg.groups;
     prm.kmask = sg.kmask; prm.nseg = sg.S; prm.seg_bytes = sg.seg_rows * 128;
-    prm.gated = gated ? 1 : 0;
-    int grid = H < p->num_sms ? H : p->num_sms;
-    if (!gated && use_dkf3()) {
-      FMT_SWITCH(p->dtype, (dkf3_kernel<false, F><<<grid, kThreadsDkf3, kSmemTotalDkf3, st>>>(tm_u, tm_d, tm_p, tm_q, prm)););
-    } else {
-      FMT_SWITCH(p->dtype, (dkf_kernel<false, F><<<grid, kThreads, gated ? kSmemTotalDkfGated : kSmemTotalDkf, st>>>(tm_u, tm_d, tm_p, tm_q, prm)););
-    }
+    const long long units = (long long)H * prm.pairs;
+    const int grid = int(units < p->num_sms ? units : p->num_sms);
+    FMT_SWITCH(p->dtype, (dkf3_kernel<false, F><<<grid, kThreadsDkf3, kSmemTotalDkf3, st>>>(tm_u, tm_d, tm_u, tm_d, prm)););
     CUDA_TRY(cudaGetLastError());
     launches += 1;
   } else {
@@ -913,19 +966,15 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
     }
     const int rows = H * p->R;
     CUtensorMap tur, tui, tdr, tdi;
-    if (int rc = make_map(&tur, ru.re, pairs * rows, kInner)) return rc;
-    if (int rc = make_map(&tui, ru.im, pairs * rows, kInner)) return rc;
-    if (int rc = make_map(&tdr, rd.re, pairs * rows, kInner)) return rc;
-    if (int rc = make_map(&tdi, rd.im, pairs * rows, kInner)) return rc;
+    if (int rc = make_map(p, &tur, ru.re, pairs * rows, kInner)) return rc;
+    if (int rc = make_map(p, &tui, ru.im, pairs * rows, kInner)) return rc;
+    if (int rc = make_map(p, &tdr, rd.re, pairs * rows, kInner)) return rc;
+    if (int rc = make_map(p, &tdi, rd.im, pairs * rows, kInner)) return rc;
     prm.B = 2 * pairs; prm.H = rows; prm.L = kInner;
     prm.kmask = 0xff; prm.nseg = 1; prm.seg_bytes = 16384;
-    prm.gated = 0;
-    int grid = rows < p->num_sms ? rows : p->num_sms;
-    if (use_dkf3()) {
-      FMT_SWITCH(p->dtype, (dkf3_kernel<true, F><<<grid, kThreadsDkf3, kSmemTotalDkf3, st>>>(tur, tdr, tui, tdi, prm)););
-    } else {
-      FMT_SWITCH(p->dtype, (dkf_kernel<true, F><<<grid, kThreads, kSmemTotalDkf, st>>>(tur, tdr, tui, tdi, prm)););
-    }
+    const long long units = (long long)rows * pairs;
+    const int grid = int(units < p->num_sms ? units : p->num_sms);
+    FMT_SWITCH(p->dtype, (dkf3_kernel<true, F><<<grid, kThreadsDkf3, kSmemTotalDkf3, st>>>(tur, tdr, tui, tdi, prm)););
     CUDA_TRY(cudaGetLastError());
     launches += 1;
   }
@@ -963,7 +1012,7 @@ size_t bffc_host_workspace_bytes(const bffc_plan* p, int B, int H, int L, int ga
   if (!p || B <= 0 || H <= 0 || L <= 0) return 0;
   const HostChunk g = host_chunk(B, H, L);
   const size_t t = align256(size_t(g.bc) * g.hc * L * 2);
-  return 2 * ((gated ? 4 : 2) * t + align256(bffc_workspace_bytes(p, g.bc, g.hc, L)));
+  return 2 * ((gated ? 4 : 2) * t + align256(bffc_workspace_bytes_ex(p, g.bc, g.hc, L, gated, 0)));
 }
 
 int bffc_fwd_host(const bffc_plan* p, const void* u_host, const void* kf, const void* pre_host, const void* post_host,
@@ -975,53 +1024,62 @@ int bffc_fwd_host(const bffc_plan* p, const void* u_host, const void* kf, const 
   const bool gated = pre_host != nullptr;
   if (!dev_ws || dev_ws_bytes < bffc_host_workspace_bytes(p, B, H, L, gated))
     return fail(BFFC_ERR_INVALID, "bffc_fwd_host: device workspace of %zu bytes required", bffc_host_workspace_bytes(p, B, H, L, gated));
-  set_map_dtype(p); g_cur_dtype = p->dtype;
-  if (!p->hs[0]) {
-    for (auto& st : p->hs) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    for (auto& ev : p->hev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  }
   cudaStream_t user = static_cast<cudaStream_t>(stream), s_in = p->hs[0], s_cmp = p->hs[1], s_out = p->hs[2];
   cudaEvent_t ev_start = p->hev[0];
-  cudaEvent_t* ev_in = &p->hev[1];    // [slot] chunk copied in
-  cudaEvent_t* ev_cmp = &p->hev[3];   // [slot] chunk convolved (input slot free again)
-  cudaEvent_t* ev_out = &p->hev[5];   // [slot] chunk copied out (output slot free again)
+  const cudaEvent_t* ev_in = &p->hev[1];    // [slot] chunk copied in
+  const cudaEvent_t* ev_cmp = &p->hev[3];   // [slot] chunk convolved (input slot free again)
+  const cudaEvent_t* ev_out = &p->hev[5];   // [slot] chunk copied out (output slot free again)
   const HostChunk g = host_chunk(B, H, L);
   const size_t t = align256(size_t(g.bc) * g.hc * L * 2);
-  const size_t conv_ws = bffc_workspace_bytes(p, g.bc, g.hc, L);
+  const size_t conv_ws = bffc_workspace_bytes_ex(p, g.bc, g.hc, L, gated, 0);
   const size_t slot_bytes = (gated ? 4 : 2) * t + align256(conv_ws);
   const size_t host_pitch = size_t(H) * L * 2;                   // one batch member of the host tensors
   const size_t kf_row = size_t(p->NE) * 4;                       // one channel of kf_engine
-  CUDA_TRY(cudaEventRecord(ev_start, user));
-  CUDA_TRY(cudaStreamWaitEvent(s_in, ev_start, 0));
-  CUDA_TRY(cudaStreamWaitEvent(s_out, ev_start, 0));
+  // Error handling: once copies are in flight a failure must not return before they have stopped touching the caller's
+  // host / device buffers, so the body runs in a lambda and every exit joins the three internal streams.
   int launches = 0, c = 0;
-  for (int b0 = 0; b0 < B; b0 += g.bc)
-    for (int h0 = 0; h0 < H; h0 += g.hc, ++c) {
-      const int nb = B - b0 < g.bc ? B - b0 : g.bc, nh = H - h0 < g.hc ? H - h0 : g.hc, slot = c & 1;
-      uint8_t* base = static_cast<uint8_t*>(dev_ws) + slot * slot_bytes;
-      uint8_t *d_u = base, *d_y = base + t, *d_p = gated ? base + 2 * t : nullptr, *d_q = gated ? base + 3 * t : nullptr;
-      uint8_t* d_ws = base + (gated ? 4 : 2) * t;
-      // chunk = rows b0..b0+nb of a (B, H*L) matrix, columns h0*L..(h0+nh)*L: pitched on the host, dense on the device
-      const size_t off = size_t(b0) * host_pitch + size_t(h0) * L * 2, width = size_t(nh) * L * 2;
-      if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(s_in, ev_cmp[slot], 0));
-      CUDA_TRY(cudaMemcpy2DAsync(d_u, width, static_cast<const uint8_t*>(u_host) + off, host_pitch, width, nb, cudaMemcpyHostToDevice, s_in));
-      if (gated) {
-        CUDA_TRY(cudaMemcpy2DAsync(d_p, width, static_cast<const uint8_t*>(pre_host) + off, host_pitch, width, nb, cudaMemcpyHostToDevice, s_in));
-        CUDA_TRY(cudaMemcpy2DAsync(d_q, width, static_cast<const uint8_t*>(post_host) + off, host_pitch, width, nb, cudaMemcpyHostToDevice, s_in));
+  auto body = [&]() -> int {
+    CUDA_TRY(cudaEventRecord(ev_start, user));
+    CUDA_TRY(cudaStreamWaitEvent(s_in, ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(s_out, ev_start, 0));
+    for (int b0 = 0; b0 < B; b0 += g.bc)
+      for (int h0 = 0; h0 < H; h0 += g.hc, ++c) {
+        const int nb = B - b0 < g.bc ? B - b0 : g.bc, nh = H - h0 < g.hc ? H - h0 : g.hc, slot = c & 1;
+        uint8_t* base = static_cast<uint8_t*>(dev_ws) + slot * slot_bytes;
+        uint8_t *d_u = base, *d_y = base + t, *d_p = gated ? base + 2 * t : nullptr, *d_q = gated ? base + 3 * t : nullptr;
+        uint8_t* d_ws = base + (gated ? 4 : 2) * t;
+        // chunk = rows b0..b0+nb of a (B, H*L) matrix, columns h0*L..(h0+nh)*L: pitched on the host, dense on the device
+        const size_t off = size_t(b0) * host_pitch + size_t(h0) * L * 2, width = size_t(nh) * L * 2;
+        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(s_in, ev_cmp[slot], 0));
+        CUDA_TRY(cudaMemcpy2DAsync(d_u, width, static_cast<const uint8_t*>(u_host) + off, host_pitch, width, nb, cudaMemcpyHostToDevice, s_in));
+        if (gated) {
+          CUDA_TRY(cudaMemcpy2DAsync(d_p, width, static_cast<const uint8_t*>(pre_host) + off, host_pitch, width, nb, cudaMemcpyHostToDevice, s_in));
+          CUDA_TRY(cudaMemcpy2DAsync(d_q, width, static_cast<const uint8_t*>(post_host) + off, host_pitch, width, nb, cudaMemcpyHostToDevice, s_in));
+        }
+        CUDA_TRY(cudaEventRecord(ev_in[slot], s_in));
+        CUDA_TRY(cudaStreamWaitEvent(s_cmp, ev_in[slot], 0));
+        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(s_cmp, ev_out[slot], 0));
+        if (int rc = conv_forward(p, d_u, static_cast<const uint8_t*>(kf) + size_t(h0) * kf_row, d_p, d_q, d_y, nb, nh, L,
+                                  conv_ws ? d_ws : nullptr, s_cmp, &launches)) return rc;
+        CUDA_TRY(cudaEventRecord(ev_cmp[slot], s_cmp));
+        CUDA_TRY(cudaStreamWaitEvent(s_out, ev_cmp[slot], 0));
+        CUDA_TRY(cudaMemcpy2DAsync(static_cast<uint8_t*>(y_host) + off, host_pitch, d_y, width, width, nb, cudaMemcpyDeviceToHost, s_out));
+        CUDA_TRY(cudaEventRecord(ev_out[slot], s_out));
       }
-      CUDA_TRY(cudaEventRecord(ev_in[slot], s_in));
-      CUDA_TRY(cudaStreamWaitEvent(s_cmp, ev_in[slot], 0));
-      if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(s_cmp, ev_out[slot], 0));
-      if (int rc = conv_forward(p, d_u, static_cast<const uint8_t*>(kf) + size_t(h0) * kf_row, d_p, d_q, d_y, nb, nh, L,
-                                conv_ws ? d_ws : nullptr, s_cmp, &launches)) return rc;
-      CUDA_TRY(cudaEventRecord(ev_cmp[slot], s_cmp));
-      CUDA_TRY(cudaStreamWaitEvent(s_out, ev_cmp[slot], 0));
-      CUDA_TRY(cudaMemcpy2DAsync(static_cast<uint8_t*>(y_host) + off, host_pitch, d_y, width, width, nb, cudaMemcpyDeviceToHost, s_out));
-      CUDA_TRY(cudaEventRecord(ev_out[slot], s_out));
-    }
-  // join: everything enqueued above is complete when the last copy-out is (s_out is in order and waited on each
-  // chunk's compute, which waited on its copy-in)
-  CUDA_TRY(cudaStreamWaitEvent(user, ev_out[(c - 1) & 1], 0));
+    // join: everything enqueued above is complete when the last copy-out is (s_out is in order and waited on each
+    // chunk's compute, which waited on its copy-in)
+    CUDA_TRY(cudaStreamWaitEvent(user, ev_out[(c - 1) & 1], 0));
+    return BFFC_OK;
+  };
+  const int rc = body();
+  if (rc != BFFC_OK) {      // keep the message of the failure; quiesce the internal streams before handing control back
+    char msg[sizeof(g_err)];
+    memcpy(msg, g_err, sizeof(msg));
+    for (auto st : p->hs) cudaStreamSynchronize(st);
+    cudaGetLastError();
+    memcpy(g_err, msg, sizeof(msg));
+    return rc;
+  }
   g_launches = launches;
   return BFFC_OK;
 }
@@ -1030,7 +1088,6 @@ int bffc_debug_fwd_stages(const bffc_plan* p, const void* u, const void* kf, voi
                           int max_stages, void* stream) {
   if (!dump || max_stages <= 0 || !p || p->R != 1) return -BFFC_ERR_INVALID;
   if (check_common(p, B, H, L, u, y, kf)) return -BFFC_ERR_INVALID;
-  set_map_dtype(p); g_cur_dtype = p->dtype;
   int rc = launch_fused(p, u, kf, nullptr, nullptr, y, B, H, L, dump, max_stages, 1, static_cast<cudaStream_t>(stream));
   if (rc) return -rc;
   return max_stages < 4 ? max_stages : 4;

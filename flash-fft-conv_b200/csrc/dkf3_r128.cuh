@@ -1,28 +1,51 @@
-// Backward filter-gradient kernel, warp-specialised software-pipelined variant (ungated): dk_f[h] = sum over batch
-// pairs of FFT(z_dout) * conj(FFT(z_u)), z = x_b + i x_{b+1}.  Same arithmetic as dkf_r128.cuh (kept for the gated case).
+// Backward filter-gradient kernel, N = 128 x 64 (= 8192), sm_100a: dk_f[h] = sum over batch pairs of
+// FFT(z_dout) * conj(FFT(z_u)), z = x_b + i x_{b+1}.
 //
-// dkf_r128.cuh runs stage 1 -> pass 1 -> stage 2 -> accumulate strictly one after the other for one pair at a time:
-// the tensor pipe idles during the passes and the CUDA cores during the MMAs (ncu: tensor pipe 31 % active, 8.6 k
-// cycles per pair against 3.1 k of MMA work).  Here
-//  * the stage-2 A operands live in shared memory (as in fwd3_r128.cuh), which frees TMEM for a THIRD 128-column
+// Path replaced (reference): the dk_f part of monarch_conv_bwd_cuda_kernel
+// (kernels_bf16/monarch_cuda_32_16_16_bwd_kernel_bf16.h:505-509,571-581,711-734: D = FFT(dout), X = FFT(u),
+// dk_f partial = sum over the CTA's batch tile of D * conj(X)) plus the host-side `dk_f_out.sum(0)` over the
+// (B/Bt, H, N, 2) bf16 partials (monarch_cuda_interface_bwd_bf16.cu:820,1107).  Here the sum over the batch is
+// accumulated in fp32 registers; nothing but the final (H, N) complex fp32 gradient is written (fp32 reductions into a
+// zeroed buffer, at most two CTAs per channel).
+//
+// Pair packing: z_u = u_b + i u_{b+1}, z_d = dout_b + i dout_{b+1}.  FFT(z_d) * conj(FFT(z_u)) is the spectrum
+// of corr(d_b,u_b) + corr(d_{b+1},u_{b+1}) + i (cross terms); the cross terms are purely imaginary in the time
+// domain, and the caller takes the real part of the inverse FFT (as the reference does, conv.py:1817-1820),
+// so summing the packed products over pairs gives exactly dk.  An odd batch is completed with an all-zero
+// partner (TMA out-of-bounds fill).
+//
+// Machine mapping (warp-specialised, software-pipelined): a strictly serial stage 1 -> pass 1 -> stage 2 -> accumulate
+// chain per pair leaves the tensor pipe idle during the passes and the CUDA cores during the MMAs (measured on the
+// first version of this kernel: tensor pipe 31 % active, 8.6 k cycles per pair against 3.1 k of MMA work).  Here
+//  * the stage-2 A operands live in shared memory (as in fwd3_r128.cuh), which leaves TMEM room for a THIRD 128-column
 //    accumulator: u and dout of pair n use buffers (2n) % 3 and (2n + 1) % 3, so stage 1 of u(n+1) runs while pair n is
 //    still being accumulated and stage 1 of dout(n+1) while pass 1 of u(n+1) runs;
 //  * a fifth warpgroup holds the ISSUER warp (TMA loads and every MMA, in program order).  A tcgen05.mma blocks its
 //    thread while the tensor pipe's short queue is full, i.e. for most of a stage; an issuer that also had a share of
-//    the passes would stall the other 15 warps at the next hand-over for exactly that long (measured: no gain from the
-//    third accumulator alone).  Registers move from the issuer warpgroup to the four compute warpgroups (setmaxnreg);
+//    the passes would stall the other 15 warps at the next hand-over for exactly that long;
 //  * hand-overs are mbarriers only: tcgen05.commit -> compute warps, one arrive per compute warp -> issuer.  The
 //    compute warps never wait for each other.
 // Input slots are released as soon as stage 1 has consumed them (A tiles have their own buffers), so the TMA loads run
-// two pairs ahead.
+// two pairs ahead.  Gated backward: the caller hands in u*pregate and dout*postgate (composite sizes: the outer stage
+// applies the gates on load; seqlen <= 8192: an elementwise pre-pass, see bffc_bwd).
 //
 //   tensor pipe:  S1d(n) | S2u(n) | S2d(n) | S1u(n+1) | S1d(n+1) | ...
 //   CUDA cores :  acc(n-1) | pass1 u(n) | pass1 d(n) | acc(n) | pass1 u(n+1) | ...
 #pragma once
-#include "dkf_r128.cuh"
 #include "fwd3_r128.cuh"
 
 namespace bffc {
+
+struct DkfParams {
+  const __nv_bfloat16* dftC;
+  const __nv_bfloat16* dftS;
+  const uint8_t* gtiles;
+  float2* dkf;               // [H][4][128][16] complex fp32: k2 = 16*q + t, frequency k = k1 + 128*k2
+  int B, H, L, pairs, kmask;  // pairs = batch groups per channel; kmask as in FwdParams
+  int nseg, seg_bytes;        // segmented tiles (small sizes), see load_tile()
+  float tw_scale;            // see FwdParams::tw_scale; dkf_unpack compensates
+};
+
 namespace r128 {
 
 constexpr int kSmemDkf3Slots = 4 * kSlotBytes;                 // u slot 0/1, dout slot 0/1
@@ -76,12 +99,17 @@ dkf3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + kSmemDkf3Slots + kSmemDkf3A + kSmemG + 64);
   const uint32_t tlane = tmem_base + (uint32_t(warp_q * 32) << 16);
 
-  // pairs of this CTA: (h, pr) for h = blockIdx.x, blockIdx.x + gridDim.x, ...
-  const int nh = (p.H - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
-  const int n_units = nh * p.pairs;
-  auto unit_h = [&](int n) { return int(blockIdx.x) + (n / p.pairs) * int(gridDim.x); };
+  // work split: the H * pairs units (channel-major: g = h * pairs + pr) are cut into gridDim.x contiguous ranges, so the
+  // grid is not limited by the channel count (H = 64 still fills 148 SMs) and no CTA carries a whole extra channel
+  // (768 channels on 148 CTAs used to be 6 vs 5).  A channel that straddles two CTAs is completed by both through
+  // fp32 reductions into the zero-initialised gradient (red.global.add), as is every other flush.
+  const long long total = (long long)p.H * p.pairs;
+  const int g_begin = int(total * blockIdx.x / gridDim.x), g_end = int(total * (blockIdx.x + 1) / gridDim.x);
+  const int n_units = g_end - g_begin;
+  auto unit_h = [&](int n) { return (g_begin + n) / p.pairs; };
+  auto unit_pr = [&](int n) { return (g_begin + n) % p.pairs; };
   auto issue_load = [&](int n, int which) {          // which: 0 = u pair, 1 = dout pair; slot = n & 1
-    const int h = unit_h(n), pr = n % p.pairs, slot = n & 1;
+    const int h = unit_h(n), pr = unit_pr(n), slot = n & 1;
     const uint32_t bar = (which ? bar_tma_d : bar_tma_u) + 8 * slot;
     const uint32_t dst = sbase + (2 * which + slot) * kSlotBytes;
     const CUtensorMap* tm = which ? &tm_d : &tm_u;
@@ -297,16 +325,16 @@ dkf3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
       }
     }
     hand_over(bar_acc);    // both accumulators of pair n are free again (dout(n+1) and u(n+2) will overwrite them)
-    // ---- channel finished: write its gradient spectrum
-    if ((n + 1) % p.pairs == 0) {
+    // ---- channel (or this CTA's share of it) finished: add it to the gradient spectrum
+    if (unit_pr(n) == p.pairs - 1 || n == n_units - 1) {
       const int h = unit_h(n);
-      float4* out = reinterpret_cast<float4*>(p.dkf + ((size_t(h) * 4 + wg) * 128 + lane) * 16);
+      float* out = reinterpret_cast<float*>(p.dkf + ((size_t(h) * 4 + wg) * 128 + lane) * 16);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         float r0, r1, i0, i1;
         upk2(acc_r[q], r0, r1);
         upk2(acc_i[q], i0, i1);
-        out[q] = make_float4(r0, i0, r1, i1);
+        red_add_v4(out + 4 * q, r0, i0, r1, i1);
         acc_r[q] = 0ull; acc_i[q] = 0ull;
       }
     }
@@ -316,6 +344,31 @@ dkf3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   tc_fence_before();
   named_bar_sync(1, 512);
   if (tid < 32) tmem_dealloc(tmem_base, 512);
+}
+
+// dk_f engine order -> natural order complex64 (reference analogue: the inverse permutation at conv.py:1818).
+// Composite sizes: channel row (h*R0 + c0)*R1 + c1 holds frequencies k = c0 + R0*(c1 + R1*(k1 + 128*k2)).
+// One thread moves the 16 consecutive-k2 values of one (row, quarter, k1): 128 contiguous bytes in, 16 stores that are
+// contiguous across the k1 lanes of a warp.
+__global__ void dkf_unpack_kernel(const float2* __restrict__ eng, float2* __restrict__ nat, int N, int R0, int R1,
+                                  float scale) {
+  const int h = blockIdx.y;
+  const int R = R0 * R1;
+  const int ngroups = R * 4 * 128;                      // (row, quarter, k1) groups per channel
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gridDim.x * blockDim.x) {
+    const int k1 = g & 127, qd = (g >> 7) & 3, row = g >> 9;
+    const int c0 = row / R1, c1 = row % R1;
+    const float4* in = reinterpret_cast<const float4*>(eng + ((size_t(h) * R + row) * 4 + qd) * 128 * 16 + size_t(k1) * 16);
+#pragma unroll
+    for (int t2 = 0; t2 < 8; ++t2) {
+      const float4 v = in[t2];
+      const int k2 = 16 * qd + 2 * t2;
+      const size_t ka = size_t(c0) + size_t(R0) * (c1 + size_t(R1) * (k1 + 128 * k2));
+      const size_t kb = size_t(c0) + size_t(R0) * (c1 + size_t(R1) * (k1 + 128 * (k2 + 1)));
+      nat[size_t(h) * N + ka] = make_float2(v.x * scale, v.y * scale);
+      nat[size_t(h) * N + kb] = make_float2(v.z * scale, v.w * scale);
+    }
+  }
 }
 
 }  // namespace r128

@@ -152,11 +152,15 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   const uint32_t sG0 = s_g;
   const f32x2 kfs2 = pk2(p.kf_scale, p.kf_scale);
 
+#ifdef BFFC_BRINGUP
   // bring-up timeline (tools/trace_fwd3.py): lane 0 of warp 0 and of warp 3 of every pipeline of CTA 0
   const bool tracing = p.trace != nullptr && blockIdx.x == 0 && (tid & 31) == 0 && (warp_q == 0 || warp_q == 3);
   long long* trace_base = p.trace + (size_t(pipe) * 2 + (warp_q == 3)) * 64 * 16;
   int trace_n = 0;
   auto stamp = [&](int ev) { if (tracing && trace_n < 64) trace_base[trace_n * 16 + ev] = clock64(); };
+#else
+  auto stamp = [](int) {};
+#endif
   uint32_t mma_phase = 0;
   auto wait_mma = [&]() {
     mbar_wait(bar_mma, mma_phase);
@@ -291,7 +295,7 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint4 kq = kfa[2 * s4 + (q >> 1)];
-          const uint32_t wr = (q & 1) ? kq.z : kq.x, wi = (q & 1) ? kq.w : kq.y;
+          const uint32_t wr = (q & 1) ? kq.z : kq.x, wi = ((q & 1) ? kq.w : kq.y) ^ p.kf_conj_mask;
           f32x2 kr2 = NT::unpack(wr), ki2 = NT::unpack(wi);
           if (kFmt == 0) { kr2 = mul2(kr2, kfs2); ki2 = mul2(ki2, kfs2); }
           f32x2 vr, vi;
@@ -408,7 +412,9 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
       __syncwarp();
     }
     stamp(15);
+#ifdef BFFC_BRINGUP
     ++trace_n;
+#endif
   }
 
   if (lead_warp) tma_store_wait_all0();

@@ -36,6 +36,8 @@ struct FwdParams {
   float tw_scale;            // folded into the twiddle table (fp16: 1/sqrt(128) keeps every stage near the input level)
   const uint32_t* pregate;   // optional (B,H,L) bf16, or null
   const uint32_t* postgate;
+  const uint32_t* postgate2; // optional second output gate: y2 = postgate2 * conv(...)  (gated backward: du and dpregate
+  uint32_t* y2;              //   come from ONE pass, reference kernels_bf16/monarch_cuda_32_16_16_bwd_kernel_bf16.h:836-870)
   int B, H, L;               // batch, channels, sequence length
   int pairs;                 // ceil(B/2)
   int kmask;                 // bit s set: 16-row K step s of the input tile can be non-zero (the rest is skipped)
@@ -43,9 +45,10 @@ struct FwdParams {
   int seg_bytes;             // bytes of one segment inside a tile = (128 / nseg) rows x 128 B
   int small_out;             // 1: store the full tiles to the fold scratch, row = 2*unit + which
   int units;                 // H * pairs
+  uint32_t kf_conj_mask;     // 0x80008000: multiply by conj(k_f) (du path of the backward: correlation), else 0
   float* dbg;                // optional stage dump [stage][128][128]
   int dbg_stages;
-  long long* trace;          // bring-up only (env BFFC_TRACE): clock64 stamps of CTA 0, [pipe][warp 0|3][unit][16]
+  long long* trace;          // bring-up builds only (-DBFFC_BRINGUP): clock64 stamps of CTA 0, [pipe][warp 0|3][unit][16]
 };
 
 namespace r128 {
@@ -385,7 +388,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const uint4 kq = kfv[4 * sub + (q >> 1)];
-        const uint32_t wr = (q & 1) ? kq.z : kq.x, wi = (q & 1) ? kq.w : kq.y;
+        const uint32_t wr = (q & 1) ? kq.z : kq.x, wi = ((q & 1) ? kq.w : kq.y) ^ p.kf_conj_mask;
         f32x2 vr, vi;
         f32x2 kr2 = NT::unpack(wr), ki2 = NT::unpack(wi);
         if (kFmt == 0) { kr2 = mul2(kr2, kfs2); ki2 = mul2(ki2, kfs2); }
@@ -490,6 +493,16 @@ fwd_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUt
           uint32_t o1 = NT::pack(__uint_as_float(v[8 * cc + 2]), __uint_as_float(v[8 * cc + 3]));
           uint32_t o2 = NT::pack(__uint_as_float(v[8 * cc + 4]), __uint_as_float(v[8 * cc + 5]));
           uint32_t o3 = NT::pack(__uint_as_float(v[8 * cc + 6]), __uint_as_float(v[8 * cc + 7]));
+          if (kGated && p.y2 != nullptr) {
+            // second gated output straight from registers: this thread owns 64 contiguous bytes of row `lane`
+            const int pb = 2 * (unit - h * p.pairs) + part;
+            if (pb < p.B && lane * 64 < p.L) {
+              const size_t w = (size_t(pb) * p.H + h) * p.L / 2 + lane * 32 + 16 * half + 4 * (2 * sub + cc);
+              const uint4 g2 = __ldg(reinterpret_cast<const uint4*>(p.postgate2 + w));
+              *reinterpret_cast<uint4*>(p.y2 + w) =
+                  make_uint4(NT::hmul2(o0, g2.x), NT::hmul2(o1, g2.y), NT::hmul2(o2, g2.z), NT::hmul2(o3, g2.w));
+            }
+          }
           if (has_post) {
             const uint4 g = pg[part][2 * sub + cc];
             o0 = NT::hmul2(o0, g.x); o1 = NT::hmul2(o1, g.y); o2 = NT::hmul2(o2, g.z); o3 = NT::hmul2(o3, g.w);

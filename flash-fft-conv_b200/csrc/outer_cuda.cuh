@@ -40,6 +40,8 @@ struct OuterParams {
   const uint4* pregate;  // optional
   const uint4* postgate; // optional
   uint4* y;              // (B, H, L) bf16 (inverse only)
+  const uint4* postgate2; // optional second gated output of the inverse: y2 = postgate2 * z' (gated backward: du, dpregate)
+  uint4* y2;
   uint4* xre;            // kPlanes: outer-side complex rows (rows x R*M), read by fwd / written by inv
   uint4* xim;
   uint4* pre;            // inner-side planes: real parts,  rows*R rows of M bf16 each
@@ -291,11 +293,13 @@ __global__ void __launch_bounds__(128, (R <= 4) ? 4 : 2) inv_kernel(const OuterP
       }
       const size_t o0 = (size_t(b0) * p.H + h) * L8 + n / kVec;
       uint4 v0 = pack8v<kFmt>(yr);
+      if (kGated && p.y2) p.y2[o0] = hmul8<kFmt>(v0, __ldg(p.postgate2 + o0));
       if (kGated) v0 = hmul8<kFmt>(v0, __ldg(p.postgate + o0));
       p.y[o0] = v0;
       if (b1 < p.B) {
         const size_t o1 = (size_t(b1) * p.H + h) * L8 + n / kVec;
         uint4 v1 = pack8v<kFmt>(yi);
+        if (kGated && p.y2) p.y2[o1] = hmul8<kFmt>(v1, __ldg(p.postgate2 + o1));
         if (kGated) v1 = hmul8<kFmt>(v1, __ldg(p.postgate + o1));
         p.y[o1] = v1;
       }

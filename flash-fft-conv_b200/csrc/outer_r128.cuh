@@ -22,6 +22,8 @@ struct OuterTcParams {
   const __nv_bfloat16* dftC;
   const __nv_bfloat16* dftS;
   const uint32_t* postgate;   // inverse only, (B,H,L) bf16 or null
+  const uint32_t* postgate2;  // inverse only: optional second gated output y2 = postgate2 * z' (gated backward)
+  uint32_t* y2;
   int has_pregate;            // forward only: tm_g is the pregate map
   float tw_scale;             // folded into the twiddle table (fp16: 1/sqrt(128))
   int B, H, L, pairs;
@@ -296,6 +298,20 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
         const uint32_t off = uint32_t(lane) * 128u + (uint32_t(chunk ^ (lane & 7)) << 4);
         uint32_t a0 = ore[4 * cc], a1 = ore[4 * cc + 1], a2 = ore[4 * cc + 2], a3 = ore[4 * cc + 3];
         uint32_t b0 = oim[4 * cc], b1 = oim[4 * cc + 1], b2 = oim[4 * cc + 2], b3 = oim[4 * cc + 3];
+        if (kInverse && p.y2 != nullptr && (long long)lane * p.M < p.L) {
+          // second gated output straight from registers (this thread owns 64 contiguous bytes of row `lane`)
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+            const int b = 2 * x.pr + part;
+            if (b < p.B) {
+              const size_t e0 = (size_t(b) * p.H + x.h) * p.L + size_t(lane) * p.M + x.cj * 64 + 32 * half + 8 * (2 * sub + cc);
+              const uint4 g2 = __ldg(reinterpret_cast<const uint4*>(p.postgate2 + e0 / 2));
+              const uint32_t v0 = part ? b0 : a0, v1 = part ? b1 : a1, v2 = part ? b2 : a2, v3 = part ? b3 : a3;
+              *reinterpret_cast<uint4*>(p.y2 + e0 / 2) =
+                  make_uint4(NT::hmul2(v0, g2.x), NT::hmul2(v1, g2.y), NT::hmul2(v2, g2.z), NT::hmul2(v3, g2.w));
+            }
+          }
+        }
         if (has_post) {
           const uint4 g0 = pg[0][2 * sub + cc], g1 = pg[1][2 * sub + cc];
           a0 = NT::hmul2(a0, g0.x); a1 = NT::hmul2(a1, g0.y); a2 = NT::hmul2(a2, g0.z); a3 = NT::hmul2(a3, g0.w);

@@ -28,6 +28,7 @@ SYMBOLS = {
     'bffc_kf_from_filter': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p]),
     'bffc_dk_from_dkf': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p]),
     'bffc_workspace_bytes': (_c.c_size_t, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int]),
+    'bffc_workspace_bytes_ex': (_c.c_size_t, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     'bffc_fwd': (_c.c_int, [_c.c_void_p] * 6 + [_c.c_int] * 3 + [_c.c_void_p, _c.c_size_t, _c.c_void_p]),
     'bffc_bwd': (_c.c_int, [_c.c_void_p] * 11 + [_c.c_int] * 3 + [_c.c_void_p, _c.c_size_t, _c.c_void_p]),
     'bffc_host_chunk_batch': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int]),

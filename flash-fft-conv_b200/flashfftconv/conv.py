@@ -8,11 +8,16 @@ Drop-in for `flashfftconv.FlashFFTConv` (reference flashfftconv/conv.py:71-560):
 All arithmetic on the hot path happens in libbffc.so (hand-written sm_100a CUDA, C ABI in
 include/bffc.h).  PyTorch is used for device memory and streams.  For seqlen <= 8192 the filter-side
 transforms (k -> k_f, dk_f -> dk) are library launches too (bffc_kf_from_filter / bffc_dk_from_dkf);
-for longer sequences they still go through torch.fft in fp32 exactly as the reference does at
+for longer sequences they go through torch.fft in fp32 exactly as the reference does at
 conv.py:575 and :1817, followed by the library's pack / unpack kernels.
+
+The filter spectrum in engine order is what forward keeps for backward (the reference keeps its permuted
+k_f, conv.py:587-588), so a training step transforms the filter once; in eval mode it is additionally cached
+across calls for as long as the SAME tensor object `k` is unmodified (identity + `_version`), which is the
+inference situation of the reference's examples (one fixed filter, many inputs).
 """
 import ctypes
-import os
+import weakref
 
 import torch
 
@@ -55,8 +60,41 @@ class FlashFFTConv(torch.nn.Module):
         self.use_32_butterfly = use_32_butterfly                     # accepted for API parity; no effect here
         if not _lib.lib().bffc_supported(self.seqlen, _DT[dtype]):
             raise NotImplementedError(f'seqlen {seqlen} not supported')   # conv.py:550-551
+        self._reset_runtime_state()
+
+    # ---- runtime state (native handles, device scratch, caches) is per process and rebuilt lazily: it must not
+    # ---- travel through copy.deepcopy / pickle / torch.save(model) (ctypes pointers cannot be pickled, and two copies
+    # ---- of a plan handle would be destroyed twice)
+    def _reset_runtime_state(self):
         self._plans = {}
         self._host_ws = {}
+        self._kf_cache = None          # (weakref(k), k._version, device, kf_engine)
+        self.last_launches = 0         # kernels enqueued by the most recent forward / backward (bench.py)
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for key in ('_plans', '_host_ws', '_kf_cache'):
+            state.pop(key, None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._reset_runtime_state()
+
+    def __deepcopy__(self, memo):
+        new = type(self)(self.seqlen, self.dtype, self.use_32_butterfly)
+        new.train(self.training)
+        memo[id(self)] = new
+        return new
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # The reference module registers its DFT / twiddle tables as persistent buffers (conv.py:89-92 and every size
+        # branch), so its checkpoints carry `<prefix>f_32_fft`, `<prefix>twiddle_factors_fft_16_16`, ...  This module
+        # owns no tensors (the tables live in the native plan): accept and drop those entries so that
+        # load_state_dict(strict=True) of a reference checkpoint succeeds.
+        for key in [k for k in state_dict if k.startswith(prefix)]:
+            del state_dict[key]
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
     def plan(self, device):
         key = (device.type, device.index)
@@ -104,14 +142,18 @@ def _forward_host(mod, u, k, pregate, postgate, out, device):
         raise RuntimeError('forward_host: out must be a contiguous host tensor like u')
     plan = mod.plan(device)
     with torch.cuda.device(device):
-        kf_engine = _pack_kf(mod, plan, k.to(device, non_blocking=True), 0)
+        kf_engine = _kf_engine_for(mod, plan, k if k.is_cuda else k.to(device, non_blocking=True), cache_key=k)
         nws = _lib.lib().bffc_host_workspace_bytes(plan.handle, B, H, L, 1 if gates else 0)
         ws = mod._host_ws.get((device, nws))
         if ws is None:
             mod._host_ws.clear()
             ws = mod._host_ws[(device, nws)] = torch.empty(nws, dtype=torch.uint8, device=device)
-        _lib.check(_lib.lib().bffc_fwd_host(plan.handle, _ptr(u), _ptr(kf_engine), _ptr(pregate), _ptr(postgate),
-                                            _ptr(out), B, H, L, _ptr(ws), nws, _stream()))
+        rc = _lib.lib().bffc_fwd_host(plan.handle, _ptr(u), _ptr(kf_engine), _ptr(pregate), _ptr(postgate),
+                                      _ptr(out), B, H, L, _ptr(ws), nws, _stream())
+        if rc:
+            torch.cuda.synchronize(device)     # nothing may still be copying into / out of buffers we are about to drop
+            _lib.check(rc)
+        mod.last_launches = 1 + _lib.lib().bffc_last_launch_count()
         # the library joins its internal streams back into the current stream before returning, so the caching
         # allocator (stream-ordered on the current stream) may recycle kf_engine / ws after this point
     return out
@@ -149,27 +191,32 @@ def _pack_kf_from_natural(mod, plan, k_f, conj):
     return kf_engine
 
 
-def _filter_state(mod, k):
-    """What forward keeps of the filter for backward.  Engine FFT size 8192 (seqlen <= 8192): the fp32 filter itself —
-    its spectrum is produced in engine order by ONE launch of the library (bffc_kf_from_filter) whenever needed.
-    Larger sizes: the rfft of the filter, as the reference keeps k_f (conv.py:575, :588)."""
-    if mod.fft_size(k.device) == 8192 and os.environ.get('BFFC_FILTER_FFT', '1') != '0':   # '0': A/B against cuFFT + pack
-        return k.detach().to(torch.float32).contiguous()
-    return _kf_natural(mod, k)
+def _pack_kf(mod, plan, k, conj=0):
+    """k (H, Lk) fp32 device -> engine-order packed spectrum (H, N) int32 words.  Engine FFT size 8192 (seqlen <= 8192):
+    ONE launch of the library's own fp32 FFT (bffc_kf_from_filter); larger sizes: fp32 rfft as the reference
+    (conv.py:575) + the library's pack kernel."""
+    if mod.fft_size(k.device) == 8192:
+        k32 = k.detach().to(torch.float32).contiguous()
+        H, Lk = k32.shape
+        kf_engine = torch.empty((H, 8192), dtype=torch.int32, device=k.device)
+        _lib.check(_lib.lib().bffc_kf_from_filter(plan.handle, _ptr(k32), int(Lk), _ptr(kf_engine), int(H), int(conj),
+                                                  _stream()))
+        return kf_engine
+    return _pack_kf_from_natural(mod, plan, _kf_natural(mod, k.detach()), conj)
 
 
-def _kf_engine(mod, plan, state, conj):
-    """engine-order packed k_f (H, N) from _filter_state()."""
-    if state.is_complex():
-        return _pack_kf_from_natural(mod, plan, state, conj)
-    H, Lk = state.shape
-    kf_engine = torch.empty((H, 8192), dtype=torch.int32, device=state.device)
-    _lib.check(_lib.lib().bffc_kf_from_filter(plan.handle, _ptr(state), int(Lk), _ptr(kf_engine), int(H), int(conj), _stream()))
-    return kf_engine
-
-
-def _pack_kf(mod, plan, k, conj):
-    return _kf_engine(mod, plan, _filter_state(mod, k), conj)
+def _kf_engine_for(mod, plan, k, cache_key=None):
+    """Engine-order spectrum of `k`, cached in eval mode while the same tensor object is unmodified."""
+    key = k if cache_key is None else cache_key
+    use_cache = not mod.training
+    if use_cache and mod._kf_cache is not None:
+        ref, ver, dev, kf = mod._kf_cache
+        if ref() is key and ver == key._version and dev == k.device:
+            return kf
+    kf = _pack_kf(mod, plan, k)
+    mod.last_launches = 1 if mod.fft_size(k.device) == 8192 else 2      # our kernels only (cuFFT launches not counted)
+    mod._kf_cache = (weakref.ref(key), key._version, k.device, kf) if use_cache else None
+    return kf
 
 
 def _pad_len(mod, device, L):
@@ -187,31 +234,36 @@ def _padded(t, Lp):
     return out
 
 
+def _workspace(plan, B, H, L, gated, backward, device):
+    n = _lib.lib().bffc_workspace_bytes_ex(plan.handle, B, H, L, int(gated), int(backward))
+    return (torch.empty(n, dtype=torch.uint8, device=device) if n else None), n
+
+
 def _fwd(mod, u, k, pregate, postgate):
     L0 = u.shape[-1]
     Lp = _pad_len(mod, u.device, L0)
     if Lp != L0:
-        y, k_f = _fwd(mod, _padded(u, Lp), k, _padded(pregate, Lp), _padded(postgate, Lp))
-        return y[..., :L0].contiguous(), k_f
+        y, kf = _fwd(mod, _padded(u, Lp), k, _padded(pregate, Lp), _padded(postgate, Lp))
+        return y[..., :L0].contiguous(), kf
     B, H, L = u.shape
     plan = mod.plan(u.device)
     with torch.cuda.device(u.device):
-        k_f = _filter_state(mod, k)
-        kf_engine = _kf_engine(mod, plan, k_f, conj=0)
+        mod.last_launches = 0
+        kf_engine = _kf_engine_for(mod, plan, k)
         y = torch.empty_like(u)
-        ws_bytes = _lib.lib().bffc_workspace_bytes(plan.handle, B, H, L)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=u.device) if ws_bytes else None
+        ws, ws_bytes = _workspace(plan, B, H, L, pregate is not None, False, u.device)
         _lib.check(_lib.lib().bffc_fwd(plan.handle, _ptr(u), _ptr(kf_engine), _ptr(pregate), _ptr(postgate),
                                        _ptr(y), B, H, L, _ptr(ws), ws_bytes, _stream()))
-    return y, k_f
+        mod.last_launches += _lib.lib().bffc_last_launch_count()
+    return y, kf_engine
 
 
-def _bwd(mod, dout, u, k_f, k_len, pregate, postgate):
+def _bwd(mod, dout, u, kf_engine, k_len, pregate, postgate):
     """du, dk[, dpregate, dpostgate] — reference: FlashFFTConvFunc.backward, conv.py:1737-1822."""
     L0 = u.shape[-1]
     Lp = _pad_len(mod, u.device, L0)
     if Lp != L0:
-        r = _bwd(mod, _padded(dout, Lp), _padded(u, Lp), k_f, k_len, _padded(pregate, Lp), _padded(postgate, Lp))
+        r = _bwd(mod, _padded(dout, Lp), _padded(u, Lp), kf_engine, k_len, _padded(pregate, Lp), _padded(postgate, Lp))
         cut = lambda t: None if t is None else t[..., :L0].contiguous()
         return cut(r[0]), r[1], cut(r[2]), cut(r[3])
     B, H, L = u.shape
@@ -219,18 +271,17 @@ def _bwd(mod, dout, u, k_f, k_len, pregate, postgate):
     plan = mod.plan(u.device)
     dout = dout.contiguous()                                          # conv.py:1742
     with torch.cuda.device(u.device):
-        kf_conj = _kf_engine(mod, plan, k_f, conj=1)
-        kf_eng = _kf_engine(mod, plan, k_f, conj=0) if pregate is not None else None
         du = torch.empty_like(u)
         dkf_engine = torch.empty((H, N, 2), dtype=torch.float32, device=u.device)
         dpre = torch.empty_like(u) if pregate is not None else None
         dpost = torch.empty_like(u) if pregate is not None else None
-        ws_bytes = _lib.lib().bffc_workspace_bytes(plan.handle, B, H, L)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=u.device) if ws_bytes else None
-        _lib.check(_lib.lib().bffc_bwd(plan.handle, _ptr(dout), _ptr(u), _ptr(kf_eng), _ptr(kf_conj), _ptr(pregate),
+        ws, ws_bytes = _workspace(plan, B, H, L, pregate is not None, True, u.device)
+        # kf_engine_conj = NULL: the kernels conjugate the forward's spectrum in their pointwise multiply
+        _lib.check(_lib.lib().bffc_bwd(plan.handle, _ptr(dout), _ptr(u), _ptr(kf_engine), None, _ptr(pregate),
                                        _ptr(postgate), _ptr(du), _ptr(dkf_engine), _ptr(dpre), _ptr(dpost),
                                        B, H, L, _ptr(ws), ws_bytes, _stream()))
-        if N == 8192 and not k_f.is_complex():
+        mod.last_launches = _lib.lib().bffc_last_launch_count() + 1
+        if N == 8192:
             # one launch: inverse fp32 FFT straight from engine order, 1/N, real part, fold of the small sizes, [:k_len]
             dk = torch.empty((H, k_len), dtype=torch.float32, device=u.device)
             _lib.check(_lib.lib().bffc_dk_from_dkf(plan.handle, _ptr(dkf_engine), _ptr(dk), int(k_len), H, _stream()))
@@ -238,11 +289,10 @@ def _bwd(mod, dout, u, k_f, k_len, pregate, postgate):
         dkf_nat = torch.empty((H, N), dtype=torch.complex64, device=u.device)
         _lib.check(_lib.lib().bffc_dkf_unpack(plan.handle, _ptr(dkf_engine), _ptr(torch.view_as_real(dkf_nat)), H,
                                               _stream()))
-        # the kernel accumulates unnormalised spectra; ifft's 1/N completes the correlation (conv.py:1817-1820)
-        c = torch.fft.ifft(dkf_nat, dim=-1).real
-        if N != mod.seqlen:        # small sizes: fold the linear correlation (lags -seqlen..seqlen) modulo seqlen
-            c = c[..., : mod.seqlen] + c[..., N - mod.seqlen:]
-        dk = c[..., :k_len].contiguous()
+        # the kernel accumulates unnormalised spectra; the inverse FFT's 1/N completes the correlation
+        # (conv.py:1817-1820).  dk is real: a Hermitian inverse (irfft of the first N/2+1 bins) gives the same real part
+        # as ifft(...).real when dk_f is Hermitian, which it is up to the cross terms the .real discards — so keep ifft.
+        dk = torch.fft.ifft(dkf_nat, dim=-1).real[..., :k_len].contiguous()
     return du, dk, dpre, dpost
 
 
@@ -250,17 +300,17 @@ class FlashFFTConvFunc(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, k, mod):
         _check_inputs(u, k, mod)
-        y, k_f = _fwd(mod, u, k, None, None)
+        y, kf_engine = _fwd(mod, u, k, None, None)
         ctx.mod = mod
         ctx.k_len = k.shape[-1]
         if mod.training:                                              # conv.py:587-588
-            ctx.save_for_backward(u, k_f)
+            ctx.save_for_backward(u, kf_engine)
         return y
 
     @staticmethod
     def backward(ctx, dout):
-        u, k_f = ctx.saved_tensors
-        du, dk, _, _ = _bwd(ctx.mod, dout, u, k_f, ctx.k_len, None, None)
+        u, kf_engine = ctx.saved_tensors
+        du, dk, _, _ = _bwd(ctx.mod, dout, u, kf_engine, ctx.k_len, None, None)
         return du, dk, None                                           # conv.py:1822
 
 
@@ -268,15 +318,15 @@ class GatedFlashFFTConvFunc(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, k, mod, pregate, postgate):
         _check_inputs(u, k, mod, (pregate, postgate))
-        y, k_f = _fwd(mod, u, k, pregate, postgate)
+        y, kf_engine = _fwd(mod, u, k, pregate, postgate)
         ctx.mod = mod
         ctx.k_len = k.shape[-1]
         if mod.training:
-            ctx.save_for_backward(u, k_f, pregate, postgate)
+            ctx.save_for_backward(u, kf_engine, pregate, postgate)
         return y
 
     @staticmethod
     def backward(ctx, dout):
-        u, k_f, pregate, postgate = ctx.saved_tensors
-        du, dk, dpre, dpost = _bwd(ctx.mod, dout, u, k_f, ctx.k_len, pregate, postgate)
+        u, kf_engine, pregate, postgate = ctx.saved_tensors
+        du, dk, dpre, dpost = _bwd(ctx.mod, dout, u, kf_engine, ctx.k_len, pregate, postgate)
         return du, dk, None, dpre, dpost                              # conv.py:3939

@@ -5,6 +5,8 @@ collective in forward or backward: each rank owns a contiguous block of channels
 produces the same block of y / du / dk.  The only communication is harness-side: gathering the blocks for a
 parity check (torch.distributed all_gather over NCCL / NVLink on GPUs, gloo in the CPU tests).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -46,3 +48,40 @@ def sharded_conv(conv_fn, u, k, group=None, gates=()):
     parts = shard(u, k, world, rank, *gates)
     y_local = conv_fn(*parts)
     return gather_channels(y_local, u.shape[1], group)
+
+
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(','):
+        if '-' in part:
+            a, b = part.split('-')
+            cpus.update(range(int(a), int(b) + 1))
+        elif part:
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Bind this process's CPU affinity to the cores of the NUMA node the GPU hangs off (sysfs: the PCI device's
+    `numa_node`, then /sys/devices/system/node/nodeN/cpulist).  Host staging buffers allocated and first touched after
+    this call (pinned memory for forward_host) then live on that node, so H2D / D2H copies of the ranks of one box do
+    not all cross the inter-socket link.  One process per GPU (torchrun) is the assumed launch.  Returns a description."""
+    import torch.cuda
+    bus = torch.cuda.get_device_properties(device_index)
+    pci = f'{bus.pci_domain_id:04x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0'
+    node = int(open(f'/sys/bus/pci/devices/{pci}/numa_node').read())
+    if node < 0:
+        return f'gpu {device_index} ({pci}): no NUMA affinity reported'
+    cpus = _cpulist(open(f'/sys/devices/system/node/node{node}/cpulist').read())
+    allowed = os.sched_getaffinity(0) & cpus
+    if not allowed:
+        return f'gpu {device_index} ({pci}): node {node} has no allowed cpus'
+    os.sched_setaffinity(0, allowed)
+    try:            # prefer the node for new pages too (a no-op where set_mempolicy is not permitted)
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))      # set_mempolicy(MPOL_PREFERRED) on x86-64
+    except Exception:
+        pass
+    return f'gpu {device_index} ({pci}): bound to NUMA node {node}, {len(allowed)} cpus'

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BFFC_ABI_VERSION 1
+#define BFFC_ABI_VERSION 2
 
 /* element types of u / y / gates */
 #define BFFC_DTYPE_BF16 0
@@ -46,7 +46,10 @@ extern "C" {
 #define BFFC_ERR_NO_DEVICE 3   /* no CUDA device, or device is not sm_100            */
 #define BFFC_ERR_CUDA 4        /* a CUDA runtime / driver call or a launch failed    */
 
-typedef struct bffc_plan bffc_plan; /* opaque; immutable after creation; thread-safe to share */
+/* Opaque.  The tables are immutable after creation and bffc_fwd / bffc_bwd / the filter-side entry points may be called
+ * concurrently on one plan from several threads and streams.  bffc_fwd_host uses streams, events and a staging order that
+ * belong to the plan: calls to it on the same plan must be serialised by the caller. */
+typedef struct bffc_plan bffc_plan;
 
 int bffc_abi_version(void);
 const char* bffc_last_error(void);
@@ -64,7 +67,11 @@ int bffc_plan_destroy(bffc_plan* plan);
 /* FFT size n the caller must use for k_f = rfft(k, n) / for the inverse FFT of dk_f: seqlen for seqlen >= 8192;
  * 8192 for the small sizes (256..4096), whose dk then is dk[i] = c[i] + c[8192 - seqlen + i], c = ifft(dk_f).real */
 int bffc_fft_size(const bffc_plan* plan);
-/* L passed to bffc_fwd / bffc_bwd must be a multiple of this (the host mirror zero-pads other lengths). */
+/* L passed to bffc_fwd / bffc_bwd / bffc_fwd_host must be a multiple of this: 64 for seqlen <= 8192 (TMA tiles of 64
+ * columns), 8 for 16K..512K (16-byte vectors of the CUDA-core outer stage), seqlen/128 for 1M / 2M / 4M (whole rows of the
+ * [128][seqlen/128] view of the tcgen05 outer stage).  Other lengths return BFFC_ERR_UNSUPPORTED; a caller holding such a
+ * tensor zero-pads it to the next multiple (the operator is unchanged: implicit zero padding), as the host mirror does.
+ * The reference itself only requires L even (README.md:270). */
 int bffc_length_multiple(const bffc_plan* plan);
 
 /*
@@ -100,12 +107,16 @@ int bffc_kf_from_filter(const bffc_plan* plan, const void* k, int Lk, void* kf_e
 int bffc_dk_from_dkf(const bffc_plan* plan, const void* dkf_engine, void* dk, int Lk, int H,
                      void* stream);
 
-/* Scratch the caller must provide to bffc_fwd / bffc_bwd (0 for fully fused sizes). */
+/* Scratch the caller must provide.  bffc_workspace_bytes_ex: exact need of bffc_fwd (backward = 0) or bffc_bwd
+ * (backward = 1) for a gated / ungated call (0 for the fully fused ungated sizes); bffc_workspace_bytes: enough for any
+ * call with these shapes.  Composite sizes hold the outer stages' output as 16-bit plane pairs of ceil(B/2)*H*N elements:
+ * forward nlev pairs, backward nlev + 1 (nlev = 1 for 16K..64K and 1M, 2 for 128K..512K, 2M, 4M). */
 size_t bffc_workspace_bytes(const bffc_plan* plan, int B, int H, int L);
+size_t bffc_workspace_bytes_ex(const bffc_plan* plan, int B, int H, int L, int gated, int backward);
 
 /*
- * Forward.  u, y, pregate, postgate: (B, H, L) contiguous, plan dtype, L <= N, L even.
- * kf_engine: from bffc_kf_pack.  pregate/postgate: both NULL or both non-NULL
+ * Forward.  u, y, pregate, postgate: (B, H, L) contiguous, plan dtype, L <= N, L a multiple of
+ * bffc_length_multiple().  kf_engine: from bffc_kf_pack* / bffc_kf_from_filter.  pregate/postgate: both NULL or both non-NULL
  * (conv.py:557-558).  y[b,h,:] = postgate * circular_conv_N(pad(u*pregate), pad(k))[:L].
  */
 int bffc_fwd(const bffc_plan* plan, const void* u, const void* kf_engine, const void* pregate,
@@ -113,11 +124,12 @@ int bffc_fwd(const bffc_plan* plan, const void* u, const void* kf_engine, const 
              size_t workspace_bytes, void* stream);
 
 /*
- * Backward.  dout, u (and gates) as in forward.  kf_engine_conj: bffc_kf_pack(..., conj=1).
- * Outputs: du (B,H,L) plan dtype; dkf_engine (H, N) float2 fp32 accumulated over B inside the
- * kernel (overwritten, not accumulated across calls); dpregate/dpostgate (B,H,L) plan dtype when
- * gated (else NULL).  kf_engine (non-conjugated) is required when gated (forward recompute for
- * dpostgate happens inside the same launch).
+ * Backward.  dout, u (and gates) as in forward.  kf_engine: the forward's filter spectrum; kf_engine_conj: NULL (the
+ * kernels conjugate kf_engine in their pointwise multiply) or a pre-conjugated copy from bffc_kf_pack(..., conj=1), in
+ * which case kf_engine may be NULL for an ungated call.
+ * Outputs: du (B,H,L) plan dtype; dkf_engine (H, N) float2 fp32 summed over B inside the kernel (overwritten, not
+ * accumulated across calls); dpregate/dpostgate (B,H,L) plan dtype when gated (else NULL).  Gated: kf_engine is
+ * required (dpostgate = dout * conv(u*pregate, k) is one pass of the forward path; du and dpregate come from one more).
  */
 int bffc_bwd(const bffc_plan* plan, const void* dout, const void* u, const void* kf_engine,
              const void* kf_engine_conj, const void* pregate, const void* postgate, void* du,

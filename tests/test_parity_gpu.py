@@ -396,22 +396,31 @@ def _unpack_kf(kf_engine, dtype):
 @pytest.mark.parametrize('N,H,Lk,dtype', [(8192, 5, 8192, torch.bfloat16), (8192, 4, 1000, torch.bfloat16),
                                           (1024, 3, 1024, torch.bfloat16), (8192, 2, 8192, torch.float16)])
 @pytest.mark.parametrize('conj', [0, 1])
-def test_kf_from_filter_matches_rfft_pack(ffc, N, H, Lk, dtype, conj):
-    """bffc_kf_from_filter (own fp32 FFT, two channels per complex transform, engine order) == rfft + bffc_kf_pack_rfft
-    up to fp32 round-off before the 16-bit rounding (<= 1 ulp of the 16-bit format on a few elements)."""
+def test_kf_from_filter_matches_fft(ffc, N, H, Lk, dtype, conj):
+    """bffc_kf_from_filter (own fp32 FFT, two channels per complex transform, engine order) and rfft +
+    bffc_kf_pack_rfft against an independent statement: torch.fft.fft in float64, the engine-order gather written out in
+    Python (vector v = cc*128 + k1 holds frequencies k1 + 128*(4cc + j), j = 0..3), rounded to the format."""
     from flashfftconv import conv as C
     torch.manual_seed(5)
     mod = ffc.FlashFFTConv(N, dtype=dtype).cuda()
-    dev = torch.device('cuda', 0)
-    plan = mod.plan(dev)
+    plan = mod.plan(torch.device('cuda', 0))
     k = (torch.randn(H, Lk) * torch.exp(-0.002 * torch.arange(Lk))).cuda()
-    a = _unpack_kf(C._kf_engine(mod, plan, C._filter_state(mod, k), conj), dtype)
-    b = _unpack_kf(C._pack_kf_from_natural(mod, plan, C._kf_natural(mod, k), conj), dtype)
+    kf = torch.fft.fft(k.double().cpu(), n=8192)
+    if dtype == torch.bfloat16:
+        kf = kf / 8192
+    if conj:
+        kf = kf.conj()
+    v = torch.arange(2048)
+    freq = (v % 128)[:, None] + 128 * (4 * (v // 128)[:, None] + torch.arange(4)[None, :])
+    want = kf[:, freq]                                                 # (H, 2048, 4)
+    want = torch.complex(want.real.float().to(dtype).float(), want.imag.float().to(dtype).float())
     ulp = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10    # largest relative spacing of the 16-bit format
-    err = (a - b).abs()
-    tol = ulp * b.abs().clamp_min(1e-30) * 1.5 + 1e-6 * b.abs().max()     # both components may flip one spacing
-    assert bool((err <= tol).all()), f'max excess {(err - tol).max().item():.3e}'
-    assert float((err > 0).float().mean()) < 0.02          # 16-bit roundings flip on a small fraction only
+    tol = ulp * want.abs().clamp_min(1e-30) * 1.5 + 2e-6 * want.abs().max()     # both components may flip one spacing
+    for got in (C._pack_kf(mod, plan, k, conj), C._pack_kf_from_natural(mod, plan, C._kf_natural(mod, k), conj)):
+        a = _unpack_kf(got, dtype).cpu()
+        err = (a - want).abs()
+        assert bool((err <= tol).all()), f'max excess {(err - tol).max().item():.3e}'
+        assert float((err > 0).float().mean()) < 0.02          # 16-bit roundings flip on a small fraction only
 
 
 @pytest.mark.parametrize('N,H,Lk', [(8192, 3, 8192), (8192, 2, 777), (2048, 3, 2048), (256, 2, 100)])
@@ -439,3 +448,26 @@ def test_filter_fft_entry_points_reject_long_plans(ffc):
     x = torch.zeros(2, 32768, device='cuda')
     assert lib.bffc_kf_from_filter(plan.handle, x.data_ptr(), 32768, x.data_ptr(), 2, 0, None) != 0
     assert b'8192' in lib.bffc_last_error()
+
+
+# ----------------------------------------------------------------------------- callers' gating routed through the fused gates
+@pytest.mark.parametrize('N,L', [(8192, 4096), (32768, 16384)])
+def test_hyena_mixer_matches_callers_pattern(ffc, N, L):
+    """the examples' `x1v = x1 * v; y = conv(x1v, k); y = y * x2` (hyenadna_flashfftconv.py:279-284)
+    equals ONE gated call; outputs and all four gradients against autograd through the fp32 oracle of that pattern."""
+    B, D = 2, 6
+    torch.manual_seed(9)
+    proj = torch.randn(B, 3 * D, L, device='cuda').to(torch.bfloat16).requires_grad_(True)
+    k = (torch.randn(D, L, device='cuda') / L ** 0.5).requires_grad_(True)
+    conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
+    y = ffc.hyena_mixer(conv, proj, k, D)
+    dout = torch.randn_like(y)
+    y.backward(dout)
+    p32 = proj.detach().float().cpu().requires_grad_(True)
+    k32 = k.detach().cpu().requires_grad_(True)
+    x1, x2, v = p32.split(D, dim=1)
+    ref = orc.ref_fft_conv(x1 * v, k32, N) * x2
+    ref.backward(dout.float().cpu())
+    _check(y.detach(), ref.detach(), 'hyena mixer y')
+    _check(proj.grad, p32.grad, 'hyena mixer d(projection)')
+    _check(k.grad, k32.grad, 'hyena mixer dk')
