@@ -11,6 +11,7 @@
 #include "bffc.h"
 #include "fwd_r128.cuh"
 #include "fwd3_r128.cuh"
+#include "fwd4_r16.cuh"
 #include "dkf3_r128.cuh"
 #include "outer_cuda.cuh"
 #include "outer_r128.cuh"
@@ -96,13 +97,23 @@ uint16_t f2bf(double x) {  // round-to-nearest-even float -> bf16 bits
   return static_cast<uint16_t>((u + r) >> 16);
 }
 
+// Inner (8192-point) frequency held by entry j (0..3) of 16-byte engine vector v (0..15) of lane `lane` (0..127).
+//   order 1 (fwd3_r128.cuh, 128 x 64): lane = k1, f = k1 + 128 (4 v + j)
+//   order 2 (fwd4_r16.cuh, 16 x 16 x 32): pass 3's thread, lane = 64 q2_hi + 8 q1_lo + q2_lo, reads vector v = 8 q1_hi + g
+//            for q3 = 4 g + j: f = q1 + 16 q2 + 256 q3   (tests/kernel_model_r16.py kf_engine_freq)
+__host__ __device__ inline int engine_inner_freq(int order, int v, int lane, int j) {
+  if (order == 1) return lane + 128 * (4 * v + j);
+  const int q1 = 8 * (v >> 3) + ((lane >> 3) & 7), q2 = 8 * (lane >> 6) + (lane & 7);
+  return q1 + 16 * q2 + 256 * (4 * (v & 7) + j);
+}
+
 // k_f -> engine order.  One thread produces one 16-byte engine vector = 4 consecutive inner frequencies k2 = 4cc..4cc+3
 // of one (row, k1): words (re k2, re k2+1) (im ..) (re k2+2, re k2+3) (im ..).  Reads are coalesced along k1
 // (stride R complex numbers), writes are fully coalesced.
 // kHalf: the source holds only frequencies 0..N/2 of a real filter (torch.fft.rfft); k > N/2 is conj(src[N-k]).
 template <bool kHalf, int kFmt>
 __global__ void kf_pack_kernel(const float2* __restrict__ kf_nat, uint4* __restrict__ kf_eng, int N, int R0, int R1,
-                               float scale, int conj) {
+                               float scale, int conj, int order) {
   const int h = blockIdx.y;
   const int R = R0 * R1;
   const float2* src = kf_nat + size_t(h) * (kHalf ? (N / 2 + 1) : N);
@@ -114,7 +125,7 @@ __global__ void kf_pack_kernel(const float2* __restrict__ kf_nat, uint4* __restr
     float2 e[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      int k = c0 + R0 * (c1 + R1 * (k1 + 128 * (4 * cc + i)));
+      int k = c0 + R0 * (c1 + R1 * engine_inner_freq(order, cc, k1, i));
       float sg = conj ? -1.f : 1.f;
       if (kHalf && k > N / 2) { k = N - k; sg = -sg; }
       const float2 t = src[k];
@@ -186,7 +197,7 @@ __global__ void gate_mul2_kernel(const uint4* __restrict__ a0, const uint4* __re
 
 template <bool kHalf, int kFmt>
 __global__ void kf_pack_tiled_kernel(const float2* __restrict__ kf_nat, uint2* __restrict__ kf_eng, int N, int R0, int R1,
-                                     float scale, int conj) {
+                                     float scale, int conj, int order) {
   __shared__ uint2 tile[32][33];
   const int h = blockIdx.z;
   const int c0b = (blockIdx.y % (R0 / 32)) * 32, c1 = blockIdx.y / (R0 / 32);
@@ -197,11 +208,10 @@ __global__ void kf_pack_tiled_kernel(const float2* __restrict__ kf_nat, uint2* _
   for (int j = ty; j < 32; j += 8) {
     const int wp = wp0 + j;                            // word pair index inside the row: (cc*128 + k1)*2 + pp
     const int pp = wp & 1, k1 = (wp >> 1) & 127, cc = wp >> 8;
-    const int kin = k1 + 128 * (4 * cc + 2 * pp);      // inner frequency of the first element
     float2 v[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      int k = (c0b + tx) + R0 * (c1 + R1 * (kin + 128 * e));
+      int k = (c0b + tx) + R0 * (c1 + R1 * engine_inner_freq(order, cc, k1, 2 * pp + e));
       float sg = conj ? -1.f : 1.f;
       if (kHalf && k > N / 2) { k = N - k; sg = -sg; }
       float2 t = src[k];
@@ -236,11 +246,18 @@ struct bffc_plan {
   __nv_bfloat16* dftS = nullptr;
   uint8_t* gtiles = nullptr;
   float2* tw8192 = nullptr;   // e^{-2 pi i t / 8192}, t < 8192: twiddles of the fp32 filter-side FFTs (filter_fft.cuh)
+  int order = 1;              // k_f engine order: 2 when the inner kernel is fwd4_r16.cuh (seqlen >= 8192), else 1
+  uint8_t* bmats = nullptr;   // fwd4: DFT operand images (r16::kBmatBytes)
+  float2* tw5 = nullptr;      // fwd4: conj W_256^{b q1}
   int num_sms = 0;
   // bffc_fwd_host: copy-in / compute / copy-out streams and the per-slot events (created with the plan)
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t hev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
+
+extern "C" { static int build_fwd4_tables(bffc_plan* p); }
+static int launch_fwd4(const bffc_plan* p, const void* in0, const void* in1, void* out0, void* out1, const void* kf, int B,
+                       int H, int L, int planes, int conj, float* dbg, cudaStream_t st);
 
 extern "C" {
 
@@ -361,6 +378,18 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
     PLAN_TRY(cudaFuncSetAttribute(bffc::ffft::kf_from_filter_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, bffc::ffft::kSmemBytes));
   );
   PLAN_TRY(cudaFuncSetAttribute(bffc::ffft::dk_from_dkf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bffc::ffft::kSmemBytes));
+  {
+    // bring-up switch (to be removed once fwd4 is the only inner kernel): BFFC_INNER=4 selects fwd4_r16.cuh
+    const char* e = getenv("BFFC_INNER");
+    p->order = (e && e[0] == '4' && p->N >= kInner) ? 2 : 1;
+  }
+  if (p->order == 2) {
+    if (int rc = build_fwd4_tables(p)) { bffc_plan_destroy(p); return rc; }
+    FMT_SWITCH(dtype,
+      PLAN_TRY(cudaFuncSetAttribute(bffc::r16::fwd4_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, bffc::r16::kSmemTotal4));
+      PLAN_TRY(cudaFuncSetAttribute(bffc::r16::fwd4_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, bffc::r16::kSmemTotal4));
+    );
+  }
   // streams / events of bffc_fwd_host (copy-in, compute, copy-out; per-slot events)
   for (auto& st : p->hs) PLAN_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   for (auto& ev : p->hev) PLAN_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -369,11 +398,56 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   return BFFC_OK;
 }
 
+// fwd4_r16.cuh: DFT operand images (K-major, no swizzle: [N rows][16 K] per K step; 8-row groups 256 B apart, the two
+// 16-byte K halves 128 B apart) and the P5 twiddle table.  B[k][n]: columns n < r hold the real part of output digit
+// q = n, columns n >= r its imaginary part; the operand for the real input plane is [Re F | Im F], for the imaginary
+// plane [-Im F | Re F].  fp16 plans carry 1/sqrt(radix) per stage (bf16: 1/N lives in k_f).
+static int build_fwd4_tables(bffc_plan* p) {
+  using namespace bffc::r16;
+  std::vector<uint8_t> img(kBmatBytes, 0);
+  const double PI = 3.14159265358979323846;
+  const bool h = p->dtype != BFFC_DTYPE_BF16;
+  auto put = [&](size_t off, int n, int k, double v) {
+    const uint16_t b = f2h16(v, p->dtype);
+    memcpy(img.data() + off + size_t(n / 8) * 256 + size_t(k / 8) * 128 + size_t(n % 8) * 16 + size_t(k % 8) * 2, &b, 2);
+  };
+  // F(k, q) = exp(sign 2 pi i (k q / r + q fold / 64))
+  auto fill = [&](size_t off, int r, int kbase, double sign, int fold, int plane, double scale) {
+    for (int n = 0; n < 2 * r; ++n)
+      for (int kk = 0; kk < 16; ++kk) {
+        const int k = kbase + kk, q = n % r, part = n / r;
+        const double ang = sign * 2.0 * PI * (double((k * q) % r) / r + double((q * fold) % 64) / 64.0);
+        const double fr = cos(ang) * scale, fi = sin(ang) * scale;
+        put(off, n, kk, plane == 0 ? (part == 0 ? fr : fi) : (part == 0 ? -fi : fr));
+      }
+  };
+  const double s16 = h ? 0.25 : 1.0, s32 = h ? 0.17677669529663687 : 1.0;
+  for (int c = 0; c < 4; ++c)
+    for (int pl = 0; pl < 2; ++pl) fill(kOffF16 + (2 * c + pl) * 1024, 16, 0, -1.0, c, pl, s16);
+  for (int pl = 0; pl < 2; ++pl) fill(kOffI16 + pl * 1024, 16, 0, 1.0, 0, pl, s16);
+  for (int pl = 0; pl < 2; ++pl)
+    for (int ks = 0; ks < 2; ++ks) {
+      fill(kOffF32 + (2 * pl + ks) * 2048, 32, 16 * ks, -1.0, 0, pl, s32);
+      fill(kOffI32 + (2 * pl + ks) * 2048, 32, 16 * ks, 1.0, 0, pl, s32);
+    }
+  std::vector<float2> tw(256);
+  for (int q1 = 0; q1 < 16; ++q1)
+    for (int b = 0; b < 16; ++b) {
+      const double ang = 2.0 * PI * double((q1 * b) % 256) / 256.0;
+      tw[q1 * 16 + b] = make_float2(float(cos(ang)), float(sin(ang)));
+    }
+  CUDA_TRY(cudaMalloc(&p->bmats, img.size()));
+  CUDA_TRY(cudaMemcpy(p->bmats, img.data(), img.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&p->tw5, tw.size() * sizeof(float2)));
+  CUDA_TRY(cudaMemcpy(p->tw5, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  return BFFC_OK;
+}
+
 int bffc_fft_size(const bffc_plan* p) { return p ? p->NE : 0; }
 
 int bffc_length_multiple(const bffc_plan* p) {
   if (!p) return 0;
-  if (p->nlev == 0) return 64;                       // fused kernel: TMA tiles of 64 columns
+  if (p->nlev == 0) return p->order == 2 ? 512 : 64; // fused kernel: TMA boxes of 64 columns (x 8 rows for fwd4)
   if (p->lev[0].tc) return p->N / 128;               // tcgen05 outer stage: whole rows of the [128][N/128] view
   return 8;                                          // CUDA-core outer stage: 16-byte vectors
 }
@@ -384,6 +458,8 @@ int bffc_plan_destroy(bffc_plan* p) {
   cudaFree(p->dftS);
   cudaFree(p->gtiles);
   cudaFree(p->tw8192);
+  cudaFree(p->bmats);
+  cudaFree(p->tw5);
   for (auto& st : p->hs) if (st) cudaStreamDestroy(st);
   for (auto& ev : p->hev) if (ev) cudaEventDestroy(ev);
   delete p;
@@ -396,14 +472,14 @@ int bffc_kf_pack(const bffc_plan* p, const void* kf_natural, void* kf_engine, in
     dim3 grid(kInner / 2 / 32, (p->lev[0].R / 32) * (p->nlev == 2 ? p->lev[1].R : 1), H);
     FMT_SWITCH(p->dtype, (kf_pack_tiled_kernel<false, F><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const float2*>(kf_natural), static_cast<uint2*>(kf_engine), p->NE, p->lev[0].R,
-        p->nlev == 2 ? p->lev[1].R : 1, p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj)););
+        p->nlev == 2 ? p->lev[1].R : 1, p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj, p->order)););
     CUDA_TRY(cudaGetLastError());
     return BFFC_OK;
   }
   dim3 grid((p->NE / 4 + 255) / 256 > 32 ? 32 : (p->NE / 4 + 255) / 256, H);
   FMT_SWITCH(p->dtype, (kf_pack_kernel<false, F><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float2*>(kf_natural), static_cast<uint4*>(kf_engine), p->NE, p->nlev >= 1 ? p->lev[0].R : 1,
-      p->nlev == 2 ? p->lev[1].R : 1, p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj)););
+      p->nlev == 2 ? p->lev[1].R : 1, p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj, p->order)););
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -414,14 +490,14 @@ int bffc_kf_pack_rfft(const bffc_plan* p, const void* kf_half, void* kf_engine, 
     dim3 grid(kInner / 2 / 32, (p->lev[0].R / 32) * (p->nlev == 2 ? p->lev[1].R : 1), H);
     FMT_SWITCH(p->dtype, (kf_pack_tiled_kernel<true, F><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const float2*>(kf_half), static_cast<uint2*>(kf_engine), p->NE, p->lev[0].R,
-        p->nlev == 2 ? p->lev[1].R : 1, p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj)););
+        p->nlev == 2 ? p->lev[1].R : 1, p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj, p->order)););
     CUDA_TRY(cudaGetLastError());
     return BFFC_OK;
   }
   dim3 grid((p->NE / 4 + 255) / 256 > 32 ? 32 : (p->NE / 4 + 255) / 256, H);
   FMT_SWITCH(p->dtype, (kf_pack_kernel<true, F><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float2*>(kf_half), static_cast<uint4*>(kf_engine), p->NE, p->nlev >= 1 ? p->lev[0].R : 1,
-      p->nlev == 2 ? p->lev[1].R : 1, p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj)););
+      p->nlev == 2 ? p->lev[1].R : 1, p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj, p->order)););
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -434,7 +510,7 @@ int bffc_kf_from_filter(const bffc_plan* p, const void* k, int Lk, void* kf_engi
   using namespace bffc::ffft;
   const float scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f;
   FMT_SWITCH(p->dtype, (kf_from_filter_kernel<F><<<(H + 1) / 2, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float*>(k), Lk, static_cast<uint4*>(kf_engine), H, scale, conj, p->tw8192)););
+      static_cast<const float*>(k), Lk, static_cast<uint4*>(kf_engine), H, scale, conj, p->tw8192, p->order)););
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -468,6 +544,32 @@ int bffc_dkf_unpack(const bffc_plan* p, const void* dkf_engine, void* dkf_natura
 
 // Composite sizes keep the outer stage's output as two bf16 planes (real, imaginary) of pairs*H*N elements.
 static size_t plane_bytes(const bffc_plan* p, int B, int H) { return size_t((B + 1) / 2) * H * p->N * 2; }
+// One launch group of a composite size works on batch members [0, B) (tensor pointers are pre-offset to the first one)
+// and channels [h0, h0 + H) of (.., Hs, L) tensors; its plane sets hold ceil(B/2) * H * N complex elements.
+struct View { int B, H, Hs, h0; };
+
+// Composite sizes run chunk by chunk so that the 16-bit plane sets written by the outer stage, rewritten in place by the
+// inner kernel and read back by the inverse outer stage stay resident in the 126 MB L2 instead of making four trips
+// through HBM: `sets` plane sets of one chunk take at most ~kPlaneBudget bytes.  Channels first (the k_f rows of a
+// channel are then shared by its batch pairs inside one chunk); a single channel that is too large is cut over batch pairs.
+constexpr size_t kPlaneBudget = size_t(40) << 20;
+static View chunk_view(const bffc_plan* p, int B, int H, int sets) {
+  const size_t item = size_t(sets) * p->N * 4;                     // one (pair, channel) in all plane sets
+  size_t items = kPlaneBudget / item;
+  if (items < 1) items = 1;
+  const int pairs = (B + 1) / 2;
+  View v{B, H, H, 0};
+  if (items >= size_t(pairs)) {
+    const size_t hc = items / pairs;
+    v.H = hc < size_t(H) ? int(hc) : H;
+  } else {
+    v.H = 1;
+    v.B = 2 * int(items);
+    if (v.B > B) v.B = B;
+  }
+  return v;
+}
+
 
 // u*pregate and dout*postgate for the dk_f kernel of a gated backward at seqlen <= 8192 (two (B,H,L) tensors)
 static size_t gate_scratch_bytes(int B, int H, int L) { return 2 * ((size_t(B) * H * L * 2 + 255) & ~size_t(255)); }
@@ -479,8 +581,15 @@ extern "C" size_t bffc_workspace_bytes_ex(const bffc_plan* p, int B, int H, int 
     return size_t(H) * G * 2 * kInner * 2 + ((gated && backward) ? gate_scratch_bytes(B, H, L) : 0);
   }
   if (p->nlev == 0) return (gated && backward) ? gate_scratch_bytes(B, H, L) : 0;
-  // plane sets (real + imaginary plane each): forward nlev sets; backward nlev + 1 (transformed u and dout)
-  return size_t(2 * (backward ? p->nlev + 1 : p->nlev)) * plane_bytes(p, B, H);
+  // plane sets (real + imaginary plane each) of ONE chunk: forward nlev sets; backward nlev + 1 (transformed u and dout)
+  const View vf = chunk_view(p, B, H, p->nlev);
+  size_t need = size_t(2 * p->nlev) * plane_bytes(p, vf.B, vf.H);
+  if (backward) {      // the du / dpostgate passes run as forward chunks, the dk_f part with one more set per chunk
+    const View vb = chunk_view(p, B, H, p->nlev + 1);
+    const size_t nb = size_t(2 * (p->nlev + 1)) * plane_bytes(p, vb.B, vb.H);
+    if (nb > need) need = nb;
+  }
+  return need;
 }
 
 extern "C" size_t bffc_workspace_bytes(const bffc_plan* p, int B, int H, int L) {
@@ -573,6 +682,12 @@ struct PassOpts {
 static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const void* pregate, const void* postgate,
                         void* y, int B, int H, int L, float* dbg, int dbg_stages, int max_units, cudaStream_t st,
                         const PassOpts& po = PassOpts()) {
+  if (p->order == 2) {
+    if (pregate || postgate || po.y2) return fail(BFFC_ERR_UNSUPPORTED, "gated seqlen-8192 calls are not wired to fwd4 yet");
+    const uint8_t* u1 = static_cast<const uint8_t*>(u) + size_t(H) * L * 2;      // member b + 1 of a pair
+    uint8_t* y1 = static_cast<uint8_t*>(y) + size_t(H) * L * 2;
+    return launch_fwd4(p, u, u1, y, y1, kf, B, H, L, 0, po.conj, dbg, st);
+  }
   if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen <= 8192 in this build", L);
   const bool small = p->N < kInner;
   const SegGeom sg = seg_geom(p, B, L);
@@ -622,9 +737,57 @@ static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const
   return BFFC_OK;
 }
 
+// fwd4: (rows, L) 16-bit viewed as [row][a = n >> 9][th = (n >> 6) & 7][64]; box = the 16 rows (a) of one th, 128B
+// swizzle; a >= L/512 is out of bounds: zero fill on load (implicit padding), dropped on store.  L % 512 == 0.
+static int make_map_r16(const bffc_plan* p, CUtensorMap* map, const void* base, int rows, int L) {
+  cuuint64_t dims[4] = {64, 8, cuuint64_t(L / 512), cuuint64_t(rows)};
+  cuuint64_t strides[3] = {128, 1024, cuuint64_t(L) * 2};
+  cuuint32_t box[4] = {64, 1, 16, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(map, map_dtype(p), 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(BFFC_ERR_CUDA, "cuTensorMapEncodeTiled (fwd4) failed (%d)", int(r));
+  return 0;
+}
+
+// fwd4_r16.cuh on (B, H, L) real sequences (planes == 0) or on complex rows in two planes, in place (planes == 1:
+// in0 = out0 = real plane, in1 = out1 = imaginary plane, B = 2 * pairs, H = k_f rows, L = 8192)
+static int launch_fwd4(const bffc_plan* p, const void* in0, const void* in1, void* out0, void* out1, const void* kf, int B,
+                       int H, int L, int planes, int conj, float* dbg, cudaStream_t st) {
+  if (L % 512 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 512 for seqlen 8192 in this build", L);
+  const int pairs = (B + 1) / 2, rows = planes ? pairs * H : B * H;
+  CUtensorMap ti0, ti1, to0, to1;
+  if (int rc = make_map_r16(p, &ti0, in0, rows, L)) return rc;
+  if (int rc = make_map_r16(p, &ti1, in1, rows, L)) return rc;
+  if (int rc = make_map_r16(p, &to0, out0, rows, L)) return rc;
+  if (int rc = make_map_r16(p, &to1, out1, rows, L)) return rc;
+  bffc::Fwd4Params prm;
+  prm.kf = static_cast<const uint32_t*>(kf);
+  prm.bmats = p->bmats;
+  prm.tw5 = p->tw5;
+  prm.kf_scale = 1.0f;
+  prm.kf_conj_mask = conj ? 0x80008000u : 0u;
+  prm.B = B; prm.H = H; prm.pairs = pairs;
+  prm.units = H * pairs;
+  prm.planes = planes;
+  prm.dbg = dbg;
+  if (dbg) prm.units = 1;
+  using namespace bffc::r16;
+  int grid = (prm.units + kPipes4 - 1) / kPipes4;
+  if (grid > p->num_sms) grid = p->num_sms;
+  FMT_SWITCH(p->dtype,
+    if (dbg) fwd4_kernel<true, F><<<grid, kThreads4, kSmemTotal4, st>>>(ti0, ti1, to0, to1, prm);
+    else fwd4_kernel<false, F><<<grid, kThreads4, kSmemTotal4, st>>>(ti0, ti1, to0, to1, prm);
+  );
+  CUDA_TRY(cudaGetLastError());
+  return BFFC_OK;
+}
+
 // fused kernel on complex rows held in two planes (in place); rows = pairs * kf_rows
 static int launch_planes(const bffc_plan* p, void* pre, void* pim, const void* kf, int pairs, int kf_rows, cudaStream_t st,
                          int conj = 0) {
+  if (p->order == 2) return launch_fwd4(p, pre, pim, pre, pim, kf, 2 * pairs, kf_rows, kInner, 1, conj, nullptr, st);
   CUtensorMap tm_r, tm_i;
   if (int rc = make_map(p, &tm_r, pre, pairs * kf_rows, kInner)) return rc;
   if (int rc = make_map(p, &tm_i, pim, pairs * kf_rows, kInner)) return rc;
@@ -703,15 +866,16 @@ static int cc_stage(const bffc_plan* p, int R, bool inverse, bool gated, bool pl
 }
 
 // tcgen05 radix-128 level 0: real endpoint x (u or y), gate g (pregate fwd / postgate inv), planes set A
-static int tc_stage(const bffc_plan* p, bool inverse, const void* x, const void* gate, PlaneSet A, int B, int H, int L,
+static int tc_stage(const bffc_plan* p, bool inverse, const void* x, const void* gate, PlaneSet A, View v, int L,
                     cudaStream_t st, const void* gate2 = nullptr, void* x2 = nullptr) {
+  const int B = v.B, H = v.H;
   const int M = p->N / 128, chunks = M / 64, pairs = (B + 1) / 2;
   if (L % M != 0) return fail(BFFC_ERR_UNSUPPORTED, "seqlen %d needs L to be a multiple of %d in this build (L=%d)", p->N, M, L);
   CUtensorMap tm_x, tm_pr, tm_pi, tm_g;
-  if (int rc = make_map4(p, &tm_x, x, chunks, L / M, B * H, size_t(M) * 2, size_t(L) * 2)) return rc;
+  if (int rc = make_map4(p, &tm_x, x, chunks, L / M, B * v.Hs, size_t(M) * 2, size_t(L) * 2)) return rc;
   if (int rc = make_map4(p, &tm_pr, A.re, chunks, 128, pairs * H, size_t(M) * 2, size_t(p->N) * 2)) return rc;
   if (int rc = make_map4(p, &tm_pi, A.im, chunks, 128, pairs * H, size_t(M) * 2, size_t(p->N) * 2)) return rc;
-  if (int rc = make_map4(p, &tm_g, (!inverse && gate) ? gate : x, chunks, L / M, B * H, size_t(M) * 2, size_t(L) * 2)) return rc;
+  if (int rc = make_map4(p, &tm_g, (!inverse && gate) ? gate : x, chunks, L / M, B * v.Hs, size_t(M) * 2, size_t(L) * 2)) return rc;
   bffc::OuterTcParams prm;
   prm.dftC = p->dftC; prm.dftS = p->dftS;
   prm.postgate = inverse ? static_cast<const uint32_t*>(gate) : nullptr;
@@ -720,6 +884,7 @@ static int tc_stage(const bffc_plan* p, bool inverse, const void* x, const void*
   prm.has_pregate = (!inverse && gate) ? 1 : 0;
   prm.tw_scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 0.08838834764831845f;
   prm.B = B; prm.H = H; prm.L = L; prm.pairs = pairs;
+  prm.Hs = v.Hs; prm.h0 = v.h0;
   prm.N = p->N; prm.M = M; prm.chunks = chunks;
   prm.ksteps = (L / M + 15) / 16;
   prm.units = pairs * H * chunks;
@@ -743,18 +908,20 @@ static PlaneSet plane_set(const bffc_plan* p, void* ws, int idx, int B, int H) {
 
 // all outer levels, forward: real (B,H,L) x (* pregate) -> complex 8192-point rows.  Level 0 writes set `s0`,
 // level 1 (if any) reads `s0` and writes `s1`; returns the set holding the rows.
-static int transform_fwd(const bffc_plan* p, const void* x, const void* pregate, int B, int H, int L, PlaneSet s0,
+static int transform_fwd(const bffc_plan* p, const void* x, const void* pregate, View v, int L, PlaneSet s0,
                          PlaneSet s1, PlaneSet* out, cudaStream_t st, int* launches) {
+  const int B = v.B, H = v.H;
   const int pairs = (B + 1) / 2;
   const bffc_level l0 = p->lev[0];
   if (l0.tc) {
-    if (int rc = tc_stage(p, false, x, pregate, s0, B, H, L, st)) return rc;
+    if (int rc = tc_stage(p, false, x, pregate, s0, v, L, st)) return rc;
   } else {
     bffc::outer::OuterParams op{};
     op.u = static_cast<const uint4*>(x);
     op.pregate = static_cast<const uint4*>(pregate);
     op.pre = reinterpret_cast<uint4*>(s0.re); op.pim = reinterpret_cast<uint4*>(s0.im);
     op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / l0.R;
+    op.Hs = v.Hs; op.h0 = v.h0;
     op.scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 1.0f / sqrtf(float(l0.R));
     fill_step(op, double(p->N));
     if (int rc = cc_stage(p, l0.R, false, pregate != nullptr, false, op, 0, st)) return rc;
@@ -777,8 +944,9 @@ static int transform_fwd(const bffc_plan* p, const void* x, const void* pregate,
 }
 
 // all outer levels, inverse: rows in `rows` (set s1 if two levels, else s0) -> real y (* postgate)
-static int transform_inv(const bffc_plan* p, void* y, const void* postgate, int B, int H, int L, PlaneSet s0, PlaneSet s1,
+static int transform_inv(const bffc_plan* p, void* y, const void* postgate, View v, int L, PlaneSet s0, PlaneSet s1,
                          cudaStream_t st, int* launches, const void* postgate2 = nullptr, void* y2 = nullptr) {
+  const int B = v.B, H = v.H;
   const int pairs = (B + 1) / 2;
   const bffc_level l0 = p->lev[0];
   if (p->nlev == 2) {
@@ -793,7 +961,7 @@ static int transform_inv(const bffc_plan* p, void* y, const void* postgate, int 
     *launches += 1;
   }
   if (l0.tc) {
-    if (int rc = tc_stage(p, true, y, postgate, s0, B, H, L, st, postgate2, y2)) return rc;
+    if (int rc = tc_stage(p, true, y, postgate, s0, v, L, st, postgate2, y2)) return rc;
   } else {
     bffc::outer::OuterParams op{};
     op.y = static_cast<uint4*>(y);
@@ -802,6 +970,7 @@ static int transform_inv(const bffc_plan* p, void* y, const void* postgate, int 
     op.y2 = static_cast<uint4*>(y2);
     op.pre = reinterpret_cast<uint4*>(s0.re); op.pim = reinterpret_cast<uint4*>(s0.im);
     op.B = B; op.H = H; op.L = L; op.pairs = pairs; op.M = p->N / l0.R;
+    op.Hs = v.Hs; op.h0 = v.h0;
     op.scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 1.0f / sqrtf(float(l0.R));
     fill_step(op, double(p->N));
     if (int rc = cc_stage(p, l0.R, true, postgate != nullptr, false, op, 0, st)) return rc;
@@ -812,6 +981,10 @@ static int transform_inv(const bffc_plan* p, void* y, const void* postgate, int 
 
 static int check_common(const bffc_plan* p, int B, int H, int L, const void* a, const void* b, const void* c) {
   if (!p) return fail(BFFC_ERR_INVALID, "null plan");
+  // Tensor maps are encoded through the driver API, which needs a current context in the CALLING thread.  A thread that
+  // has made no runtime call yet (PyTorch's autograd worker entering bffc_bwd) has none: this runtime no-op binds the
+  // device's primary context (cuTensorMapEncodeTiled otherwise fails with CUDA_ERROR_INVALID_CONTEXT).
+  CUDA_TRY(cudaFree(nullptr));
   if (B <= 0 || H <= 0 || L <= 0 || L > p->N) return fail(BFFC_ERR_INVALID, "bad shape B=%d H=%d L=%d (seqlen %d)", B, H, L, p->N);
   if (L % 8 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 8 in this build", L);
   if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15)
@@ -844,12 +1017,23 @@ static int conv_forward(const bffc_plan* p, const void* u, const void* kf, const
     *launches += 1;
     return launch_fused(p, u, kf, pregate, postgate, y, B, H, L, nullptr, 0, 0, st, po);
   }
-  const int pairs = (B + 1) / 2;
-  PlaneSet s0 = plane_set(p, ws, 0, B, H), s1 = plane_set(p, ws, p->nlev == 2 ? 1 : 0, B, H), rows;
-  if (int rc = transform_fwd(p, u, pregate, B, H, L, s0, s1, &rows, st, launches)) return rc;
-  if (int rc = launch_planes(p, rows.re, rows.im, kf, pairs, H * p->R, st, po.conj)) return rc;
-  *launches += 1;
-  return transform_inv(p, y, postgate, B, H, L, s0, s1, st, launches, po.postgate2, po.y2);
+  // composite sizes, chunk by chunk (see chunk_view): outer stage(s) -> inner kernel in place -> inverse outer stage(s)
+  const View c = chunk_view(p, B, H, p->nlev);
+  const size_t bstride = size_t(H) * L * 2;                       // bytes of one batch member of the (B, H, L) tensors
+  auto at = [&](const void* t, int b0) { return t ? static_cast<const uint8_t*>(t) + size_t(b0) * bstride : nullptr; };
+  for (int b0 = 0; b0 < B; b0 += c.B)
+    for (int h0 = 0; h0 < H; h0 += c.H) {
+      const View v{B - b0 < c.B ? B - b0 : c.B, H - h0 < c.H ? H - h0 : c.H, H, h0};
+      const int pairs = (v.B + 1) / 2;
+      PlaneSet s0 = plane_set(p, ws, 0, c.B, c.H), s1 = plane_set(p, ws, p->nlev == 2 ? 1 : 0, c.B, c.H), rows;
+      if (int rc = transform_fwd(p, at(u, b0), at(pregate, b0), v, L, s0, s1, &rows, st, launches)) return rc;
+      const uint8_t* kfc = static_cast<const uint8_t*>(kf) + size_t(h0) * p->NE * 4;
+      if (int rc = launch_planes(p, rows.re, rows.im, kfc, pairs, v.H * p->R, st, po.conj)) return rc;
+      *launches += 1;
+      if (int rc = transform_inv(p, const_cast<uint8_t*>(at(y, b0)), at(postgate, b0), v, L, s0, s1, st, launches,
+                                 at(po.postgate2, b0), const_cast<uint8_t*>(at(po.y2, b0)))) return rc;
+    }
+  return BFFC_OK;
 }
 
 extern "C" {
@@ -953,30 +1137,41 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
     CUDA_TRY(cudaGetLastError());
     launches += 1;
   } else {
-    // transformed u rows -> set U, transformed dout rows -> set D (set 0 is the level-0 intermediate when nlev == 2)
-    PlaneSet s0 = plane_set(p, workspace, 0, B, H);
-    PlaneSet sU = p->nlev == 2 ? plane_set(p, workspace, 1, B, H) : s0;
-    PlaneSet sD = plane_set(p, workspace, p->nlev == 2 ? 2 : 1, B, H);
-    PlaneSet ru, rd;
-    if (int rc = transform_fwd(p, u, pregate, B, H, L, s0, sU, &ru, st, &launches)) return rc;
-    if (p->nlev == 2) {
-      if (int rc = transform_fwd(p, dout, postgate, B, H, L, s0, sD, &rd, st, &launches)) return rc;
-    } else {
-      if (int rc = transform_fwd(p, dout, postgate, B, H, L, sD, sD, &rd, st, &launches)) return rc;
-    }
-    const int rows = H * p->R;
-    CUtensorMap tur, tui, tdr, tdi;
-    if (int rc = make_map(p, &tur, ru.re, pairs * rows, kInner)) return rc;
-    if (int rc = make_map(p, &tui, ru.im, pairs * rows, kInner)) return rc;
-    if (int rc = make_map(p, &tdr, rd.re, pairs * rows, kInner)) return rc;
-    if (int rc = make_map(p, &tdi, rd.im, pairs * rows, kInner)) return rc;
-    prm.B = 2 * pairs; prm.H = rows; prm.L = kInner;
-    prm.kmask = 0xff; prm.nseg = 1; prm.seg_bytes = 16384;
-    const long long units = (long long)rows * pairs;
-    const int grid = int(units < p->num_sms ? units : p->num_sms);
-    FMT_SWITCH(p->dtype, (dkf3_kernel<true, F><<<grid, kThreadsDkf3, kSmemTotalDkf3, st>>>(tur, tdr, tui, tdi, prm)););
-    CUDA_TRY(cudaGetLastError());
-    launches += 1;
+    // chunk by chunk: transformed u rows -> set U, transformed dout rows -> set D (set 0 is the level-0 intermediate
+    // when nlev == 2), then the dk_f kernel on the chunk's rows; batch chunks of a channel add into the same rows
+    const View c = chunk_view(p, B, H, p->nlev + 1);
+    const size_t bstride = size_t(H) * L * 2;
+    auto at = [&](const void* t, int b0) { return t ? static_cast<const uint8_t*>(t) + size_t(b0) * bstride : nullptr; };
+    for (int b0 = 0; b0 < B; b0 += c.B)
+      for (int h0 = 0; h0 < H; h0 += c.H) {
+        const View v{B - b0 < c.B ? B - b0 : c.B, H - h0 < c.H ? H - h0 : c.H, H, h0};
+        const int vpairs = (v.B + 1) / 2;
+        PlaneSet s0 = plane_set(p, workspace, 0, c.B, c.H);
+        PlaneSet sU = p->nlev == 2 ? plane_set(p, workspace, 1, c.B, c.H) : s0;
+        PlaneSet sD = plane_set(p, workspace, p->nlev == 2 ? 2 : 1, c.B, c.H);
+        PlaneSet ru, rd;
+        if (int rc = transform_fwd(p, at(u, b0), at(pregate, b0), v, L, s0, sU, &ru, st, &launches)) return rc;
+        if (p->nlev == 2) {
+          if (int rc = transform_fwd(p, at(dout, b0), at(postgate, b0), v, L, s0, sD, &rd, st, &launches)) return rc;
+        } else {
+          if (int rc = transform_fwd(p, at(dout, b0), at(postgate, b0), v, L, sD, sD, &rd, st, &launches)) return rc;
+        }
+        const int rows = v.H * p->R;
+        CUtensorMap tur, tui, tdr, tdi;
+        if (int rc = make_map(p, &tur, ru.re, vpairs * rows, kInner)) return rc;
+        if (int rc = make_map(p, &tui, ru.im, vpairs * rows, kInner)) return rc;
+        if (int rc = make_map(p, &tdr, rd.re, vpairs * rows, kInner)) return rc;
+        if (int rc = make_map(p, &tdi, rd.im, vpairs * rows, kInner)) return rc;
+        prm.B = 2 * vpairs; prm.H = rows; prm.L = kInner;
+        prm.pairs = vpairs;
+        prm.dkf = static_cast<float2*>(dkf) + size_t(h0) * p->NE;
+        prm.kmask = 0xff; prm.nseg = 1; prm.seg_bytes = 16384;
+        const long long units = (long long)rows * vpairs;
+        const int grid = int(units < p->num_sms ? units : p->num_sms);
+        FMT_SWITCH(p->dtype, (dkf3_kernel<true, F><<<grid, kThreadsDkf3, kSmemTotalDkf3, st>>>(tur, tdr, tui, tdi, prm)););
+        CUDA_TRY(cudaGetLastError());
+        launches += 1;
+      }
   }
   g_launches = launches;
   return BFFC_OK;
@@ -1088,9 +1283,11 @@ int bffc_debug_fwd_stages(const bffc_plan* p, const void* u, const void* kf, voi
                           int max_stages, void* stream) {
   if (!dump || max_stages <= 0 || !p || p->R != 1) return -BFFC_ERR_INVALID;
   if (check_common(p, B, H, L, u, y, kf)) return -BFFC_ERR_INVALID;
+  const int nst = p->order == 2 ? 6 : 4;
+  if (p->order == 2 && max_stages < 6) return -BFFC_ERR_INVALID;
   int rc = launch_fused(p, u, kf, nullptr, nullptr, y, B, H, L, dump, max_stages, 1, static_cast<cudaStream_t>(stream));
   if (rc) return -rc;
-  return max_stages < 4 ? max_stages : 4;
+  return max_stages < nst ? max_stages : nst;
 }
 
 }  // extern "C"

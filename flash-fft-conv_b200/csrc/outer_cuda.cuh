@@ -46,7 +46,8 @@ struct OuterParams {
   uint4* xim;
   uint4* pre;            // inner-side planes: real parts,  rows*R rows of M bf16 each
   uint4* pim;            // inner-side planes: imaginary parts
-  int B, H, L, pairs;
+  int B, H, L, pairs;    // this launch covers batch members [0, B) and channels [h0, h0 + H) of tensors with Hs channels
+  int Hs, h0;            // channel count of the (B, Hs, L) tensors and first channel of this launch (planes are chunk local)
   int M;                 // inner row length
   float2 step[8];        // exp(-2 pi i t / (R*M)), t = 0..7: neighbour twiddle steps (host computed, double precision)
   int lookahead;         // blocks: a block pulls the input lines of block (its linear id + lookahead) into L2 (0 = off)
@@ -135,7 +136,7 @@ DEVINL void readahead_level0(const OuterParams& p, bool planes_in) {
   for (int a = 0; a < R; ++a) {
     const int n = a * p.M + np;
     if (n >= p.L) break;
-    const size_t o0 = (size_t(b0) * p.H + h) * L8 + n / kVec, o1 = (size_t(b1) * p.H + h) * L8 + n / kVec;
+    const size_t o0 = (size_t(b0) * p.Hs + p.h0 + h) * L8 + n / kVec, o1 = (size_t(b1) * p.Hs + p.h0 + h) * L8 + n / kVec;
     if (!planes_in) {
       prefetch_l2(p.u + o0);
       if (b1 < p.B) prefetch_l2(p.u + o1);
@@ -188,12 +189,12 @@ __global__ void __launch_bounds__(128, (R <= 4) ? 4 : 2) fwd_kernel(const OuterP
       unpack8v<kFmt>(__ldg(p.xim + o), zi[a]);
     } else if (n < p.L) {
       rows = a + 1;
-      const size_t o0 = (size_t(b0) * p.H + h) * L8 + n / kVec;
+      const size_t o0 = (size_t(b0) * p.Hs + p.h0 + h) * L8 + n / kVec;
       uint4 v0 = __ldg(p.u + o0);
       if (kGated) v0 = hmul8<kFmt>(v0, __ldg(p.pregate + o0));
       unpack8v<kFmt>(v0, zr[a]);
       if (b1 < p.B) {
-        const size_t o1 = (size_t(b1) * p.H + h) * L8 + n / kVec;
+        const size_t o1 = (size_t(b1) * p.Hs + p.h0 + h) * L8 + n / kVec;
         uint4 v1 = __ldg(p.u + o1);
         if (kGated) v1 = hmul8<kFmt>(v1, __ldg(p.pregate + o1));
         unpack8v<kFmt>(v1, zi[a]);
@@ -291,13 +292,13 @@ __global__ void __launch_bounds__(128, (R <= 4) ? 4 : 2) inv_kernel(const OuterP
         p.xim[o] = pack8v<kFmt>(yi);
         continue;
       }
-      const size_t o0 = (size_t(b0) * p.H + h) * L8 + n / kVec;
+      const size_t o0 = (size_t(b0) * p.Hs + p.h0 + h) * L8 + n / kVec;
       uint4 v0 = pack8v<kFmt>(yr);
       if (kGated && p.y2) p.y2[o0] = hmul8<kFmt>(v0, __ldg(p.postgate2 + o0));
       if (kGated) v0 = hmul8<kFmt>(v0, __ldg(p.postgate + o0));
       p.y[o0] = v0;
       if (b1 < p.B) {
-        const size_t o1 = (size_t(b1) * p.H + h) * L8 + n / kVec;
+        const size_t o1 = (size_t(b1) * p.Hs + p.h0 + h) * L8 + n / kVec;
         uint4 v1 = pack8v<kFmt>(yi);
         if (kGated && p.y2) p.y2[o1] = hmul8<kFmt>(v1, __ldg(p.postgate2 + o1));
         if (kGated) v1 = hmul8<kFmt>(v1, __ldg(p.postgate + o1));

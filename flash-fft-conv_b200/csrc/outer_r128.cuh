@@ -26,7 +26,8 @@ struct OuterTcParams {
   uint32_t* y2;
   int has_pregate;            // forward only: tm_g is the pregate map
   float tw_scale;             // folded into the twiddle table (fp16: 1/sqrt(128))
-  int B, H, L, pairs;
+  int B, H, L, pairs;         // this launch: batch members [0, B), channels [h0, h0 + H) of tensors with Hs channels
+  int Hs, h0;
   int N, M, chunks;           // M = N/128, chunks = M/64
   int ksteps;                 // 16-row K steps of the [128][M] view that are non-zero: ceil(L/M/16)
   int units;                  // pairs * H * chunks
@@ -129,7 +130,7 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
   const uint32_t tC0 = tmem_base + kColC;
   const uint32_t tS0 = tmem_base + kColS;
   const uint32_t bar_id = 1 + pipe;
-  const int BH = p.B * p.H;
+  const int BH = p.B * p.Hs;      // out-of-bounds sequence index of the 4-D maps (zero fill / dropped)
   const bool gated_in = (!kInverse) && p.has_pregate;
   const int nslots = gated_in ? 2 : kOuterSlots;
   const uint32_t s_gate0 = s_slot0 + 2 * kSlotBytes;     // gated: the third ring slot holds the pregate tiles
@@ -150,7 +151,7 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
     mbar_expect_tx(bar, gated_in ? 2 * kSlotBytes : kSlotBytes);
     if (!kInverse) {
       const int b0 = 2 * x.pr, b1 = 2 * x.pr + 1;
-      const int s0 = b0 * p.H + x.h, s1 = b1 < p.B ? b1 * p.H + x.h : BH;    // BH: out of bounds -> zeros
+      const int s0 = b0 * p.Hs + p.h0 + x.h, s1 = b1 < p.B ? b1 * p.Hs + p.h0 + x.h : BH;    // BH: out of bounds -> zeros
       tma_load_4d(dst, &tm_x, bar, 0, x.cj, 0, s0);
       tma_load_4d(dst + kTileBytes, &tm_x, bar, 0, x.cj, 0, s1);
       if (gated_in) {
@@ -262,7 +263,7 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
 #pragma unroll
       for (int part = 0; part < 2; ++part) {
         const int b = 2 * x.pr + part;
-        const size_t e0 = (size_t(b < p.B ? b : p.B - 1) * p.H + x.h) * p.L + size_t(lane) * p.M + x.cj * 64 + 32 * half;
+        const size_t e0 = (size_t(b < p.B ? b : p.B - 1) * p.Hs + p.h0 + x.h) * p.L + size_t(lane) * p.M + x.cj * 64 + 32 * half;
         const uint4* gp_ = reinterpret_cast<const uint4*>(p.postgate + e0 / 2);
 #pragma unroll
         for (int c = 0; c < 4; ++c) pg[part][c] = row_ok ? __ldg(gp_ + c) : make_uint4(0, 0, 0, 0);
@@ -304,7 +305,7 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
           for (int part = 0; part < 2; ++part) {
             const int b = 2 * x.pr + part;
             if (b < p.B) {
-              const size_t e0 = (size_t(b) * p.H + x.h) * p.L + size_t(lane) * p.M + x.cj * 64 + 32 * half + 8 * (2 * sub + cc);
+              const size_t e0 = (size_t(b) * p.Hs + p.h0 + x.h) * p.L + size_t(lane) * p.M + x.cj * 64 + 32 * half + 8 * (2 * sub + cc);
               const uint4 g2 = __ldg(reinterpret_cast<const uint4*>(p.postgate2 + e0 / 2));
               const uint32_t v0 = part ? b0 : a0, v1 = part ? b1 : a1, v2 = part ? b2 : a2, v3 = part ? b3 : a3;
               *reinterpret_cast<uint4*>(p.y2 + e0 / 2) =
@@ -332,8 +333,8 @@ outer_tc_kernel(const __grid_constant__ CUtensorMap tm_x,    // real endpoint: u
           tma_store_4d(&tm_pi, sX + kTileBytes, 0, x.cj, 0, row);
         } else {
           const int b0 = 2 * x.pr, b1 = 2 * x.pr + 1;
-          tma_store_4d(&tm_x, sX, 0, x.cj, 0, b0 * p.H + x.h);
-          if (b1 < p.B) tma_store_4d(&tm_x, sX + kTileBytes, 0, x.cj, 0, b1 * p.H + x.h);
+          tma_store_4d(&tm_x, sX, 0, x.cj, 0, b0 * p.Hs + p.h0 + x.h);
+          if (b1 < p.B) tma_store_4d(&tm_x, sX + kTileBytes, 0, x.cj, 0, b1 * p.Hs + p.h0 + x.h);
         }
         tma_store_commit();
       }
