@@ -548,11 +548,13 @@ static size_t plane_bytes(const bffc_plan* p, int B, int H) { return size_t((B +
 // and channels [h0, h0 + H) of (.., Hs, L) tensors; its plane sets hold ceil(B/2) * H * N complex elements.
 struct View { int B, H, Hs, h0; };
 
-// Composite sizes run chunk by chunk so that the 16-bit plane sets written by the outer stage, rewritten in place by the
-// inner kernel and read back by the inverse outer stage stay resident in the 126 MB L2 instead of making four trips
-// through HBM: `sets` plane sets of one chunk take at most ~kPlaneBudget bytes.  Channels first (the k_f rows of a
-// channel are then shared by its batch pairs inside one chunk); a single channel that is too large is cut over batch pairs.
-constexpr size_t kPlaneBudget = size_t(40) << 20;
+// Composite sizes can run chunk by chunk: `sets` plane sets of one chunk take at most ~kPlaneBudget bytes.  Channels
+// first (the k_f rows of a channel are then shared by its batch pairs inside one chunk); a single channel that is too
+// large is cut over batch pairs.  Measured (profiles/r2_chunking.md): L2-sized chunks (40 MB, planes resident in the
+// 126 MB L2) LOSE — C3 0.72 -> 1.00 ms, C4 0.85 -> 1.23 ms, C5 1.16 -> 2.52 ms — because every chunk pays the launch
+// gaps, prologues and tails of 3-5 small persistent launches.  The budget therefore only bounds the workspace (and with
+// it the peak memory of a call): 4 GB of plane sets per chunk.
+constexpr size_t kPlaneBudget = size_t(4) << 30;
 static View chunk_view(const bffc_plan* p, int B, int H, int sets) {
   const size_t item = size_t(sets) * p->N * 4;                     // one (pair, channel) in all plane sets
   size_t items = kPlaneBudget / item;
@@ -684,9 +686,7 @@ static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const
                         const PassOpts& po = PassOpts()) {
   if (p->order == 2) {
     if (pregate || postgate || po.y2) return fail(BFFC_ERR_UNSUPPORTED, "gated seqlen-8192 calls are not wired to fwd4 yet");
-    const uint8_t* u1 = static_cast<const uint8_t*>(u) + size_t(H) * L * 2;      // member b + 1 of a pair
-    uint8_t* y1 = static_cast<uint8_t*>(y) + size_t(H) * L * 2;
-    return launch_fwd4(p, u, u1, y, y1, kf, B, H, L, 0, po.conj, dbg, st);
+    return launch_fwd4(p, u, u, y, y, kf, B, H, L, 0, po.conj, dbg, st);    // both members of a pair through one map
   }
   if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen <= 8192 in this build", L);
   const bool small = p->N < kInner;

@@ -44,6 +44,11 @@ def main():
         rl2 = np.linalg.norm(got - ref) / np.linalg.norm(ref)
         print(f'stage {s} {names[s]:12s} max|ref|={sc:.4e} max err={err:.4e} rel-L2={rl2:.3e}', flush=True)
         if rl2 > 2e-2:
+            # error map: rel-L2 per (32-lane block, 16-column block)
+            em = [[np.linalg.norm(got[32 * a:32 * a + 32, 16 * b:16 * b + 16] - ref[32 * a:32 * a + 32, 16 * b:16 * b + 16]) /
+                   (np.linalg.norm(ref[32 * a:32 * a + 32, 16 * b:16 * b + 16]) + 1e-30) for b in range(8)] for a in range(4)]
+            for a in range(4):
+                print('   lanes %3d..: ' % (32 * a) + ' '.join('%.2f' % e for e in em[a]))
             bad = np.argwhere(np.abs(got - ref) > 5e-2 * sc)
             print('   first bad (lane,col):', bad[:8].tolist(), ' n_bad', len(bad))
             for r in (0, 1, 9, 64):
