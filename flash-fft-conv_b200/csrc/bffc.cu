@@ -737,13 +737,26 @@ static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const
   return BFFC_OK;
 }
 
-// fwd4: (rows, L) 16-bit viewed as [row][a = n >> 9][th = (n >> 6) & 7][64]; box = the 16 rows (a) of one th, 128B
-// swizzle; a >= L/512 is out of bounds: zero fill on load (implicit padding), dropped on store.  L % 512 == 0.
-static int make_map_r16(const bffc_plan* p, CUtensorMap* map, const void* base, int rows, int L) {
+// fwd4: (rows, L) 16-bit viewed as [row][a = n >> 9][th = (n >> 6) & 7][64], 128B swizzle; a >= L/512 is out of bounds:
+// zero fill on load (implicit padding), dropped on store.  L % 512 == 0.  The kernel wants a plane in shared memory as
+// rows (th major, a minor).  Preferred: ONE box per plane from a map whose dimensions are ordered (64, a, th, row), i.e.
+// with a NON-monotonic stride list (1024, 128, 2L bytes); if the driver rejects that, eight boxes (one per th) from
+// the map ordered (64, th, a, row).  Returns 1 in *one_box for the first form.
+static int make_map_r16(const bffc_plan* p, CUtensorMap* map, const void* base, int rows, int L, int* one_box) {
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  {
+    cuuint64_t dims[4] = {64, cuuint64_t(L / 512), 8, cuuint64_t(rows)};
+    cuuint64_t strides[3] = {1024, 128, cuuint64_t(L) * 2};
+    cuuint32_t box[4] = {64, 16, 8, 1};
+    CUresult r = g_encode(map, map_dtype(p), 4, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS && (*one_box != 0)) { *one_box = 1; return 0; }
+  }
+  *one_box = 0;
   cuuint64_t dims[4] = {64, 8, cuuint64_t(L / 512), cuuint64_t(rows)};
   cuuint64_t strides[3] = {128, 1024, cuuint64_t(L) * 2};
   cuuint32_t box[4] = {64, 1, 16, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode(map, map_dtype(p), 4, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -758,10 +771,13 @@ static int launch_fwd4(const bffc_plan* p, const void* in0, const void* in1, voi
   if (L % 512 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 512 for seqlen 8192 in this build", L);
   const int pairs = (B + 1) / 2, rows = planes ? pairs * H : B * H;
   CUtensorMap ti0, ti1, to0, to1;
-  if (int rc = make_map_r16(p, &ti0, in0, rows, L)) return rc;
-  if (int rc = make_map_r16(p, &ti1, in1, rows, L)) return rc;
-  if (int rc = make_map_r16(p, &to0, out0, rows, L)) return rc;
-  if (int rc = make_map_r16(p, &to1, out1, rows, L)) return rc;
+  // BFFC_FWD4_BOXES=8 (bring-up): force the eight-box form for an A/B of the two map layouts
+  static const int force8 = getenv("BFFC_FWD4_BOXES") && getenv("BFFC_FWD4_BOXES")[0] == '8';
+  int one_box = force8 ? 0 : 1;
+  if (int rc = make_map_r16(p, &ti0, in0, rows, L, &one_box)) return rc;
+  if (int rc = make_map_r16(p, &ti1, in1, rows, L, &one_box)) return rc;
+  if (int rc = make_map_r16(p, &to0, out0, rows, L, &one_box)) return rc;
+  if (int rc = make_map_r16(p, &to1, out1, rows, L, &one_box)) return rc;
   bffc::Fwd4Params prm;
   prm.kf = static_cast<const uint32_t*>(kf);
   prm.bmats = p->bmats;
@@ -771,6 +787,7 @@ static int launch_fwd4(const bffc_plan* p, const void* in0, const void* in1, voi
   prm.B = B; prm.H = H; prm.pairs = pairs;
   prm.units = H * pairs;
   prm.planes = planes;
+  prm.one_box = one_box;
   prm.dbg = dbg;
   if (dbg) prm.units = 1;
   using namespace bffc::r16;

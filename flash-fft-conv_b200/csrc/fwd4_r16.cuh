@@ -25,8 +25,11 @@
 //   S3 radix 32 over n[4:0]   ->  P3 * k_f (engine order v2)   ->  S3' inverse radix 32 (row local, K-major A)
 //   P4 * conj W_8192^{c (q1 + 16 q2)}  ->  S2' inverse radix 16  ->  P5 (transposing) * conj W_256^{b q1}
 //   S1' inverse radix 16      ->  P6 (transposing) 16-bit tiles ->  TMA store
-// Machine mapping as fwd3_r128.cuh: one persistent CTA per SM, three independent pipelines of one warpgroup, two
-// 32 KB tile slots per pipeline (current unit, prefetched next unit), one 128-column fp32 accumulator each.
+// Machine mapping: one persistent CTA per SM, FOUR independent pipelines of one warpgroup (no DFT matrix lives in TMEM,
+// so all 512 columns are accumulators: 4 x 128), and a ring of six 32 KB tile slots shared by them: the CTA's units are
+// numbered j = 0, 1, ...; unit j runs on pipeline j % 4 in slot j % 6, so four slots are being worked on while two
+// receive the next units.  A slot is handed from its previous user (unit j - 6, the partner pipeline (j + 2) % 4) to the
+// pipeline that loads unit j through a "free" mbarrier, armed when the TMA store of unit j - 6 has read the slot.
 #pragma once
 #include "fwd3_r128.cuh"
 
@@ -42,6 +45,7 @@ struct Fwd4Params {
   int pairs;                 // ceil(B/2) (planes mode: complex rows per k_f row)
   int units;                 // H * pairs
   int planes;                // 1: unit = complex row `pr * H + h` of two planes
+  int one_box;               // 1: the tensor maps deliver a whole plane (rows th-major) as ONE box; 0: eight boxes (one per th)
   float* dbg;                // bring-up: TMEM image after every stage [6][128][128] of unit 0
 };
 
@@ -49,9 +53,10 @@ namespace r16 {
 
 using namespace r128;       // tile geometry (kTileBytes, kSlotBytes), atile_desc
 
-constexpr int kThreads4 = 384;
-constexpr int kPipes4 = 3;
-constexpr int kSmemData4 = kPipes4 * 2 * kSlotBytes;
+constexpr int kPipes4 = 4;
+constexpr int kThreads4 = 128 * kPipes4;
+constexpr int kSlots4 = 6;
+constexpr int kSmemData4 = kSlots4 * kSlotBytes;
 // DFT operand images, K-major without swizzle: [N rows][16 K] per K step, 8 x 16-byte core matrices
 //   FWD16[chunk 0..3][plane]  4 x 2 x 1 KB   (W16^{k q} * W_64^{q chunk}: forward radix 16 + folded chunk twiddle)
 //   INV16[plane]              2 x 1 KB
@@ -59,7 +64,7 @@ constexpr int kSmemData4 = kPipes4 * 2 * kSlotBytes;
 //   INV32[plane][kstep]       2 x 2 x 2 KB
 constexpr int kOffF16 = 0, kOffI16 = 8192, kOffF32 = 10240, kOffI32 = 18432, kBmatBytes = 26624;
 constexpr int kTw5Bytes = 16 * 16 * 8;
-constexpr int kSmemBars4 = 128;
+constexpr int kSmemBars4 = 192;
 constexpr int kSmemTotal4 = kSmemData4 + kBmatBytes + kTw5Bytes + kSmemBars4 + 1024;
 
 DEVINL constexpr uint32_t idesc_mn(int fmt, int n) {     // A MN-major, B K-major
@@ -87,9 +92,6 @@ DEVINL void stmatrix_x4_trans(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t 
                "r"(r3)
                : "memory");
 }
-DEVINL void tma_store_4d_nb(const void* map, uint32_t src_smem, int c0, int c1, int c2, int c3) {
-  tma_store_4d(map, src_smem, c0, c1, c2, c3);
-}
 
 // tm_*0 / tm_*1: 4-D maps [sequence][a = n >> 9][th = (n >> 6) & 7][64] of the two members of a pair (planes mode:
 // real / imaginary plane); a box is the 16 rows (a) of one th.
@@ -113,20 +115,18 @@ fwd4_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ 
   const int wl = tid & 31;                                    // lane in warp
   const bool lead_warp = lane < 32;
 
-  const uint32_t bar_tma0 = s_bars + pipe * 24;
-  const uint32_t bar_mma = s_bars + pipe * 24 + 16;
-  const uint32_t bar_c = s_bars + 80;
-  const uint32_t s_tmemptr = s_bars + 96;
+  // barriers: full[slot] (TMA load landed), free[slot] (TMA store of the slot's previous unit has read it), mma[pipe]
+  const uint32_t bar_full0 = s_bars, bar_free0 = s_bars + 48;
+  const uint32_t bar_mma = s_bars + 96 + pipe * 8;
+  const uint32_t bar_c = s_bars + 128;
+  const uint32_t s_tmemptr = s_bars + 136;
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_in0); tma_prefetch_desc(&tm_in1);
     tma_prefetch_desc(&tm_out0); tma_prefetch_desc(&tm_out1);
     mbar_init(bar_c, 1);
-  }
-  if (lane == 0) {
-    mbar_init(bar_tma0, 1);
-    mbar_init(bar_tma0 + 8, 1);
-    mbar_init(bar_mma, 1);
+    for (int i = 0; i < kSlots4; ++i) { mbar_init(bar_full0 + 8 * i, 1); mbar_init(bar_free0 + 8 * i, 1); }
+    for (int i = 0; i < kPipes4; ++i) mbar_init(s_bars + 96 + 8 * i, 1);
     fence_barrier_init();
   }
   if (tid < 32) {
@@ -136,14 +136,12 @@ fwd4_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + kSmemData4 + kBmatBytes + kTw5Bytes + 96);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + kSmemData4 + kBmatBytes + kTw5Bytes + 136);
   const uint32_t tlane = tmem_base + (uint32_t(wq * 32) << 16);
 
-  const int gp = blockIdx.x * kPipes4 + pipe;
-  const int GP = gridDim.x * kPipes4;
-  const int u_begin = int((long long)p.units * gp / GP);
-  const int u_end = int((long long)p.units * (gp + 1) / GP);
-  const uint32_t s_slot0 = sbase + pipe * 2 * kSlotBytes;
+  // units of this CTA: [c_begin, c_begin + NU); local unit j -> pipeline j % kPipes4, slot j % kSlots4
+  const int c_begin = int((long long)p.units * blockIdx.x / gridDim.x);
+  const int NU = int((long long)p.units * (blockIdx.x + 1) / gridDim.x) - c_begin;
 
   // sequence (row) index of member `which` of a unit; beyond the batch: row B*H is out of bounds -> zero fill / dropped
   auto seq_index = [&](int unit, int which) {
@@ -152,18 +150,31 @@ fwd4_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ 
     const int b = 2 * pr + which;
     return b < p.B ? b * p.H + h : p.B * p.H;
   };
-  // 16 boxes per unit (2 members x 8 th), one per lane of the lead warp
-  auto issue_load = [&](int unit, int slot) {
-    const uint32_t bar = bar_tma0 + 8 * slot;
-    const uint32_t dst = s_slot0 + slot * kSlotBytes;
-    if (wl == 0) mbar_expect_tx(bar, kSlotBytes);
-    __syncwarp();
-    if (wl < 16) {
-      const int which = wl >> 3, th = wl & 7;
-      tma_load_4d(dst + which * kTileBytes + th * 2048, which ? &tm_in1 : &tm_in0, bar, 0, th, 0, seq_index(unit, which));
+  // TMA traffic of a pipeline is issued by one elected lane of its SECOND warp, so that the MMA-issuing lead warp never
+  // sits behind it (one box per plane; eight when the driver rejects the th-major map, see make_map_r16)
+  const bool tma_warp = (lane >> 5) == 1;
+  auto issue_load = [&](int j) {            // local unit j into its slot
+    const int unit = c_begin + j, slot = j % kSlots4;
+    const uint32_t bar = bar_full0 + 8 * slot;
+    const uint32_t dst = sbase + slot * kSlotBytes;
+    mbar_expect_tx(bar, kSlotBytes);
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const CUtensorMap* tm = which ? &tm_in1 : &tm_in0;
+      const int sq = seq_index(unit, which);
+      if (p.one_box) tma_load_4d(dst + which * kTileBytes, tm, bar, 0, 0, 0, sq);
+      else
+        for (int th = 0; th < 8; ++th) tma_load_4d(dst + which * kTileBytes + th * 2048, tm, bar, 0, th, 0, sq);
     }
   };
-  if (lead_warp && u_begin < u_end) issue_load(u_begin, 0);
+  // all six slots start free: the first unit of this pipeline and, for the pipelines that own them, units kPipes4..5
+  if (tma_warp) {
+    if (elect_one()) {
+      if (pipe < NU) issue_load(pipe);
+      if (pipe + kPipes4 < kSlots4 && pipe + kPipes4 < NU) issue_load(pipe + kPipes4);
+    }
+    __syncwarp();
+  }
   if (tid == 0) {
     mbar_expect_tx(bar_c, kBmatBytes + kTw5Bytes);
     for (int c = 0; c < kBmatBytes; c += 2048) bulk_load(s_b + c, p.bmats + c, 2048, bar_c);
@@ -243,27 +254,21 @@ fwd4_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ 
 
   if (lead_warp) mbar_wait(bar_c, 0);      // DFT operands have landed (hidden behind the seed set-up)
 
-  for (int unit = u_begin, n = 0; unit < u_end; ++unit, ++n) {
-    const int slot = n & 1;
-    const uint32_t sX = s_slot0 + slot * kSlotBytes;
+  for (int j = pipe; j < NU; j += kPipes4) {
+    const int unit = c_begin + j, slot = j % kSlots4;
+    const uint32_t sX = sbase + slot * kSlotBytes;
     const int h = unit / p.pairs;
     const bool first = kDebug && unit == 0;
 
     // ---------------- S1: radix 16 over the top time digit (raw tiles, rows (t, h, a))
     if (lead_warp) {
-      mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
+      mbar_wait(bar_full0 + 8 * slot, (j / kSlots4) & 1);
       tc_fence_after();
       if (elect_one()) {
         issue_r16(sX, false);
         mma_commit(bar_mma);
       }
       __syncwarp();
-      // prefetch the next unit into the other slot (its last reader, the previous unit's TMA store, was issued a
-      // whole unit ago)
-      if (unit + 1 < u_end) {
-        tma_store_wait_read0();
-        issue_load(unit + 1, slot ^ 1);
-      }
     }
     wait_mma();
     dump(first);
@@ -360,6 +365,17 @@ fwd4_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ 
         mma_commit(bar_mma);
       }
       __syncwarp();
+    }
+    // prefetch this pipeline's next unit (half a unit of lead time covers HBM latency many times over)
+    if (tma_warp) {
+      const int jn = j + kPipes4;          // this pipeline's next unit (units below kSlots4 were loaded at the start)
+      if (jn < NU && jn >= kSlots4) {
+        if (elect_one()) {
+          mbar_wait(bar_free0 + 8 * (jn % kSlots4), (jn / kSlots4 - 1) & 1);     // slot released by unit jn - 6
+          issue_load(jn);
+        }
+        __syncwarp();
+      }
     }
     // k_f of this lane: 16 vectors of 4 complex; the first half (chunk q1_hi = 0) is requested before the MMA wait
     const uint4* kfp = reinterpret_cast<const uint4*>(p.kf) + size_t(h) * 16 * 128 + lane;
@@ -554,19 +570,28 @@ fwd4_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ 
       }
     }
     sync_pipe_smem();
-    if (lead_warp) {
-      if (wl < 16) {
-        const int which = wl >> 3, th = wl & 7;
+    if (tma_warp) {
+      if (elect_one()) {
         const int pr = unit - h * p.pairs;
-        if (p.planes || 2 * pr + which < p.B)
-          tma_store_4d(which ? &tm_out1 : &tm_out0, sX + which * kTileBytes + th * 2048, 0, th, 0, seq_index(unit, which));
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+          if (!(p.planes || 2 * pr + which < p.B)) break;
+          const CUtensorMap* tm = which ? &tm_out1 : &tm_out0;
+          const int sq = seq_index(unit, which);
+          if (p.one_box) tma_store_4d(tm, sX + which * kTileBytes, 0, 0, 0, sq);
+          else
+            for (int th = 0; th < 8; ++th) tma_store_4d(tm, sX + which * kTileBytes + th * 2048, 0, th, 0, sq);
+        }
         tma_store_commit();
+        // release the slot as soon as the store has read it (this lane would otherwise idle in the next unit's stage 1)
+        tma_store_wait_read0();
+        mbar_arrive(bar_free0 + 8 * slot);
       }
       __syncwarp();
     }
   }
 
-  if (lead_warp) tma_store_wait_all0();
+  if (tma_warp) tma_store_wait_all0();
   tc_fence_before();
   __syncthreads();
   if (tid < 32) tmem_dealloc(tmem_base, 512);
