@@ -132,8 +132,7 @@ DEVINL int pos_of_freq(int f) { return 512 * (f & 15) + 32 * ((f >> 4) & 15) + (
 // grid = ceil(H / 2): channels 2*blockIdx.x (real part) and 2*blockIdx.x + 1 (imaginary part)
 template <int kFmt>
 __global__ void __launch_bounds__(kThreads, 3) kf_from_filter_kernel(const float* __restrict__ k, int Lk, uint4* __restrict__ kf_eng,
-                                                                     int H, float scale, int conj, const float2* __restrict__ tw,
-                                                                     int order) {
+                                                                     int H, float scale, int conj, const float2* __restrict__ tw) {
   extern __shared__ float2 fbuf[];
   const int tid = threadIdx.x, ha = 2 * blockIdx.x, hb = ha + 1;
   const float* ka = k + size_t(ha) * Lk;
@@ -142,8 +141,8 @@ __global__ void __launch_bounds__(kThreads, 3) kf_from_filter_kernel(const float
     fbuf[slot(n)] = n < Lk ? make_float2(ka[n], hb < H ? kb[n] : 0.f) : make_float2(0.f, 0.f);
   __syncthreads();
   fft8192<-1>(fbuf, tid, tw);
-  // K_a[f] = (Z[f] + conj Z[-f]) / 2,  K_b[f] = (Z[f] - conj Z[-f]) / (2i); engine vector v = c*128 + lane holds the four
-  // frequencies engine_inner_freq(order, c, lane, j), j = 0..3, as (re01, im01, re23, im23)
+  // K_a[f] = (Z[f] + conj Z[-f]) / 2,  K_b[f] = (Z[f] - conj Z[-f]) / (2i); engine vector v = c*128 + k1 holds
+  // frequencies k1 + 128 (4c + j), j = 0..3, as (re01, im01, re23, im23)
   using NT = Num<kFmt>;
   const float sa = 0.5f * scale, sgn = conj ? -1.f : 1.f;
   for (int v = tid; v < kN / 4; v += kThreads) {
@@ -151,8 +150,7 @@ __global__ void __launch_bounds__(kThreads, 3) kf_from_filter_kernel(const float
     float2 A[4], Bv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int f = order == 1 ? k1 + 128 * (4 * c + j)
-                               : (8 * (c >> 3) + ((k1 >> 3) & 7)) + 16 * (8 * (k1 >> 6) + (k1 & 7)) + 256 * (4 * (c & 7) + j);
+      const int f = k1 + 128 * (4 * c + j);
       const float2 z = fbuf[slot(pos_of_freq(f))], zc = fbuf[slot(pos_of_freq((kN - f) & (kN - 1)))];
       A[j] = make_float2((z.x + zc.x) * sa, (z.y - zc.y) * sa * sgn);
       Bv[j] = make_float2((z.y + zc.y) * sa, (zc.x - z.x) * sa * sgn);
