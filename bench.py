@@ -37,6 +37,11 @@ WORKLOADS = {
     'c3': (32768, 8, 1024, 16384, True),      # configs[2]: Hyena-style, gated, implicit 2x causal padding
     'c4': (1048576, 2, 128, 1048576, False),  # configs[3]: HyenaDNA long range, B x H shard over 1..4 GPUs
     'c5': (4194304, 8, 64, 4194304, False),   # configs[4]: 8 x B200 B x H shard (H = 64 / n_gpus per rank)
+    # the shape of the reference's own published table (README.md:224-231: gated conv, forward, "batch size 64, hidden
+    # dimension 768", H100-SXM: 0.29 ms at N=1K, 3.58 ms at N=8K) — the small-size path (folded linear convolution in
+    # the 8192-point engine) and the gated 8192 kernel get a measured line too
+    'r1k': (1024, 64, 768, 1024, True),
+    'r8k': (8192, 64, 768, 8192, True),
 }
 STRONG = ('c4', 'c5')          # sharded over ranks (strong scaling); c2 / c3 are per-rank (weak)
 
@@ -385,7 +390,7 @@ def run_ours(args):
         cx.sampler.stop()
     configs = {head_name: head}
     if args.workload is None:
-        for name in ('c3', 'c4', 'c5'):
+        for name in ('c3', 'c4', 'c5', 'r1k', 'r8k'):
             torch.cuda.empty_cache()
             try:
                 configs[name] = measure(cx, name, max(3, min(args.steps, 5)), 3)

@@ -71,7 +71,8 @@ dkf3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   const int wg = __shfl_sync(0xffffffffu, tid >> 7, 0);     // warpgroup = column quarter (warp-uniform)
   const int lane = tid & 127;                               // TMEM lane = k1
   const int warp_q = (tid >> 5) & 3;
-  const bool issuer_warp = (tid >> 5) == kComputeWarps;     // first warp of the fifth warpgroup
+  const bool issuer_warp = (tid >> 5) == kComputeWarps;     // first warp of the fifth warpgroup: stage 1 + loads
+  const bool issuer2_warp = (tid >> 5) == kComputeWarps + 1;  // second warp: stage 2
   const bool compute = tid < 512;
 
   // barriers: TMA full [which: u/d][slot]; MMA done: stage 1 of u, stage 1 of dout, stage 2 (both); DFT-64 tiles;
@@ -79,6 +80,7 @@ dkf3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   const uint32_t bar_tma_u = s_bars, bar_tma_d = s_bars + 16;
   const uint32_t bar_s1u = s_bars + 32, bar_s1d = s_bars + 40, bar_s2 = s_bars + 48, bar_g = s_bars + 56;
   const uint32_t bar_p1u = s_bars + 72, bar_p1d = s_bars + 80, bar_acc = s_bars + 88;
+  const uint32_t bar_s1u_odd = s_bars + 96;          // stage 1 of u completes on bar_s1u (even pairs) / bar_s1u_odd (odd pairs)
   const uint32_t s_tmemptr = s_bars + 64;
 
   if (tid == 0) {
@@ -87,6 +89,7 @@ dkf3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     if (kPlanes) { tma_prefetch_desc(&tm_ui); tma_prefetch_desc(&tm_di); }
     for (int i = 0; i < 8; ++i) mbar_init(s_bars + 8 * i, 1);
     mbar_init(bar_p1u, kComputeWarps); mbar_init(bar_p1d, kComputeWarps); mbar_init(bar_acc, kComputeWarps);
+    mbar_init(bar_s1u_odd, 1);
     fence_barrier_init();
   }
   if (tid < 32) {
@@ -156,7 +159,7 @@ dkf3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 
   if (!compute) {
     // ======================================================================================= issuer warpgroup
-    if (!issuer_warp || n_units == 0) return;
+    if ((!issuer_warp && !issuer2_warp) || n_units == 0) return;
     const uint32_t tC0 = tmem_base + kColC, tS0 = tmem_base + kColS;
     // stage 1 (TS): D = F128 * X, X = the two tiles of a slot
     auto issue_s1 = [&](uint32_t sX, uint32_t tD0) {
@@ -187,7 +190,31 @@ dkf3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
       for (int s = 0; s < 4; ++s) mma_ss(tD0, dAi + 2 * s, dG1 + 128 * s, ID_N128_MN, 1);
     };
-    mbar_wait(bar_g, 0);
+    // Two issuing warps.  A single thread that waits on every hand-over, issues all 64 MMAs of a pair and the TMA loads
+    // runs ~600 dependent uniform-datapath instructions per pair: 7.2 k cycles against the 3.1 k cycles of tensor work
+    // it has to feed (profiles/r2_dkf3_ncu_summary.txt: tensor pipe 42 % active, compute warps waiting on stage
+    // completions).  Warp 16 issues stage 1 of both inputs and the loads, warp 17 stage 2.  Stage 1 of u(n+1) is queued
+    // right behind stage 1 of dout(n) (its accumulator held dout(n-1): free since acc(n-1)); because that lets its
+    // completion overtake slow observers of stage 1 of u(n), the two alternate between two barriers.
+    auto s1u_bar = [&](int n) { return (n & 1) ? bar_s1u_odd : bar_s1u; };
+    if (issuer2_warp) {
+      mbar_wait(bar_g, 0);
+      for (int n = 0; n < n_units; ++n) {
+        const uint32_t par = n & 1;
+        mbar_wait(bar_p1u, par);
+        tc_fence_after();
+        if (elect_one()) issue_s2(s_au, tmem_base + dcol(2 * n));
+        __syncwarp();
+        mbar_wait(bar_p1d, par);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_s2(s_ad, tmem_base + dcol(2 * n + 1));
+          mma_commit(bar_s2);                         // this thread's MMAs: stage 2 of u(n) and of dout(n)
+        }
+        __syncwarp();
+      }
+      return;
+    }
     mbar_wait(bar_tma_u, 0);
     tc_fence_after();
     if (elect_one()) {
@@ -207,36 +234,22 @@ dkf3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         mma_commit(bar_s1d);
       }
       __syncwarp();
-      // stage 1 of u(n) has consumed its slot: fetch pair n+2 into it
-      mbar_wait(bar_s1u, par);
-      if (n + 2 < n_units) {
-        if (elect_one()) issue_load(n + 2, 0);
-        __syncwarp();
-      }
-      // stage 2 of u(n) once every compute warp has written its part of the A tiles
-      mbar_wait(bar_p1u, par);
-      tc_fence_after();
-      if (elect_one()) issue_s2(s_au, tmem_base + dcol(2 * n));
-      __syncwarp();
-      mbar_wait(bar_s1d, par);
-      if (n + 2 < n_units) {
-        if (elect_one()) issue_load(n + 2, 1);
-        __syncwarp();
-      }
-      mbar_wait(bar_p1d, par);
-      tc_fence_after();
-      if (elect_one()) {
-        issue_s2(s_ad, tmem_base + dcol(2 * n + 1));
-        mma_commit(bar_s2);                         // covers stage 2 of u(n) as well
-      }
-      __syncwarp();
-      if (n + 1 < n_units) {                        // stage 1 of u(n+1) into the third accumulator (free since acc(n-1))
+      if (n + 1 < n_units) {                          // stage 1 of u(n+1) into the third accumulator
         mbar_wait(bar_tma_u + 8 * (slot ^ 1), ((n + 1) >> 1) & 1);
         tc_fence_after();
         if (elect_one()) {
           issue_s1(sbase + (slot ^ 1) * kSlotBytes, tmem_base + dcol(2 * n + 2));
-          mma_commit(bar_s1u);
+          mma_commit(s1u_bar(n + 1));                 // fires when this thread's earlier MMAs (incl. dout(n)) are done too
         }
+        __syncwarp();
+      }
+      // input slots are free once their stage 1 has run: fetch pair n+2 into them
+      if (n + 2 < n_units) {
+        mbar_wait(s1u_bar(n), (n >> 1) & 1);
+        if (elect_one()) issue_load(n + 2, 0);
+        __syncwarp();
+        mbar_wait(bar_s1d, par);
+        if (elect_one()) issue_load(n + 2, 1);
         __syncwarp();
       }
     }
@@ -294,7 +307,7 @@ dkf3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     const uint32_t par = n & 1;                     // every per-pair barrier completes once per pair
     const uint32_t tDu = tlane + dcol(2 * n), tDd = tlane + dcol(2 * n + 1);
     // ---- pass 1 of u(n), of dout(n).  The A buffers are free: this thread saw stage 2 of pair n-1 complete (bar_s2).
-    mbar_wait(bar_s1u, par);
+    mbar_wait((n & 1) ? bar_s1u_odd : bar_s1u, (n >> 1) & 1);
     tc_fence_after();
     pass1(tDu, s_au);
     hand_over(bar_p1u);
