@@ -172,6 +172,15 @@ __global__ void fold_kernel(const uint4* __restrict__ t, const uint4* __restrict
   y[r * per + v] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+template <int kFmt>
+__global__ void gate_mul1_kernel(const uint4* __restrict__ a, const uint4* __restrict__ g, uint4* __restrict__ o, size_t nvec) {
+  using NT = bffc::Num<kFmt>;
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  const uint4 x = a[i], y = g[i];
+  o[i] = make_uint4(NT::hmul2(x.x, y.x), NT::hmul2(x.y, y.y), NT::hmul2(x.z, y.z), NT::hmul2(x.w, y.w));
+}
+
 // o0 = a0 * g0, o1 = a1 * g1 elementwise in the 16-bit format (gated loads of the dk_f kernel, seqlen <= 8192)
 template <int kFmt>
 __global__ void gate_mul2_kernel(const uint4* __restrict__ a0, const uint4* __restrict__ g0, uint4* __restrict__ o0,
@@ -463,6 +472,17 @@ int bffc_dkf_unpack(const bffc_plan* p, const void* dkf_engine, void* dkf_natura
   return BFFC_OK;
 }
 
+int bffc_dkf_unpack_half(const bffc_plan* p, const void* dkf_engine, void* dkf_half, int H, void* stream) {
+  if (!p || !dkf_engine || !dkf_half || H <= 0) return fail(BFFC_ERR_INVALID, "bffc_dkf_unpack_half: bad argument");
+  const int R0 = p->nlev >= 1 ? p->lev[0].R : 1, R1 = p->nlev >= 2 ? p->lev[1].R : 1, R = R0 * R1;
+  dim3 grid(R < 32 ? 1 : R / 32, 128 * 2, H);
+  bffc::r128::dkf_unpack_half_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float2*>(dkf_engine), static_cast<float2*>(dkf_half), p->NE, R0, R1,
+      p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 128.0f * float(p->R));       // fp16: as bffc_dkf_unpack
+  CUDA_TRY(cudaGetLastError());
+  return BFFC_OK;
+}
+
 }  // extern "C"
 
 // Composite sizes keep the outer stage's output as two bf16 planes (real, imaginary) of pairs*H*N elements.
@@ -499,11 +519,17 @@ static View chunk_view(const bffc_plan* p, int B, int H, int sets) {
 // u*pregate and dout*postgate for the dk_f kernel of a gated backward at seqlen <= 8192 (two (B,H,L) tensors)
 static size_t gate_scratch_bytes(int B, int H, int L) { return 2 * ((size_t(B) * H * L * 2 + 255) & ~size_t(255)); }
 
+static size_t small_fold_bytes(const bffc_plan* p, int B, int H) {
+  const int S = 4096 / p->N, G = (B + 2 * S - 1) / (2 * S);
+  return size_t(H) * G * 2 * kInner * 2;
+}
+
 extern "C" size_t bffc_workspace_bytes_ex(const bffc_plan* p, int B, int H, int L, int gated, int backward) {
   if (!p) return 0;
-  if (p->N < kInner) {   // small sizes: S = 4096/N batch members share one 8192-point slot; scratch of full output tiles
-    const int S = 4096 / p->N, G = (B + 2 * S - 1) / (2 * S);
-    return size_t(H) * G * 2 * kInner * 2 + ((gated && backward) ? gate_scratch_bytes(B, H, L) : 0);
+  if (p->N < kInner) {   // small sizes: S = 4096/N batch members share one 8192-point slot; scratch of full output tiles,
+                         // gated: + u*pregate (one tensor), gated backward: + the two gated inputs of the dk_f kernel
+    return small_fold_bytes(p, B, H) + (gated ? gate_scratch_bytes(B, H, L) / 2 : 0) +
+           ((gated && backward) ? gate_scratch_bytes(B, H, L) : 0);
   }
   if (p->nlev == 0) return (gated && backward) ? gate_scratch_bytes(B, H, L) : 0;
   // plane sets (real + imaginary plane each) of ONE chunk: forward nlev sets; backward nlev + 1 (transformed u and dout)
@@ -875,7 +901,20 @@ static int conv_forward(const bffc_plan* p, const void* u, const void* kf, const
     // S = 4096/N batch members of a channel share one 8192-point slot (spacing 2N), so a unit carries 2S sequences.
     const int off = corr ? kInner - p->N : p->N;
     const SegGeom sg = seg_geom(p, B, L);
-    if (int rc = launch_fused(p, u, kf, pregate, nullptr, ws, B, H, L, nullptr, 0, 0, st, po)) return rc;
+    const void* uin = u;
+    if (pregate) {
+      // gated small sizes: u * pregate by an elementwise pre-pass (reference: __hmul2 on load, monarch_cuda_kernel_bf16.h),
+      // so that the three-pipeline kernel runs them too — measured at B=64 H=768 N=1024: gated two-pipeline kernel 325 us
+      // vs pre-pass + ungated kernel (profiles/r2_launches.md); the postgate is applied by the fold
+      uint8_t* pm = static_cast<uint8_t*>(ws) + small_fold_bytes(p, B, H);
+      const size_t nvec = size_t(B) * H * L / 8;
+      FMT_SWITCH(p->dtype, (gate_mul1_kernel<F><<<unsigned((nvec + 255) / 256), 256, 0, st>>>(
+          static_cast<const uint4*>(u), static_cast<const uint4*>(pregate), reinterpret_cast<uint4*>(pm), nvec)););
+      CUDA_TRY(cudaGetLastError());
+      *launches += 1;
+      uin = pm;
+    }
+    if (int rc = launch_fused(p, uin, kf, nullptr, nullptr, ws, B, H, L, nullptr, 0, 0, st, po)) return rc;
     const size_t rows = size_t(B) * H, total = rows * (L / 8);
     FMT_SWITCH(p->dtype, (fold_kernel<F><<<unsigned((total + 255) / 256), 256, 0, st>>>(
         static_cast<const uint4*>(ws), static_cast<const uint4*>(postgate), static_cast<uint4*>(y),
@@ -985,7 +1024,7 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
     if (gated) {
       // gated loads: u*pregate and dout*postgate (reference: ..._bwd_kernel_bf16.h:505-509,571-581) from an elementwise
       // pre-pass into the tail of the workspace
-      uint8_t* g0 = static_cast<uint8_t*>(workspace) + (p->N < kInner ? bffc_workspace_bytes_ex(p, B, H, L, 0, 0) : 0);
+      uint8_t* g0 = static_cast<uint8_t*>(workspace) + (p->N < kInner ? small_fold_bytes(p, B, H) + gate_scratch_bytes(B, H, L) / 2 : 0);
       uint8_t* g1 = g0 + gate_scratch_bytes(B, H, L) / 2;
       const size_t nvec = size_t(B) * H * L / 8;
       FMT_SWITCH(p->dtype, (gate_mul2_kernel<F><<<unsigned((nvec + 255) / 256), 256, 0, st>>>(

@@ -286,13 +286,13 @@ def _bwd(mod, dout, u, kf_engine, k_len, pregate, postgate):
             dk = torch.empty((H, k_len), dtype=torch.float32, device=u.device)
             _lib.check(_lib.lib().bffc_dk_from_dkf(plan.handle, _ptr(dkf_engine), _ptr(dk), int(k_len), H, _stream()))
             return du, dk, dpre, dpost
-        dkf_nat = torch.empty((H, N), dtype=torch.complex64, device=u.device)
-        _lib.check(_lib.lib().bffc_dkf_unpack(plan.handle, _ptr(dkf_engine), _ptr(torch.view_as_real(dkf_nat)), H,
-                                              _stream()))
-        # the kernel accumulates unnormalised spectra; the inverse FFT's 1/N completes the correlation
-        # (conv.py:1817-1820).  dk is real: a Hermitian inverse (irfft of the first N/2+1 bins) gives the same real part
-        # as ifft(...).real when dk_f is Hermitian, which it is up to the cross terms the .real discards — so keep ifft.
-        dk = torch.fft.ifft(dkf_nat, dim=-1).real[..., :k_len].contiguous()
+        # the kernel accumulates unnormalised pair-packed spectra; the reference takes ifft(dk_f).real[..., :k_len]
+        # (conv.py:1817-1820).  The real part of the inverse transform only sees the Hermitian part of dk_f: the library
+        # writes its N/2 + 1 non-redundant bins in natural order and a real inverse FFT (1/N included) finishes the job.
+        dkf_half = torch.empty((H, N // 2 + 1), dtype=torch.complex64, device=u.device)
+        _lib.check(_lib.lib().bffc_dkf_unpack_half(plan.handle, _ptr(dkf_engine), _ptr(torch.view_as_real(dkf_half)), H,
+                                                   _stream()))
+        dk = torch.fft.irfft(dkf_half, n=N, dim=-1)[..., :k_len].contiguous()
     return du, dk, dpre, dpost
 
 

@@ -93,6 +93,11 @@ int bffc_kf_pack_rfft(const bffc_plan* plan, const void* kf_half, void* kf_engin
                       void* stream);
 int bffc_dkf_unpack(const bffc_plan* plan, const void* dkf_engine, void* dkf_natural, int H,
                     void* stream);
+/* dkf_engine -> dkf_half (H, N/2 + 1) complex64: the non-redundant bins of the Hermitian part (X[k] + conj X[N-k]) / 2 of
+ * the gradient spectrum, natural order, so that dk = irfft(dkf_half, n = N)[:, :Lk] (the real part the reference takes of
+ * its complex inverse FFT, conv.py:1817-1820, at half the transform work). */
+int bffc_dkf_unpack_half(const bffc_plan* plan, const void* dkf_engine, void* dkf_half, int H,
+                         void* stream);
 
 /*
  * Filter-side transforms in one launch each, for plans whose bffc_fft_size() is 8192 (seqlen <= 8192; other plans
