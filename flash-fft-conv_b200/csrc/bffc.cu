@@ -73,6 +73,21 @@ int check_device() {
   return 0;
 }
 
+// column-FFT kernels of the filter side are instantiated per outer size R = N / 8192
+#define COLS_SWITCH(R_, ...)                                                                          \
+  do {                                                                                               \
+    switch (R_) {                                                                                    \
+      case 2: { constexpr int RR = 2; __VA_ARGS__ } break;                                           \
+      case 4: { constexpr int RR = 4; __VA_ARGS__ } break;                                           \
+      case 8: { constexpr int RR = 8; __VA_ARGS__ } break;                                           \
+      case 16: { constexpr int RR = 16; __VA_ARGS__ } break;                                         \
+      case 32: { constexpr int RR = 32; __VA_ARGS__ } break;                                         \
+      case 64: { constexpr int RR = 64; __VA_ARGS__ } break;                                         \
+      case 128: { constexpr int RR = 128; __VA_ARGS__ } break;                                       \
+      case 256: { constexpr int RR = 256; __VA_ARGS__ } break;                                       \
+      default: { constexpr int RR = 512; __VA_ARGS__ } break;                                        \
+    }                                                                                                \
+  } while (0)
 #define FMT_SWITCH(dtype_, ...)                         \
   do {                                                   \
     if ((dtype_) == BFFC_DTYPE_BF16) { constexpr int F = 1; __VA_ARGS__ } \
@@ -244,6 +259,9 @@ struct bffc_plan {
   __nv_bfloat16* dftS = nullptr;
   uint8_t* gtiles = nullptr;
   float2* tw8192 = nullptr;   // e^{-2 pi i t / 8192}, t < 8192: twiddles of the fp32 filter-side FFTs (filter_fft.cuh)
+  float2* tw512 = nullptr;    // composite sizes: e^{-2 pi i t / 512} (column FFTs), W_N^{j} j < 2048, W_N^{2048 i} i < N/2048
+  float2* tw_lo = nullptr;
+  float2* tw_hi = nullptr;
   int num_sms = 0;
   // bffc_fwd_host: copy-in / compute / copy-out streams and the per-slot events (created with the plan)
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
@@ -340,14 +358,22 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   PLAN_TRY(cudaMalloc(&p->gtiles, gt.size()));
   PLAN_TRY(cudaMemcpy(p->gtiles, gt.data(), gt.size(), cudaMemcpyHostToDevice));
 
-  if (p->NE == kInner) {
-    std::vector<float2> tw(kInner);
-    for (int t = 0; t < kInner; ++t) {
-      const double a = -2.0 * M_PI * double(t) / double(kInner);
-      tw[t] = make_float2(float(cos(a)), float(sin(a)));
+  {
+    auto table = [&](float2** dst, int n, double period) -> cudaError_t {
+      std::vector<float2> tw(n);
+      for (int t = 0; t < n; ++t) {
+        const double a = -2.0 * M_PI * double(t) / period;
+        tw[t] = make_float2(float(cos(a)), float(sin(a)));
+      }
+      cudaError_t e = cudaMalloc(dst, tw.size() * sizeof(float2));
+      return e != cudaSuccess ? e : cudaMemcpy(*dst, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice);
+    };
+    PLAN_TRY(table(&p->tw8192, kInner, double(kInner)));
+    if (p->NE > kInner) {
+      PLAN_TRY(table(&p->tw512, 512, 512.0));
+      PLAN_TRY(table(&p->tw_lo, 2048, double(p->NE)));
+      PLAN_TRY(table(&p->tw_hi, p->NE / 2048, double(p->NE) / 2048.0));
     }
-    PLAN_TRY(cudaMalloc(&p->tw8192, tw.size() * sizeof(float2)));
-    PLAN_TRY(cudaMemcpy(p->tw8192, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
   }
 
   // engine order of k_f (32-bit words), per channel h: R rows of 8192 words, row = c0*R1 + c1 (outer digits); inside a
@@ -369,6 +395,13 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
     PLAN_TRY(cudaFuncSetAttribute(bffc::ffft::kf_from_filter_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, bffc::ffft::kSmemBytes));
   );
   PLAN_TRY(cudaFuncSetAttribute(bffc::ffft::dk_from_dkf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bffc::ffft::kSmemBytes));
+  if (p->NE > kInner) {
+    using namespace bffc::ffft;
+    FMT_SWITCH(dtype, PLAN_TRY(cudaFuncSetAttribute(filter_rows_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)););
+    PLAN_TRY(cudaFuncSetAttribute(dk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    COLS_SWITCH(p->R, PLAN_TRY(cudaFuncSetAttribute(filter_cols_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, ColRadix<RR>::kSmem));
+                      PLAN_TRY(cudaFuncSetAttribute(dk_cols_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, ColRadix<RR>::kSmem)););
+  }
   // streams / events of bffc_fwd_host (copy-in, compute, copy-out; per-slot events)
   for (auto& st : p->hs) PLAN_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   for (auto& ev : p->hev) PLAN_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -392,6 +425,9 @@ int bffc_plan_destroy(bffc_plan* p) {
   cudaFree(p->dftS);
   cudaFree(p->gtiles);
   cudaFree(p->tw8192);
+  cudaFree(p->tw512);
+  cudaFree(p->tw_lo);
+  cudaFree(p->tw_hi);
   for (auto& st : p->hs) if (st) cudaStreamDestroy(st);
   for (auto& ev : p->hev) if (ev) cudaEventDestroy(ev);
   delete p;
@@ -435,27 +471,85 @@ int bffc_kf_pack_rfft(const bffc_plan* p, const void* kf_half, void* kf_engine, 
 }
 
 // ---------------------------------------------------------------------------------------------- filter-side FFTs
-int bffc_kf_from_filter(const bffc_plan* p, const void* k, int Lk, void* kf_engine, int H, int conj, void* stream) {
+// composite sizes: T = (channels, R/2 + 1, 8192) fp32 complex between the column and the row launch; the host walks the
+// channels in groups whose T fits the workspace (bffc_filter_workspace_bytes sizes it to stay in L2)
+static size_t filter_pair_bytes(const bffc_plan* p) { return size_t(2) * (p->R / 2 + 1) * kInner * sizeof(float2); }
+
+size_t bffc_filter_workspace_bytes(const bffc_plan* p, int H) {
+  if (!p || H <= 0 || p->NE == kInner) return 0;
+  const size_t pairs = size_t(H + 1) / 2, per = filter_pair_bytes(p);
+  // one group when it fits 576 MB (C4: 128 channels x 65 rows x 64 KB = 520 MB): the two launches are latency / issue
+  // bound rather than HBM bound, so fewer, larger launches beat L2-sized groups (profiles/r2_filter_fft.md)
+  size_t group = (size_t(576) << 20) / per;
+  if (group < 1) group = 1;
+  return (pairs < group ? pairs : group) * per;
+}
+
+int bffc_kf_from_filter(const bffc_plan* p, const void* k, int Lk, void* kf_engine, int H, int conj, void* workspace,
+                        size_t workspace_bytes, void* stream) {
   if (!p || !k || !kf_engine || H <= 0 || Lk <= 0) return fail(BFFC_ERR_INVALID, "bffc_kf_from_filter: bad argument");
-  if (p->NE != kInner) return fail(BFFC_ERR_UNSUPPORTED, "bffc_kf_from_filter: engine FFT size %d (only 8192 in this build; use rfft + bffc_kf_pack_rfft)", p->NE);
   if (Lk > p->N) return fail(BFFC_ERR_INVALID, "bffc_kf_from_filter: Lk=%d exceeds seqlen %d", Lk, p->N);
   using namespace bffc::ffft;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f;
-  FMT_SWITCH(p->dtype, (kf_from_filter_kernel<F><<<(H + 1) / 2, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float*>(k), Lk, static_cast<uint4*>(kf_engine), H, scale, conj, p->tw8192)););
+  g_launches = 0;
+  if (p->NE == kInner) {
+    FMT_SWITCH(p->dtype, (kf_from_filter_kernel<F><<<(H + 1) / 2, kThreads, kSmemBytes, st>>>(
+        static_cast<const float*>(k), Lk, static_cast<uint4*>(kf_engine), H, scale, conj, p->tw8192)););
+    CUDA_TRY(cudaGetLastError());
+    g_launches = 1;
+    return BFFC_OK;
+  }
+  const size_t per = filter_pair_bytes(p);
+  if (!workspace || workspace_bytes < per)
+    return fail(BFFC_ERR_INVALID, "bffc_kf_from_filter: workspace %zu B < %zu B (one channel pair; see bffc_filter_workspace_bytes)", workspace_bytes, per);
+  const int group = int(std::min<size_t>(workspace_bytes / per, size_t(H + 1) / 2)) * 2;   // channels per group
+  const int R = p->R, R0 = p->lev[0].R, R1 = p->nlev >= 2 ? p->lev[1].R : 1;
+  float2* T = static_cast<float2*>(workspace);
+  for (int h0 = 0; h0 < H; h0 += group) {
+    const int Hc = std::min(group, H - h0);
+    const float* kc = static_cast<const float*>(k) + size_t(h0) * Lk;
+    uint4* out = static_cast<uint4*>(kf_engine) + size_t(h0) * (p->NE / 4);
+    COLS_SWITCH(R, (filter_cols_kernel<RR><<<dim3(kInner / ColRadix<RR>::kTC, (Hc + 1) / 2), kColThreads, ColRadix<RR>::kSmem, st>>>(
+        kc, Lk, T, Hc, scale, p->tw512, p->tw_lo, p->tw_hi)););
+    FMT_SWITCH(p->dtype, (filter_rows_kernel<F><<<dim3(R / 2 + 1, Hc), kThreads, kSmemBytes, st>>>(T, out, R, R0, R1, conj, p->tw8192)););
+    g_launches += 2;
+  }
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
 
-int bffc_dk_from_dkf(const bffc_plan* p, const void* dkf_engine, void* dk, int Lk, int H, void* stream) {
+int bffc_dk_from_dkf(const bffc_plan* p, const void* dkf_engine, void* dk, int Lk, int H, void* workspace,
+                     size_t workspace_bytes, void* stream) {
   if (!p || !dkf_engine || !dk || H <= 0 || Lk <= 0) return fail(BFFC_ERR_INVALID, "bffc_dk_from_dkf: bad argument");
-  if (p->NE != kInner) return fail(BFFC_ERR_UNSUPPORTED, "bffc_dk_from_dkf: engine FFT size %d (only 8192 in this build; use bffc_dkf_unpack + ifft)", p->NE);
   if (Lk > p->N) return fail(BFFC_ERR_INVALID, "bffc_dk_from_dkf: Lk=%d exceeds seqlen %d", Lk, p->N);
   using namespace bffc::ffft;
-  dk_from_dkf_kernel<<<H, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float2*>(dkf_engine), static_cast<float*>(dk), Lk,
-      p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 128.0f * float(p->R),      // as bffc_dkf_unpack
-      p->N < kInner ? kInner - p->N : 0, p->tw8192);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // fp16: both spectra carry 1/sqrt(128) (fused kernel) and 1/sqrt(R) per outer level: undo the product
+  const float fscale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 128.0f * float(p->R);
+  g_launches = 0;
+  if (p->NE == kInner) {
+    dk_from_dkf_kernel<<<H, kThreads, kSmemBytes, st>>>(static_cast<const float2*>(dkf_engine), static_cast<float*>(dk), Lk,
+                                                         fscale, p->N < kInner ? kInner - p->N : 0, p->tw8192);
+    CUDA_TRY(cudaGetLastError());
+    g_launches = 1;
+    return BFFC_OK;
+  }
+  const size_t per = filter_pair_bytes(p);
+  if (!workspace || workspace_bytes < per)
+    return fail(BFFC_ERR_INVALID, "bffc_dk_from_dkf: workspace %zu B < %zu B (one channel pair; see bffc_filter_workspace_bytes)", workspace_bytes, per);
+  const int group = int(std::min<size_t>(workspace_bytes / per, size_t(H + 1) / 2)) * 2;
+  const int R = p->R, R0 = p->lev[0].R, R1 = p->nlev >= 2 ? p->lev[1].R : 1;
+  float2* T = static_cast<float2*>(workspace);
+  for (int h0 = 0; h0 < H; h0 += group) {
+    const int Hc = std::min(group, H - h0);
+    const float2* in = static_cast<const float2*>(dkf_engine) + size_t(h0) * p->NE;
+    float* out = static_cast<float*>(dk) + size_t(h0) * Lk;
+    dk_rows_kernel<<<dim3(R / 2 + 1, Hc), kThreads, kSmemBytes, st>>>(in, T, R, R0, R1, p->tw8192, p->tw_lo, p->tw_hi);
+    COLS_SWITCH(R, (dk_cols_kernel<RR><<<dim3(kInner / ColRadix<RR>::kTC, (Hc + 1) / 2), kColThreads, ColRadix<RR>::kSmem, st>>>(
+        T, out, Lk, Hc, fscale / float(p->NE), p->tw512)););
+    g_launches += 2;
+  }
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }

@@ -137,8 +137,18 @@ __global__ void __launch_bounds__(kThreads, 3) kf_from_filter_kernel(const float
   const int tid = threadIdx.x, ha = 2 * blockIdx.x, hb = ha + 1;
   const float* ka = k + size_t(ha) * Lk;
   const float* kb = k + size_t(hb < H ? hb : ha) * Lk;
-  for (int n = tid; n < kN; n += kThreads)
-    fbuf[slot(n)] = n < Lk ? make_float2(ka[n], hb < H ? kb[n] : 0.f) : make_float2(0.f, 0.f);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {               // 2 x 16 loads per channel in flight
+    float a[16], b[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int n = tid + (16 * half + i) * kThreads;
+      a[i] = n < Lk ? __ldg(ka + n) : 0.f;
+      b[i] = n < Lk ? __ldg(kb + n) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) fbuf[slot(tid + (16 * half + i) * kThreads)] = make_float2(a[i], hb < H ? b[i] : 0.f);
+  }
   __syncthreads();
   fft8192<-1>(fbuf, tid, tw);
   // K_a[f] = (Z[f] + conj Z[-f]) / 2,  K_b[f] = (Z[f] - conj Z[-f]) / (2i); engine vector v = c*128 + k1 holds
@@ -170,9 +180,10 @@ __global__ void __launch_bounds__(kThreads, 3) dk_from_dkf_kernel(const float2* 
   extern __shared__ float2 fbuf[];
   const int tid = threadIdx.x, h = blockIdx.x;
   const float2* src = dkf_eng + size_t(h) * kN;
+#pragma unroll 16
   for (int e = tid; e < kN; e += kThreads) {
     const int k2l = e & 15, k1 = (e >> 4) & 127, qd = e >> 11;
-    fbuf[slot(k1 + 128 * (16 * qd + k2l))] = src[e];
+    fbuf[slot(k1 + 128 * (16 * qd + k2l))] = __ldg(src + e);
   }
   __syncthreads();
   fft8192<1>(fbuf, tid, tw);
@@ -181,6 +192,272 @@ __global__ void __launch_bounds__(kThreads, 3) dk_from_dkf_kernel(const float2* 
     float c = fbuf[slot(pos_of_freq(n))].x;
     if (fold_off) c += fbuf[slot(pos_of_freq((fold_off + n) & (kN - 1)))].x;
     dk[size_t(h) * Lk + n] = c * s;
+  }
+}
+
+// =====================================================================================================================
+// Composite sizes, N = R * 8192 (R = 2 .. 512): the filter spectrum in two fp32 launches, no library FFT.
+//   n = n1*8192 + n2,  k = rho + R*k''  (rho = k mod R is the engine ROW, k'' the frequency inside the row):
+//   X[rho + R k''] = sum_{n2} W_8192^{n2 k''} * ( W_N^{n2 rho} * sum_{n1} W_R^{n1 rho} x[n1*8192 + n2] )
+//   filter_cols_kernel : the R-point DFTs down the columns n2 (two real channels as one complex column set), Hermitian
+//                        separation, twiddle W_N^{n2 rho}; only rho = 0..R/2 is kept (real input)    -> T (fp32 complex)
+//   filter_rows_kernel : one 8192-point FFT per (channel, rho) in shared memory (fft8192 above), written straight into
+//                        engine row(rho) and, conjugated and reversed, into row(R - rho):
+//                        X[(R - rho) + R k''] = conj X[rho + R (8191 - k'')]
+// T is sized to stay in L2 between the two launches (the host loops over groups of channels).
+// The inverse pair (dk from dk_f, reference conv.py:1817-1820) runs the same two steps backwards.
+// =====================================================================================================================
+template <int SIGN>
+DEVINL void dft8(float2 (&v)[8]) {
+  // m = 2a + b, q = c + 4d:  X[c + 4d] = t0[c] + (-1)^d W_8^{c} t1[c],  t_b = DFT4 over a of x[2a + b]
+  dft4<SIGN>(v[0], v[2], v[4], v[6]);
+  dft4<SIGN>(v[1], v[3], v[5], v[7]);
+  constexpr float r2 = 0.70710678118654752f;
+  const float sg = float(SIGN);
+  v[3] = cmul(v[3], make_float2(r2, sg * r2));
+  v[5] = mul_i<SIGN>(v[5]);
+  v[7] = cmul(v[7], make_float2(-r2, sg * r2));
+  float2 o[8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { o[c] = cadd(v[2 * c], v[2 * c + 1]); o[c + 4] = csub(v[2 * c], v[2 * c + 1]); }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v[q] = o[q];
+}
+
+template <int RADIX, int SIGN>
+DEVINL void dftr(float2 (&v)[RADIX]) {
+  if constexpr (RADIX == 2) { const float2 t = csub(v[0], v[1]); v[0] = cadd(v[0], v[1]); v[1] = t; }
+  else if constexpr (RADIX == 4) dft4<SIGN>(v[0], v[1], v[2], v[3]);
+  else if constexpr (RADIX == 8) dft8<SIGN>(v);
+  else dft16<SIGN>(v);
+}
+
+// radices of the column FFT, outermost first
+template <int R> struct ColRadix {
+  static constexpr int r1 = R >= 16 ? 16 : R;
+  static constexpr int r2 = (R / r1) >= 16 ? 16 : (R / r1);
+  static constexpr int r3 = R / (r1 * r2);
+  static constexpr int kTC = 8192 / R;                            // columns per CTA: a [R][TC] tile of 8192 complex numbers
+  static constexpr int kSmem = R * kTC * 8;
+  // frequency (or, for the inverse, time index) f = q1 + r1 q2 + r1 r2 q3 is left at this row of the tile
+  static DEVINL int pos(int f) { return (f % r1) * (R / r1) + ((f / r1) % r2) * (R / (r1 * r2)) + f / (r1 * r2); }
+};
+
+// one decimation-in-frequency pass of radix RADIX over sub-transforms of length S down the rows of a [R][TC] tile
+constexpr int kColThreads = 512;
+template <int RADIX, int SIGN, int R, int S, int TC>
+DEVINL void col_pass(float2* cb, int tid, const float2* __restrict__ tw512) {
+  constexpr int st = S / RADIX, nb = R / RADIX;
+#pragma unroll 1
+  for (int t = tid; t < nb * TC; t += kColThreads) {
+    const int c = t % TC, bi = t / TC;
+    const int j = bi % st, blk = bi / st;
+    float2* p = cb + (blk * S + j) * TC + c;
+    float2 v[RADIX];
+#pragma unroll
+    for (int m = 0; m < RADIX; ++m) v[m] = p[m * st * TC];
+    dftr<RADIX, SIGN>(v);
+    p[0] = v[0];
+#pragma unroll
+    for (int q = 1; q < RADIX; ++q) {
+      if constexpr (st > 1) {
+        float2 w = __ldg(tw512 + (((512 / S) * j * q) & 511));
+        if (SIGN > 0) w.y = -w.y;
+        v[q] = cmul(v[q], w);
+      }
+      p[q * st * TC] = v[q];
+    }
+  }
+  __syncthreads();
+}
+
+template <int R, int SIGN>
+DEVINL void col_fft(float2* cb, int tid, const float2* __restrict__ tw512) {
+  using P = ColRadix<R>;
+  col_pass<P::r1, SIGN, R, R, P::kTC>(cb, tid, tw512);
+  if constexpr (P::r2 > 1) col_pass<P::r2, SIGN, R, R / P::r1, P::kTC>(cb, tid, tw512);
+  if constexpr (P::r3 > 1) col_pass<P::r3, SIGN, R, R / (P::r1 * P::r2), P::kTC>(cb, tid, tw512);
+}
+
+// W_N^{m}, m < N, from two plan tables: tw_lo[j] = W_N^{j} (j < 2048), tw_hi[i] = W_N^{2048 i}
+DEVINL float2 twiddle_n(int m, const float2* __restrict__ tw_lo, const float2* __restrict__ tw_hi) {
+  return cmul(__ldg(tw_hi + (m >> 11)), __ldg(tw_lo + (m & 2047)));
+}
+
+// grid (8192 / TC, ceil(Hc / 2)), kColThreads.  k: (Hc, Lk) fp32, zero beyond Lk.  T: (Hc, R/2 + 1, 8192) fp32 complex.
+template <int R>
+__global__ void __launch_bounds__(kColThreads) filter_cols_kernel(const float* __restrict__ k, int Lk, float2* __restrict__ T, int Hc,
+                                                                  float scale, const float2* __restrict__ tw512,
+                                                                  const float2* __restrict__ tw_lo, const float2* __restrict__ tw_hi) {
+  using P = ColRadix<R>;
+  constexpr int TC = P::kTC, TC4 = TC / 4, NV = R * TC4 / kColThreads;      // 4 x 16-byte loads per thread and channel
+  extern __shared__ float2 cb[];
+  const int tid = threadIdx.x, n20 = blockIdx.x * TC, ha = 2 * blockIdx.y, hb = ha + 1;
+  const bool two = hb < Hc;
+  const float* ka = k + size_t(ha) * Lk;
+  const float* kb = k + size_t(two ? hb : ha) * Lk;
+  const bool vec = (Lk & 3) == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0;
+  float4 va[NV], vb[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {                       // all loads of the tile in flight before the first use
+    const int e4 = tid + i * kColThreads, n1 = e4 / TC4, c4 = e4 % TC4;
+    const int idx = n1 * kN + n20 + 4 * c4;
+    if (vec && idx + 3 < Lk) {
+      va[i] = __ldg(reinterpret_cast<const float4*>(ka + idx));
+      vb[i] = __ldg(reinterpret_cast<const float4*>(kb + idx));
+    } else {
+      float a[4], b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a[q] = idx + q < Lk ? ka[idx + q] : 0.f; b[q] = idx + q < Lk ? kb[idx + q] : 0.f; }
+      va[i] = make_float4(a[0], a[1], a[2], a[3]);
+      vb[i] = make_float4(b[0], b[1], b[2], b[3]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e4 = tid + i * kColThreads;
+    if (!two) vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* dst = reinterpret_cast<float4*>(cb + 4 * e4);          // row n1, columns 4 c4 .. 4 c4 + 3
+    dst[0] = make_float4(va[i].x, vb[i].x, va[i].y, vb[i].y);
+    dst[1] = make_float4(va[i].z, vb[i].z, va[i].w, vb[i].w);
+  }
+  __syncthreads();
+  col_fft<R, -1>(cb, tid, tw512);
+  const float sa = 0.5f * scale;
+  float2* Ta = T + size_t(ha) * (R / 2 + 1) * kN + n20;
+  float2* Tb = T + size_t(hb) * (R / 2 + 1) * kN + n20;
+#pragma unroll 4
+  for (int e = tid; e < (R / 2 + 1) * TC; e += kColThreads) {
+    const int rho = e / TC, c = e % TC;
+    const float2 z = cb[P::pos(rho) * TC + c], zc = cb[P::pos((R - rho) & (R - 1)) * TC + c];
+    const float2 w = twiddle_n((n20 + c) * rho, tw_lo, tw_hi);
+    const float2 A = make_float2((z.x + zc.x) * sa, (z.y - zc.y) * sa), B = make_float2((z.y + zc.y) * sa, (zc.x - z.x) * sa);
+    Ta[size_t(rho) * kN + c] = cmul(A, w);
+    if (two) Tb[size_t(rho) * kN + c] = cmul(B, w);
+  }
+}
+
+// 8192 complex numbers, global -> fbuf[slot(n)]: 16 coalesced 8-byte loads in flight per thread, conflict-free stores
+DEVINL void load_row(float2* fbuf, const float2* __restrict__ src, int tid) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float2 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __ldg(src + tid + (16 * half + i) * kThreads);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) fbuf[slot(tid + (16 * half + i) * kThreads)] = v[i];
+  }
+}
+
+// engine vector v = c*128 + k1 holds the frequencies f_j = k1 + 128 (4c + j); with k1 fixed per thread (v = tid + 256 i)
+// pos_of_freq(f_j) = 512 (k1 & 15) + 32 ((k1 >> 4) + 8 (j & 1)) + 2c + (j >> 1); the mirrored row reads 8191 - f_j
+template <int kFmt, bool kMirror>
+DEVINL void store_engine_row(const float2* fbuf, uint4* __restrict__ row, int tid, float sgn) {
+  using NT = Num<kFmt>;
+  const int k1 = tid & 127;
+#pragma unroll 4
+  for (int i = 0; i < 8; ++i) {
+    const int c = (tid >> 7) + 2 * i;
+    float2 A[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int p;
+      if (!kMirror) p = 512 * (k1 & 15) + 32 * ((k1 >> 4) + 8 * (j & 1)) + 2 * c + (j >> 1);
+      else {                                            // f' = 8191 - f_j: k1' = 127 - k1, inner (4c + j)' = 63 - (4c + j)
+        const int k1m = 127 - k1, jm = 3 - j, cm = 15 - c;
+        p = 512 * (k1m & 15) + 32 * ((k1m >> 4) + 8 * (jm & 1)) + 2 * cm + (jm >> 1);
+      }
+      A[j] = fbuf[slot(p)];
+    }
+    row[tid + 256 * i] = make_uint4(NT::pack(A[0].x, A[1].x), NT::pack(sgn * A[0].y, sgn * A[1].y),
+                                    NT::pack(A[2].x, A[3].x), NT::pack(sgn * A[2].y, sgn * A[3].y));
+  }
+}
+
+// grid (R/2 + 1, Hc).  kf_eng: (Hc, R rows, 2048 vectors of 16 bytes); row of residue rho = (rho % R0) * R1 + rho / R0
+template <int kFmt>
+__global__ void __launch_bounds__(kThreads, 3) filter_rows_kernel(const float2* __restrict__ T, uint4* __restrict__ kf_eng, int R, int R0,
+                                                                  int R1, int conj, const float2* __restrict__ tw) {
+  extern __shared__ float2 fbuf[];
+  const int tid = threadIdx.x, rho = blockIdx.x, h = blockIdx.y;
+  load_row(fbuf, T + (size_t(h) * (R / 2 + 1) + rho) * kN, tid);
+  __syncthreads();
+  fft8192<-1>(fbuf, tid, tw);
+  const float sgn = conj ? -1.f : 1.f;
+  store_engine_row<kFmt, false>(fbuf, kf_eng + (size_t(h) * R + (rho % R0) * R1 + rho / R0) * (kN / 4), tid, sgn);
+  if (rho == 0 || 2 * rho == R) return;
+  const int rm = R - rho;
+  store_engine_row<kFmt, true>(fbuf, kf_eng + (size_t(h) * R + (rm % R0) * R1 + rm / R0) * (kN / 4), tid, -sgn);
+}
+
+// ---- inverse: dk (Hc, Lk) fp32 from dk_f engine rows (fp32 complex, row layout [quarter 4][k1 128][k2l 16], frequency
+// k'' = k1 + 128 (16 quarter + k2l) — dkf3_r128.cuh).  dk = Re ifft(dk_f): only the Hermitian part of the pair-packed
+// spectrum contributes, G[k] = (D[k] + conj D[N - k]) / 2; the partner of (rho, k'') is (R - rho, 8191 - k''), i.e. the
+// partner row read backwards (row 0: (0, (8192 - k'') mod 8192)).
+// grid (R/2 + 1, Hc).  T: (Hc, R/2 + 1, 8192) = Y[rho][n2] = sum_{n1} W_R^{n1 rho} dk[n1*8192 + n2], unscaled.
+__global__ void __launch_bounds__(kThreads, 3) dk_rows_kernel(const float2* __restrict__ dkf_eng, float2* __restrict__ T, int R, int R0,
+                                                              int R1, const float2* __restrict__ tw,
+                                                              const float2* __restrict__ tw_lo, const float2* __restrict__ tw_hi) {
+  extern __shared__ float2 fbuf[];
+  const int tid = threadIdx.x, rho = blockIdx.x, h = blockIdx.y;
+  const int rm = (R - rho) & (R - 1);
+  const float2* row = dkf_eng + (size_t(h) * R + (rho % R0) * R1 + rho / R0) * kN;
+  const float2* mrow = dkf_eng + (size_t(h) * R + (rm % R0) * R1 + rm / R0) * kN;
+#pragma unroll 8
+  for (int e = tid; e < kN; e += kThreads) {
+    const int k2l = e & 15, k1 = (e >> 4) & 127, qd = e >> 11;
+    const int f = k1 + 128 * (16 * qd + k2l);
+    int em = kN - 1 - e;
+    if (rho == 0) {
+      const int fm = (kN - f) & (kN - 1), k2m = fm >> 7;
+      em = ((k2m >> 4) * 128 + (fm & 127)) * 16 + (k2m & 15);
+    }
+    const float2 a = row[e], b = mrow[em];
+    fbuf[slot(f)] = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+  }
+  __syncthreads();
+  fft8192<1>(fbuf, tid, tw);
+  float2* dst = T + (size_t(h) * (R / 2 + 1) + rho) * kN;
+#pragma unroll 8
+  for (int n = tid; n < kN; n += kThreads) {
+    float2 w = twiddle_n(n * rho, tw_lo, tw_hi);
+    w.y = -w.y;
+    dst[n] = cmul(fbuf[slot(pos_of_freq(n))], w);
+  }
+}
+
+// grid (8192 / TC, ceil(Hc / 2)): inverse R-point DFTs down the columns, channels 2*blockIdx.y (real) / +1 (imaginary)
+template <int R>
+__global__ void __launch_bounds__(kColThreads) dk_cols_kernel(const float2* __restrict__ T, float* __restrict__ dk, int Lk, int Hc,
+                                                           float scale, const float2* __restrict__ tw512) {
+  using P = ColRadix<R>;
+  constexpr int TC = P::kTC;
+  extern __shared__ float2 cb[];
+  const int tid = threadIdx.x, n20 = blockIdx.x * TC, ha = 2 * blockIdx.y, hb = ha + 1;
+  const bool two = hb < Hc;
+#pragma unroll 4
+  for (int e = tid; e < (R / 2 + 1) * TC; e += kColThreads) {
+    const int rho = e / TC, c = e % TC;
+    const float2 ya = T[(size_t(ha) * (R / 2 + 1) + rho) * kN + n20 + c];
+    const float2 yb = two ? T[(size_t(hb) * (R / 2 + 1) + rho) * kN + n20 + c] : make_float2(0.f, 0.f);
+    if (rho == 0 || 2 * rho == R) {
+      cb[rho * TC + c] = make_float2(ya.x, yb.x);                                  // real bins of both channels
+    } else {
+      cb[rho * TC + c] = make_float2(ya.x - yb.y, ya.y + yb.x);                    // Ya + i Yb
+      cb[(R - rho) * TC + c] = make_float2(ya.x + yb.y, yb.x - ya.y);              // conj Ya + i conj Yb
+    }
+  }
+  __syncthreads();
+  col_fft<R, 1>(cb, tid, tw512);
+  float* da = dk + size_t(ha) * Lk;
+  float* db = dk + size_t(hb) * Lk;
+  for (int e = tid; e < R * TC; e += kColThreads) {
+    const int n1 = e / TC, c = e % TC;
+    const int idx = n1 * kN + n20 + c;
+    if (idx >= Lk) continue;
+    const float2 x = cb[P::pos(n1) * TC + c];
+    da[idx] = x.x * scale;
+    if (two) db[idx] = x.y * scale;
   }
 }
 

@@ -6,10 +6,9 @@ Drop-in for `flashfftconv.FlashFFTConv` (reference flashfftconv/conv.py:71-560):
 (`backward -> (du, dk, None[, dpregate, dpostgate])`, conv.py:1822, :3939).
 
 All arithmetic on the hot path happens in libbffc.so (hand-written sm_100a CUDA, C ABI in
-include/bffc.h).  PyTorch is used for device memory and streams.  For seqlen <= 8192 the filter-side
-transforms (k -> k_f, dk_f -> dk) are library launches too (bffc_kf_from_filter / bffc_dk_from_dkf);
-for longer sequences they go through torch.fft in fp32 exactly as the reference does at
-conv.py:575 and :1817, followed by the library's pack / unpack kernels.
+include/bffc.h).  PyTorch is used for device memory and streams only: the filter-side transforms
+(k -> k_f, reference conv.py:575 + :640; dk_f -> dk, conv.py:1817-1820) are the library's own fp32 FFT launches
+for every supported size (bffc_kf_from_filter / bffc_dk_from_dkf) — no library FFT call is left in this module.
 
 The filter spectrum in engine order is what forward keeps for backward (the reference keeps its permuted
 k_f, conv.py:587-588), so a training step transforms the filter once; in eval mode it is additionally cached
@@ -177,12 +176,6 @@ def _check_inputs(u, k, mod, gates=()):
     return B, H, L
 
 
-def _kf_natural(mod, k):
-    """k (H, Lk) fp32 -> the N/2+1 non-redundant frequencies of FFT_N(k), complex64 (reference: conv.py:575 computes
-    the full complex FFT of the real filter; the second half is its Hermitian mirror and is rebuilt by the pack kernel)."""
-    return torch.fft.rfft(k.to(torch.float32), n=mod.fft_size(k.device)).contiguous()
-
-
 def _pack_kf_from_natural(mod, plan, k_f, conj):
     """rfft k_f -> engine-order packed (H, N) 4-byte complex, scaled 1/N (replaces conv.py:640)."""
     kf_engine = torch.empty((k_f.shape[0], mod.fft_size(k_f.device)), dtype=torch.int32, device=k_f.device)
@@ -191,18 +184,23 @@ def _pack_kf_from_natural(mod, plan, k_f, conj):
     return kf_engine
 
 
+def _filter_workspace(plan, H, device):
+    n = _lib.lib().bffc_filter_workspace_bytes(plan.handle, int(H))
+    return (torch.empty(n, dtype=torch.uint8, device=device) if n else None), n
+
+
 def _pack_kf(mod, plan, k, conj=0):
-    """k (H, Lk) fp32 device -> engine-order packed spectrum (H, N) int32 words.  Engine FFT size 8192 (seqlen <= 8192):
-    ONE launch of the library's own fp32 FFT (bffc_kf_from_filter); larger sizes: fp32 rfft as the reference
-    (conv.py:575) + the library's pack kernel."""
-    if mod.fft_size(k.device) == 8192:
-        k32 = k.detach().to(torch.float32).contiguous()
-        H, Lk = k32.shape
-        kf_engine = torch.empty((H, 8192), dtype=torch.int32, device=k.device)
-        _lib.check(_lib.lib().bffc_kf_from_filter(plan.handle, _ptr(k32), int(Lk), _ptr(kf_engine), int(H), int(conj),
-                                                  _stream()))
-        return kf_engine
-    return _pack_kf_from_natural(mod, plan, _kf_natural(mod, k.detach()), conj)
+    """k (H, Lk) fp32 device -> engine-order packed spectrum (H, N) int32 words by the library's own fp32 FFT
+    (bffc_kf_from_filter): one launch for engine size 8192, column + row FFT launches per L2-sized channel group for
+    the composite sizes (replaces conv.py:575 + :640)."""
+    k32 = k.detach().to(torch.float32).contiguous()
+    H, Lk = k32.shape
+    kf_engine = torch.empty((H, mod.fft_size(k.device)), dtype=torch.int32, device=k.device)
+    ws, ws_bytes = _filter_workspace(plan, H, k.device)
+    _lib.check(_lib.lib().bffc_kf_from_filter(plan.handle, _ptr(k32), int(Lk), _ptr(kf_engine), int(H), int(conj),
+                                              _ptr(ws), ws_bytes, _stream()))
+    mod.last_launches = _lib.lib().bffc_last_launch_count()
+    return kf_engine
 
 
 def _kf_engine_for(mod, plan, k, cache_key=None):
@@ -214,7 +212,6 @@ def _kf_engine_for(mod, plan, k, cache_key=None):
         if ref() is key and ver == key._version and dev == k.device:
             return kf
     kf = _pack_kf(mod, plan, k)
-    mod.last_launches = 1 if mod.fft_size(k.device) == 8192 else 2      # our kernels only (cuFFT launches not counted)
     mod._kf_cache = (weakref.ref(key), key._version, k.device, kf) if use_cache else None
     return kf
 
@@ -280,19 +277,15 @@ def _bwd(mod, dout, u, kf_engine, k_len, pregate, postgate):
         _lib.check(_lib.lib().bffc_bwd(plan.handle, _ptr(dout), _ptr(u), _ptr(kf_engine), None, _ptr(pregate),
                                        _ptr(postgate), _ptr(du), _ptr(dkf_engine), _ptr(dpre), _ptr(dpost),
                                        B, H, L, _ptr(ws), ws_bytes, _stream()))
-        mod.last_launches = _lib.lib().bffc_last_launch_count() + 1
-        if N == 8192:
-            # one launch: inverse fp32 FFT straight from engine order, 1/N, real part, fold of the small sizes, [:k_len]
-            dk = torch.empty((H, k_len), dtype=torch.float32, device=u.device)
-            _lib.check(_lib.lib().bffc_dk_from_dkf(plan.handle, _ptr(dkf_engine), _ptr(dk), int(k_len), H, _stream()))
-            return du, dk, dpre, dpost
-        # the kernel accumulates unnormalised pair-packed spectra; the reference takes ifft(dk_f).real[..., :k_len]
-        # (conv.py:1817-1820).  The real part of the inverse transform only sees the Hermitian part of dk_f: the library
-        # writes its N/2 + 1 non-redundant bins in natural order and a real inverse FFT (1/N included) finishes the job.
-        dkf_half = torch.empty((H, N // 2 + 1), dtype=torch.complex64, device=u.device)
-        _lib.check(_lib.lib().bffc_dkf_unpack_half(plan.handle, _ptr(dkf_engine), _ptr(torch.view_as_real(dkf_half)), H,
-                                                   _stream()))
-        dk = torch.fft.irfft(dkf_half, n=N, dim=-1)[..., :k_len].contiguous()
+        mod.last_launches = _lib.lib().bffc_last_launch_count()
+        # the kernels accumulate unnormalised pair-packed spectra in engine order; the reference takes
+        # ifft(dk_f).real[..., :k_len] (conv.py:1817-1820): inverse fp32 FFT straight from engine order, 1/N, real part
+        # (only the Hermitian part of dk_f contributes), fold of the small sizes, [:k_len]
+        dk = torch.empty((H, k_len), dtype=torch.float32, device=u.device)
+        fws, fws_bytes = _filter_workspace(plan, H, u.device)
+        _lib.check(_lib.lib().bffc_dk_from_dkf(plan.handle, _ptr(dkf_engine), _ptr(dk), int(k_len), H, _ptr(fws), fws_bytes,
+                                               _stream()))
+        mod.last_launches += _lib.lib().bffc_last_launch_count()
     return du, dk, dpre, dpost
 
 

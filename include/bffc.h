@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BFFC_ABI_VERSION 2
+#define BFFC_ABI_VERSION 3
 
 /* element types of u / y / gates */
 #define BFFC_DTYPE_BF16 0
@@ -100,17 +100,22 @@ int bffc_dkf_unpack_half(const bffc_plan* plan, const void* dkf_engine, void* dk
                          void* stream);
 
 /*
- * Filter-side transforms in one launch each, for plans whose bffc_fft_size() is 8192 (seqlen <= 8192; other plans
- * return BFFC_ERR_UNSUPPORTED and the caller uses rfft + bffc_kf_pack_rfft / bffc_dkf_unpack + ifft):
- *   bffc_kf_from_filter: k (H, Lk) fp32 device, Lk <= seqlen  ->  kf_engine, = bffc_kf_pack_rfft(rfft(k, n=8192))
- *                        (replaces conv.py:572-575 + :640, fp32 FFT on CUDA cores, two channels per complex FFT)
- *   bffc_dk_from_dkf:    dkf_engine (H, 8192) float2 as written by bffc_bwd  ->  dk (H, Lk) fp32
+ * Filter-side transforms, fp32 on CUDA cores, written / read directly in engine order (no library FFT on the path):
+ *   bffc_kf_from_filter: k (H, Lk) fp32 device, Lk <= seqlen  ->  kf_engine  = bffc_kf_pack_rfft(rfft(k, n = fft size))
+ *                        (replaces conv.py:572-575 + :640; two real channels share one complex FFT)
+ *   bffc_dk_from_dkf:    dkf_engine (H, fft size) float2 as written by bffc_bwd  ->  dk (H, Lk) fp32
  *                        = ifft(unpack(dkf)).real[:, :Lk] incl. the fold of the small sizes (replaces conv.py:1817-1820)
+ * Plans with fft size 8192 (seqlen <= 8192): one launch, no workspace (NULL / 0).  Composite sizes N = R * 8192: per group
+ * of channels one launch of R-point column FFTs and one of 8192-point row FFTs, with (channels, R/2 + 1, 8192) complex64
+ * between them in `workspace`.  bffc_filter_workspace_bytes(plan, H) is the recommended size (a group that stays in L2,
+ * at most H channels); any size >= 2 * (R/2 + 1) * 65536 bytes (one channel pair) works, smaller groups = more launches.
+ * bffc_last_launch_count() reports the launches of the call.
  */
+size_t bffc_filter_workspace_bytes(const bffc_plan* plan, int H);
 int bffc_kf_from_filter(const bffc_plan* plan, const void* k, int Lk, void* kf_engine, int H, int conj,
-                        void* stream);
+                        void* workspace, size_t workspace_bytes, void* stream);
 int bffc_dk_from_dkf(const bffc_plan* plan, const void* dkf_engine, void* dk, int Lk, int H,
-                     void* stream);
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* Scratch the caller must provide.  bffc_workspace_bytes_ex: exact need of bffc_fwd (backward = 0) or bffc_bwd
  * (backward = 1) for a gated / ungated call (0 for the fully fused ungated sizes); bffc_workspace_bytes: enough for any

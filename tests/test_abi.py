@@ -35,7 +35,7 @@ def test_header_symbols_exported(lib):
 
 def test_abi_version_and_supported(lib):
     l = lib.lib()
-    assert l.bffc_abi_version() == 2
+    assert l.bffc_abi_version() == 3
     assert l.bffc_supported(8192, lib.BFFC_DTYPE_BF16) == 1
     assert l.bffc_supported(8191, lib.BFFC_DTYPE_BF16) == 0
 
