@@ -9,7 +9,7 @@
 //   the three-kernel orchestration of the long sizes (conv.py:1420-1524: butterfly -> complex Monarch -> ibutterfly)
 // No torch types cross this boundary; there is no CPU fallback.
 #include "bffc.h"
-#include "fwd_r128.cuh"
+#include "r128_common.cuh"
 #include "fwd3_r128.cuh"
 #include "dkf3_r128.cuh"
 #include "outer_cuda.cuh"
@@ -187,27 +187,6 @@ __global__ void fold_kernel(const uint4* __restrict__ t, const uint4* __restrict
   y[r * per + v] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-template <int kFmt>
-__global__ void gate_mul1_kernel(const uint4* __restrict__ a, const uint4* __restrict__ g, uint4* __restrict__ o, size_t nvec) {
-  using NT = bffc::Num<kFmt>;
-  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= nvec) return;
-  const uint4 x = a[i], y = g[i];
-  o[i] = make_uint4(NT::hmul2(x.x, y.x), NT::hmul2(x.y, y.y), NT::hmul2(x.z, y.z), NT::hmul2(x.w, y.w));
-}
-
-// o0 = a0 * g0, o1 = a1 * g1 elementwise in the 16-bit format (gated loads of the dk_f kernel, seqlen <= 8192)
-template <int kFmt>
-__global__ void gate_mul2_kernel(const uint4* __restrict__ a0, const uint4* __restrict__ g0, uint4* __restrict__ o0,
-                                 const uint4* __restrict__ a1, const uint4* __restrict__ g1, uint4* __restrict__ o1, size_t nvec) {
-  using NT = bffc::Num<kFmt>;
-  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= nvec) return;
-  const uint4 x = a0[i], g = g0[i], y = a1[i], q = g1[i];
-  o0[i] = make_uint4(NT::hmul2(x.x, g.x), NT::hmul2(x.y, g.y), NT::hmul2(x.z, g.z), NT::hmul2(x.w, g.w));
-  o1[i] = make_uint4(NT::hmul2(y.x, q.x), NT::hmul2(y.y, q.y), NT::hmul2(y.z, q.z), NT::hmul2(y.w, q.w));
-}
-
 template <bool kHalf, int kFmt>
 __global__ void kf_pack_tiled_kernel(const float2* __restrict__ kf_nat, uint2* __restrict__ kf_eng, int N, int R0, int R1,
                                      float scale, int conj) {
@@ -382,12 +361,9 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
 
   using namespace bffc::r128;
   FMT_SWITCH(dtype,
-    PLAN_TRY(cudaFuncSetAttribute(fwd_kernel<false, false, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    PLAN_TRY(cudaFuncSetAttribute(fwd_kernel<true, false, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    PLAN_TRY(cudaFuncSetAttribute(fwd_kernel<false, true, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalGated));
-    PLAN_TRY(cudaFuncSetAttribute(fwd_kernel<false, false, true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    PLAN_TRY(cudaFuncSetAttribute(fwd3_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal3));
-    PLAN_TRY(cudaFuncSetAttribute(fwd3_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal3));
+    PLAN_TRY(cudaFuncSetAttribute(fwd3_kernel<false, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal3));
+    PLAN_TRY(cudaFuncSetAttribute(fwd3_kernel<false, true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal3));
+    PLAN_TRY(cudaFuncSetAttribute(fwd3_kernel<true, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal3));
     PLAN_TRY(cudaFuncSetAttribute(dkf3_kernel<true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf3));
     PLAN_TRY(cudaFuncSetAttribute(dkf3_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalDkf3));
     PLAN_TRY(cudaFuncSetAttribute(outer_tc_kernel<false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOuterGated));
@@ -621,9 +597,8 @@ static size_t small_fold_bytes(const bffc_plan* p, int B, int H) {
 extern "C" size_t bffc_workspace_bytes_ex(const bffc_plan* p, int B, int H, int L, int gated, int backward) {
   if (!p) return 0;
   if (p->N < kInner) {   // small sizes: S = 4096/N batch members share one 8192-point slot; scratch of full output tiles,
-                         // gated: + u*pregate (one tensor), gated backward: + the two gated inputs of the dk_f kernel
-    return small_fold_bytes(p, B, H) + (gated ? gate_scratch_bytes(B, H, L) / 2 : 0) +
-           ((gated && backward) ? gate_scratch_bytes(B, H, L) : 0);
+                         // gated backward: + the two gated inputs of the dk_f kernel
+    return small_fold_bytes(p, B, H) + ((gated && backward) ? gate_scratch_bytes(B, H, L) : 0);
   }
   if (p->nlev == 0) return (gated && backward) ? gate_scratch_bytes(B, H, L) : 0;
   // plane sets (real + imaginary plane each) of ONE chunk: forward nlev sets; backward nlev + 1 (transformed u and dout)
@@ -674,9 +649,8 @@ static void fill_params(const bffc_plan* p, bffc::FwdParams& prm, const void* kf
   prm.postgate = nullptr;
   prm.postgate2 = nullptr;
   prm.y2 = nullptr;
+  prm.xg_out = nullptr;
   prm.kf_conj_mask = 0;
-  prm.dbg = nullptr;
-  prm.dbg_stages = 0;
   prm.trace = nullptr;
 }
 
@@ -721,11 +695,12 @@ struct PassOpts {
   int conj = 0;                     // 1: conjugate k_f inside the kernel's pointwise multiply (else kf is pre-conjugated)
   const void* postgate2 = nullptr;  // second gated output y2 = postgate2 * conv(...) from the same pass
   void* y2 = nullptr;
+  void* xg_out = nullptr;           // seqlen <= 8192, gated: the pass also stores its gated input u * pregate here
 };
 
 // fused 8192-point kernel on (B, H, L) real sequences.  Small sizes (p->N < 8192): `y` is the fold scratch.
 static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const void* pregate, const void* postgate,
-                        void* y, int B, int H, int L, float* dbg, int dbg_stages, int max_units, cudaStream_t st,
+                        void* y, int B, int H, int L, cudaStream_t st,
                         const PassOpts& po = PassOpts()) {
   if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen <= 8192 in this build", L);
   const bool small = p->N < kInner;
@@ -742,6 +717,7 @@ static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const
   prm.postgate2 = small ? nullptr : static_cast<const uint32_t*>(po.postgate2);   // small sizes: applied by the fold
   prm.y2 = small ? nullptr : static_cast<uint32_t*>(po.y2);
   prm.kf_conj_mask = po.conj ? 0x80008000u : 0u;
+  prm.xg_out = pregate ? po.xg_out : nullptr;
   prm.B = B; prm.H = H; prm.L = L;
   prm.pairs = sg.groups;
   prm.kmask = sg.kmask;
@@ -749,24 +725,27 @@ static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const
   prm.seg_bytes = sg.seg_rows * 128;
   prm.small_out = small ? 1 : 0;
   prm.units = H * prm.pairs;
-  if (max_units > 0 && prm.units > max_units) prm.units = max_units;
-  prm.dbg = dbg;
-  prm.dbg_stages = dbg_stages;
-  int grid = (prm.units + 1) / 2;
-  if (grid > p->num_sms) grid = p->num_sms;
   using namespace bffc::r128;
+  const bool gated = pregate || postgate || prm.y2;
+  // gate tiles travel by TMA like the inputs: pregate with the (segmented) geometry of u, output gates with that of y
+  GateMaps gm{tm_g, tm_u, tm_u, tm_u, tm_u};
+  if (prm.xg_out) { if (int rc = make_map(p, &gm.xg, prm.xg_out, B * H, L, sg.seg_rows)) return rc; }
+  if (!small && postgate) { if (int rc = make_map(p, &gm.post, postgate, B * H, L)) return rc; }
+  if (prm.y2) {
+    if (int rc = make_map(p, &gm.post2, prm.postgate2, B * H, L)) return rc;
+    if (int rc = make_map(p, &gm.y2, prm.y2, B * H, L)) return rc;
+  }
+  if (small) prm.postgate = nullptr;                  // small sizes: the fold applies the output gates
+  int g3 = (prm.units + kPipes3 - 1) / kPipes3;
+  if (g3 > p->num_sms) g3 = p->num_sms;
   FMT_SWITCH(p->dtype,
-    if (dbg)
-      fwd_kernel<true, false, false, F><<<grid, kThreads, kSmemTotal, st>>>(tm_u, tm_y, tm_g, prm);
-    else if (pregate || postgate || prm.y2)
-      fwd_kernel<false, true, false, F><<<grid, kThreads, kSmemTotalGated, st>>>(tm_u, tm_y, tm_g, prm);
+    if (gated)
+      fwd3_kernel<false, true, F><<<g3, kThreads3, kSmemTotal3, st>>>(tm_u, tm_y, tm_g, gm, prm);
     else {
-      int g3 = (prm.units + kPipes3 - 1) / kPipes3;
-      if (g3 > p->num_sms) g3 = p->num_sms;
 #ifdef BFFC_BRINGUP
       prm.trace = trace_buffer();
 #endif
-      fwd3_kernel<false, F><<<g3, kThreads3, kSmemTotal3, st>>>(tm_u, tm_y, tm_g, prm);
+      fwd3_kernel<false, false, F><<<g3, kThreads3, kSmemTotal3, st>>>(tm_u, tm_y, tm_g, gm, prm);
 #ifdef BFFC_BRINGUP
       if (prm.trace) trace_dump(st);
 #endif
@@ -792,7 +771,8 @@ static int launch_planes(const bffc_plan* p, void* pre, void* pim, const void* k
   using namespace bffc::r128;
   int g3 = (prm.units + kPipes3 - 1) / kPipes3;
   if (g3 > p->num_sms) g3 = p->num_sms;
-  FMT_SWITCH(p->dtype, (fwd3_kernel<true, F><<<g3, kThreads3, kSmemTotal3, st>>>(tm_r, tm_r, tm_i, prm)););
+  const GateMaps gm{tm_r, tm_r, tm_r, tm_r, tm_r};      // unused in this mode
+  FMT_SWITCH(p->dtype, (fwd3_kernel<true, false, F><<<g3, kThreads3, kSmemTotal3, st>>>(tm_r, tm_r, tm_i, gm, prm)););
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -995,20 +975,8 @@ static int conv_forward(const bffc_plan* p, const void* u, const void* kf, const
     // S = 4096/N batch members of a channel share one 8192-point slot (spacing 2N), so a unit carries 2S sequences.
     const int off = corr ? kInner - p->N : p->N;
     const SegGeom sg = seg_geom(p, B, L);
-    const void* uin = u;
-    if (pregate) {
-      // gated small sizes: u * pregate by an elementwise pre-pass (reference: __hmul2 on load, monarch_cuda_kernel_bf16.h),
-      // so that the three-pipeline kernel runs them too — measured at B=64 H=768 N=1024: gated two-pipeline kernel 325 us
-      // vs pre-pass + ungated kernel (profiles/r2_launches.md); the postgate is applied by the fold
-      uint8_t* pm = static_cast<uint8_t*>(ws) + small_fold_bytes(p, B, H);
-      const size_t nvec = size_t(B) * H * L / 8;
-      FMT_SWITCH(p->dtype, (gate_mul1_kernel<F><<<unsigned((nvec + 255) / 256), 256, 0, st>>>(
-          static_cast<const uint4*>(u), static_cast<const uint4*>(pregate), reinterpret_cast<uint4*>(pm), nvec)););
-      CUDA_TRY(cudaGetLastError());
-      *launches += 1;
-      uin = pm;
-    }
-    if (int rc = launch_fused(p, uin, kf, nullptr, nullptr, ws, B, H, L, nullptr, 0, 0, st, po)) return rc;
+    // gated small sizes: the pregate is multiplied in the kernel's pass 0, the output gates by the fold
+    if (int rc = launch_fused(p, u, kf, pregate, nullptr, ws, B, H, L, st, po)) return rc;
     const size_t rows = size_t(B) * H, total = rows * (L / 8);
     FMT_SWITCH(p->dtype, (fold_kernel<F><<<unsigned((total + 255) / 256), 256, 0, st>>>(
         static_cast<const uint4*>(ws), static_cast<const uint4*>(postgate), static_cast<uint4*>(y),
@@ -1019,7 +987,7 @@ static int conv_forward(const bffc_plan* p, const void* u, const void* kf, const
   }
   if (p->nlev == 0) {
     *launches += 1;
-    return launch_fused(p, u, kf, pregate, postgate, y, B, H, L, nullptr, 0, 0, st, po);
+    return launch_fused(p, u, kf, pregate, postgate, y, B, H, L, st, po);
   }
   // composite sizes, chunk by chunk (see chunk_view): outer stage(s) -> inner kernel in place -> inverse outer stage(s)
   const View c = chunk_view(p, B, H, p->nlev);
@@ -1089,6 +1057,7 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
   dx.corr = 1;
   dx.conj = kf_conj ? 0 : 1;
   const void* kfc = kf_conj ? kf_conj : kf;
+  uint8_t *gate_x = nullptr, *gate_d = nullptr;
   if (!gated) {
     if (int rc = conv_forward(p, dout, kfc, nullptr, nullptr, du, B, H, L, workspace, st, &launches, dx)) return rc;
   } else {
@@ -1096,7 +1065,16 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
     // monarch_cuda_interface_bwd_bf16.cu:798-808).  With dx = corr(dout*q, k):
     //   dpostgate = dout * conv(u*p, k)                        — one pass of the forward path
     //   du = p * dx  and  dpregate = u * dx                    — ONE more pass with two gated outputs
-    if (int rc = conv_forward(p, u, kf, pregate, dout, dpostgate, B, H, L, workspace, st, &launches)) return rc;
+    // seqlen <= 8192: the dk_f kernel below needs u*p and dout*q — the gated inputs of these two passes, which store
+    // them into the tail of the workspace on the way (composite sizes gate inside their outer stages instead)
+    PassOpts p1;
+    if (p->nlev == 0) {
+      gate_x = static_cast<uint8_t*>(workspace) + (p->N < kInner ? small_fold_bytes(p, B, H) : 0);
+      gate_d = gate_x + gate_scratch_bytes(B, H, L) / 2;
+      p1.xg_out = gate_x;
+      dx.xg_out = gate_d;
+    }
+    if (int rc = conv_forward(p, u, kf, pregate, dout, dpostgate, B, H, L, workspace, st, &launches, p1)) return rc;
     dx.postgate2 = u;
     dx.y2 = dpregate;
     if (int rc = conv_forward(p, dout, kfc, postgate, pregate, du, B, H, L, workspace, st, &launches, dx)) return rc;
@@ -1114,20 +1092,8 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
   using namespace bffc::r128;
   if (p->nlev == 0) {
     if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen <= 8192 in this build", L);
-    const void *xu = u, *xd = dout;
-    if (gated) {
-      // gated loads: u*pregate and dout*postgate (reference: ..._bwd_kernel_bf16.h:505-509,571-581) from an elementwise
-      // pre-pass into the tail of the workspace
-      uint8_t* g0 = static_cast<uint8_t*>(workspace) + (p->N < kInner ? small_fold_bytes(p, B, H) + gate_scratch_bytes(B, H, L) / 2 : 0);
-      uint8_t* g1 = g0 + gate_scratch_bytes(B, H, L) / 2;
-      const size_t nvec = size_t(B) * H * L / 8;
-      FMT_SWITCH(p->dtype, (gate_mul2_kernel<F><<<unsigned((nvec + 255) / 256), 256, 0, st>>>(
-          static_cast<const uint4*>(u), static_cast<const uint4*>(pregate), reinterpret_cast<uint4*>(g0),
-          static_cast<const uint4*>(dout), static_cast<const uint4*>(postgate), reinterpret_cast<uint4*>(g1), nvec)););
-      CUDA_TRY(cudaGetLastError());
-      launches += 1;
-      xu = g0; xd = g1;
-    }
+    // gated loads (reference: ..._bwd_kernel_bf16.h:505-509,571-581): the products stored by the two passes above
+    const void *xu = gated ? gate_x : u, *xd = gated ? gate_d : dout;
     CUtensorMap tm_u, tm_d;
     const SegGeom sg = seg_geom(p, B, L);
     if (int rc = make_map(p, &tm_u, xu, B * H, L, sg.seg_rows)) return rc;
@@ -1281,16 +1247,6 @@ int bffc_fwd_host(const bffc_plan* p, const void* u_host, const void* kf, const 
   }
   g_launches = launches;
   return BFFC_OK;
-}
-
-int bffc_debug_fwd_stages(const bffc_plan* p, const void* u, const void* kf, void* y, int B, int H, int L, float* dump,
-                          int max_stages, void* stream) {
-  if (!dump || max_stages <= 0 || !p || p->R != 1) return -BFFC_ERR_INVALID;
-  if (check_common(p, B, H, L, u, y, kf)) return -BFFC_ERR_INVALID;
-  const int nst = 4;
-  int rc = launch_fused(p, u, kf, nullptr, nullptr, y, B, H, L, dump, max_stages, 1, static_cast<cudaStream_t>(stream));
-  if (rc) return -rc;
-  return max_stages < nst ? max_stages : nst;
 }
 
 }  // extern "C"

@@ -1,13 +1,25 @@
-// Fused forward FFT-convolution kernel, N = 8192 — three-pipeline variant (v3), ungated.
+// Fused forward FFT-convolution kernel, N = 8192 — three pipelines of one warpgroup each; ungated, gated, and the
+// complex-rows mode of the composite sizes.
 //
-// Same algorithm and stage list as fwd_r128.cuh.  The v2 kernel is latency-bound with only two sequence pairs in
+// Same algorithm and stage list as r128_common.cuh.  The v2 kernel is latency-bound with only two sequence pairs in
 // flight per SM (TMEM: 128 columns DFT-128 + 2 x (128 accumulator + 64 operand)); see profiles/r1_v21_summary.md.
 // Here the A operand of the two radix-64 stages is staged in SHARED memory (the unit's own tile slot, K-major,
 // 128B swizzle — byte-for-byte the layout pass 5 already writes for stage 4) instead of TMEM, which frees the
 // operand columns: TMEM = 128 (DFT-128) + 3 x 128 accumulators, i.e. three pipelines of one warpgroup each.
 // Stage 2 / 3 become SS-mode MMAs (A and B descriptors), stage 1 / 4 stay TS-mode (DFT-128 in TMEM).
+//
+// kGated: y = postgate * conv(u * pregate, k) (reference: GatedFlashFFTConvFunc, conv.py:3239-3325; __hmul2 on load /
+// store, kernels_bf16/monarch_cuda_32_16_16_kernel_bf16.h:550-585).  Shared memory is full (3 x 2 slots + DFT-64 tiles),
+// so a gated pipeline gives up the prefetch slot: slot 0 is the work area, slot 1 receives the gate tiles by TMA —
+// the pregate next to the input (pass 0 multiplies in place, 16-bit product), then the postgate while the stages run
+// (pass 6 multiplies the rounded result before the store), then optionally a second output gate (y2 = postgate2 * conv:
+// du and dpregate of the gated backward from ONE pass, ...bwd_kernel_bf16.h:836-870; the accumulator is still in TMEM).
+// The next unit's loads are issued when the last store has read slot 0; the other two pipelines cover that latency.
+// p.xg_out: the gated input u * pregate is also stored (TMA, from slot 0 right after pass 0) — the backward's dk_f kernel
+// consumes exactly these products, so the two gated passes of the backward hand them over instead of a separate
+// elementwise pre-pass re-reading all four tensors.
 #pragma once
-#include "fwd_r128.cuh"
+#include "r128_common.cuh"
 
 namespace bffc {
 namespace r128 {
@@ -21,10 +33,13 @@ constexpr int kSmemTotal3 = kSmemData3 + kSmemG + kSmemBars3 + 1024;
 // K-major, 128B-swizzled A operand tile (128 rows x 64 bf16): 8-row groups 1024 B apart
 DEVINL uint64_t atile_desc(uint32_t saddr) { return make_sdesc(saddr, 16, 1024, 2); }
 
-template <bool kPlanes, int kFmt>
+struct GateMaps { CUtensorMap pre, post, post2, y2, xg; };
+
+template <bool kPlanes, bool kGated, int kFmt>
 __global__ void __launch_bounds__(kThreads3, 1)
 fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_y,
-            const __grid_constant__ CUtensorMap tm_g, const FwdParams p) {
+            const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ GateMaps gm, const FwdParams p) {
+  static_assert(!(kPlanes && kGated), "composite sizes apply their gates in the outer stages");
   using NT = Num<kFmt>;
   constexpr uint32_t ID_N128_MN = Idesc<kFmt>::N128_MN, ID_N64_MN = Idesc<kFmt>::N64_MN, ID_N64_MN_NEG = Idesc<kFmt>::N64_MN_NEG;
   extern __shared__ uint8_t smem_raw[];
@@ -50,6 +65,10 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     tma_prefetch_desc(&tm_u);
     tma_prefetch_desc(&tm_y);
     if (kPlanes) tma_prefetch_desc(&tm_g);
+    if (kGated) {
+      tma_prefetch_desc(&gm.pre); tma_prefetch_desc(&gm.post); tma_prefetch_desc(&gm.post2); tma_prefetch_desc(&gm.y2);
+      tma_prefetch_desc(&gm.xg);
+    }
   }
   if ((tid & 127) == 0) {
     mbar_init(bar_tma0, 1);
@@ -68,6 +87,12 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + kSmemData3 + kSmemG + 96);
   const uint32_t tlane = tmem_base + (uint32_t(warp_q * 32) << 16);
 
+  const bool has_pre = kGated && p.pregate != nullptr, has_post = kGated && p.postgate != nullptr;
+  const bool has_post2 = kGated && p.y2 != nullptr;
+  const bool emit_xg = has_pre && p.xg_out != nullptr;
+  const uint32_t bar_gate = bar_tma0 + 8;          // gated: slot 1 = gate tiles, its barrier counts postgate arrivals
+  uint32_t gate_phase = 0;
+
   const int gp = blockIdx.x * kPipes3 + pipe;
   const int GP = gridDim.x * kPipes3;
   const int u_begin = int((long long)p.units * gp / GP);
@@ -83,6 +108,17 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   auto issue_load = [&](int unit, int slot) {
     const uint32_t bar = bar_tma0 + 8 * slot;
     const uint32_t dst = s_slot0 + slot * kSlotBytes;
+    if (kGated) {                        // input tiles -> slot 0, pregate tiles -> slot 1, one barrier
+      const int uh = unit / p.pairs, ug = unit - uh * p.pairs;
+      mbar_expect_tx(bar_tma0, has_pre ? 2 * kSlotBytes : kSlotBytes);
+      load_tile(s_slot0, &tm_u, bar_tma0, p.B, p.H, uh, ug, 0, p.nseg, p.seg_bytes);
+      load_tile(s_slot0 + kTileBytes, &tm_u, bar_tma0, p.B, p.H, uh, ug, 1, p.nseg, p.seg_bytes);
+      if (has_pre) {
+        load_tile(s_slot0 + kSlotBytes, &gm.pre, bar_tma0, p.B, p.H, uh, ug, 0, p.nseg, p.seg_bytes);
+        load_tile(s_slot0 + kSlotBytes + kTileBytes, &gm.pre, bar_tma0, p.B, p.H, uh, ug, 1, p.nseg, p.seg_bytes);
+      }
+      return;
+    }
     mbar_expect_tx(bar, kSlotBytes);
     if (kPlanes) {
       tma_load_3d(dst, &tm_u, bar, 0, 0, seq_index(unit, 0));
@@ -183,14 +219,50 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   if (lead_warp) mbar_wait(bar_g, 0);     // DFT-64 tiles have landed (long ago: hidden behind the table set-up)
 
   for (int unit = u_begin, n = 0; unit < u_end; ++unit, ++n) {
-    const int slot = n & 1;
+    const int slot = kGated ? 0 : (n & 1);
     const uint32_t sX = s_slot0 + slot * kSlotBytes;
+    const uint32_t sGate = s_slot0 + kSlotBytes;
     const int h = unit / p.pairs;
     stamp(0);
 
+    if (kGated) {
+      // ---------------- pass 0: u * pregate in place (same swizzled image on both sides: linear 16-byte chunks)
+      if (has_pre) {
+        mbar_wait(bar_tma0, n & 1);
+#pragma unroll 4
+        for (int i = 0; i < kSlotBytes / 16 / 128; ++i) {
+          const uint32_t off = uint32_t(i * 128 + lane) * 16u;
+          const uint4 a = ld_shared_v4(sX + off), g = ld_shared_v4(sGate + off);
+          st_shared_v4(sX + off, NT::hmul2(a.x, g.x), NT::hmul2(a.y, g.y), NT::hmul2(a.z, g.z), NT::hmul2(a.w, g.w));
+        }
+        sync_pipe_smem();                 // products visible to the tensor core; slot 1 is free again
+      }
+      if (emit_xg && lead_warp) {
+        if (elect_one()) {                // mirror of load_tile: segments of existing batch members only
+          const int ug = unit - h * p.pairs;
+          for (int w = 0; w < 2; ++w)
+            for (int sg = 0; sg < p.nseg; ++sg) {
+              const int b = (ug * p.nseg + sg) * 2 + w;
+              if (b < p.B) tma_store_3d(&gm.xg, sX + w * kTileBytes + sg * p.seg_bytes, 0, 0, b * p.H + h);
+            }
+          tma_store_commit();
+        }
+        __syncwarp();
+      }
+      if (has_post && lead_warp) {
+        if (elect_one()) {
+          const int ug = unit - h * p.pairs;
+          mbar_expect_tx(bar_gate, kSlotBytes);
+          load_tile(sGate, &gm.post, bar_gate, p.B, p.H, h, ug, 0, 1, 0);
+          load_tile(sGate + kTileBytes, &gm.post, bar_gate, p.B, p.H, h, ug, 1, 1, 0);
+        }
+        __syncwarp();
+      }
+    }
+
     // ---------------- stage 1 (TS): D1 = F128 * X
     if (lead_warp) {
-      mbar_wait(bar_tma0 + 8 * slot, (n >> 1) & 1);
+      mbar_wait(bar_tma0 + 8 * slot, kGated ? (n & 1) : ((n >> 1) & 1));
       tc_fence_after();
       stamp(1);
       if (elect_one()) {
@@ -212,6 +284,7 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
           for (int s = 0; s < 8; ++s)
             if ((p.kmask >> s) & 1) mma_ts(tD0 + 64, tS0 + 8 * s, dXr + 128 * s, ID_N64_MN_NEG, 1);
         }
+        if (emit_xg) tma_store_wait_read0();   // pass 1 overwrites slot 0: nobody passes bar_mma before the store has read it
         mma_commit(bar_mma);
       }
       __syncwarp();
@@ -261,7 +334,7 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
         for (int s = 0; s < 4; ++s) mma_ss(tD0, dAi + 2 * s, dG1 + 128 * s, ID_N128_MN, 1);
         mma_commit(bar_mma);
-        if (unit + 1 < u_end) {
+        if (!kGated && unit + 1 < u_end) {
           tma_store_wait_read0();
           issue_load(unit + 1, slot ^ 1);
         }
@@ -378,36 +451,71 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     wait_mma();
     stamp(13);
 
-    // ---------------- pass 6: fp32 -> 16 bit output tiles, TMA store
-    {
+    // ---------------- pass 6: fp32 -> 16 bit output tiles (x output gate), TMA store
+    auto pass6 = [&](bool gate) {
 #pragma unroll 1
-    for (int sub = 0; sub < 4; ++sub) {
-      uint32_t re[16], im[16];
-      tmem_ld16(tD + 16 * sub, re);
-      tmem_ld16(tD + 64 + 16 * sub, im);
-      tmem_ld_wait();
-      reg_fence(re); reg_fence(im);
+      for (int sub = 0; sub < 4; ++sub) {
+        uint32_t re[16], im[16];
+        tmem_ld16(tD + 16 * sub, re);
+        tmem_ld16(tD + 64 + 16 * sub, im);
+        tmem_ld_wait();
+        reg_fence(re); reg_fence(im);
 #pragma unroll
-      for (int blk = 0; blk < 2; ++blk) {
-        uint32_t ore[4], oim[4];
+        for (int blk = 0; blk < 2; ++blk) {
+          uint32_t ore[4], oim[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          ore[q] = NT::pack(__uint_as_float(re[8 * blk + 2 * q]), __uint_as_float(re[8 * blk + 2 * q + 1]));
-          oim[q] = NT::pack(__uint_as_float(im[8 * blk + 2 * q]), __uint_as_float(im[8 * blk + 2 * q + 1]));
+          for (int q = 0; q < 4; ++q) {
+            ore[q] = NT::pack(__uint_as_float(re[8 * blk + 2 * q]), __uint_as_float(re[8 * blk + 2 * q + 1]));
+            oim[q] = NT::pack(__uint_as_float(im[8 * blk + 2 * q]), __uint_as_float(im[8 * blk + 2 * q + 1]));
+          }
+          if (kGated && gate) {
+            const uint32_t off = uint32_t(lane) * 128u + (uint32_t((2 * sub + blk) ^ (lane & 7)) << 4);
+            const uint4 g0 = ld_shared_v4(sGate + off), g1 = ld_shared_v4(sGate + kTileBytes + off);
+            ore[0] = NT::hmul2(ore[0], g0.x); ore[1] = NT::hmul2(ore[1], g0.y); ore[2] = NT::hmul2(ore[2], g0.z); ore[3] = NT::hmul2(ore[3], g0.w);
+            oim[0] = NT::hmul2(oim[0], g1.x); oim[1] = NT::hmul2(oim[1], g1.y); oim[2] = NT::hmul2(oim[2], g1.z); oim[3] = NT::hmul2(oim[3], g1.w);
+          }
+          store_chunk(sX, 2 * sub + blk, ore, oim);
         }
-        store_chunk(sX, 2 * sub + blk, ore, oim);
       }
-    }
-    }
+    };
+    auto store_out = [&](const CUtensorMap* my) {
+      const int pr = unit - h * p.pairs;
+      tma_store_3d(my, sX, 0, 0, seq_index(unit, 0));
+      if (kPlanes) tma_store_3d(&tm_g, sX + kTileBytes, 0, 0, seq_index(unit, 1));
+      else if (p.small_out || 2 * pr + 1 < p.B) tma_store_3d(my, sX + kTileBytes, 0, 0, seq_index(unit, 1));
+      tma_store_commit();
+    };
+    if (has_post) { mbar_wait(bar_gate, gate_phase); gate_phase ^= 1; }
+    pass6(has_post);
     stamp(14);
     sync_pipe_smem();
     if (lead_warp) {
       if (elect_one()) {
-        const int pr = unit - h * p.pairs;
-        tma_store_3d(&tm_y, sX, 0, 0, seq_index(unit, 0));
-        if (kPlanes) tma_store_3d(&tm_g, sX + kTileBytes, 0, 0, seq_index(unit, 1));
-        else if (p.small_out || 2 * pr + 1 < p.B) tma_store_3d(&tm_y, sX + kTileBytes, 0, 0, seq_index(unit, 1));
-        tma_store_commit();
+        store_out(&tm_y);
+        if (has_post2) {                  // slot 1 has been read by every thread (barrier above): second gate -> slot 1
+          const int ug = unit - h * p.pairs;
+          mbar_expect_tx(bar_gate, kSlotBytes);
+          load_tile(sGate, &gm.post2, bar_gate, p.B, p.H, h, ug, 0, 1, 0);
+          load_tile(sGate + kTileBytes, &gm.post2, bar_gate, p.B, p.H, h, ug, 1, 1, 0);
+          tma_store_wait_read0();         // the first output has left slot 0
+        }
+      }
+      __syncwarp();
+    }
+    if (has_post2) {
+      named_bar_sync(bar_id, 128);
+      mbar_wait(bar_gate, gate_phase); gate_phase ^= 1;
+      pass6(true);
+      sync_pipe_smem();
+      if (lead_warp) {
+        if (elect_one()) store_out(&gm.y2);
+        __syncwarp();
+      }
+    }
+    if (kGated && lead_warp && unit + 1 < u_end) {
+      if (elect_one()) {
+        tma_store_wait_read0();
+        issue_load(unit + 1, 0);
       }
       __syncwarp();
     }

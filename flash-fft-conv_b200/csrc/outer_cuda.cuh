@@ -6,7 +6,7 @@
 // is the 8192-point one.  Same role: outer DFT down the stride-M columns + (R x M) twiddle, with the implicit
 // zero padding (rows >= L/M are never read) and the gates applied on load / store.
 //
-//   n = a*M + n',  k = c + R*k',  M = 8192,  z = u_b + i u_{b+1} (pair packing, see fwd_r128.cuh)
+//   n = a*M + n',  k = c + R*k',  M = 8192,  z = u_b + i u_{b+1} (pair packing, see r128_common.cuh)
 //   forward : V_c[n'] = W_N^{n' c} * sum_a W_R^{a c} z[a*M + n']          -> planes row ((pair*H + h)*R + c)
 //   inverse : z'[a*M + n'] = sum_c W_R^{-a c} W_N^{-n' c} T_c[n']         (1/N is folded into k_f)
 // Each thread owns 8 consecutive n' (one 16-byte vector per row).

@@ -11,10 +11,10 @@
 //
 // Machine mapping: the unit is one 64-column chunk of one sequence pair: a (128 x 64) tile per member, TMA
 // loaded with a 4-D map (col, chunk, row, sequence); DFT-128 cos / sin planes resident in TMEM as the A operand
-// (exactly stage 1 / stage 4 of fwd_r128.cuh); the twiddle is applied by the CUDA cores on the accumulator
+// (exactly stage 1 / stage 4 of r128_common.cuh); the twiddle is applied by the CUDA cores on the accumulator
 // (forward) or on the tile in shared memory before the MMA (inverse).  Two pipelines x two warpgroups per CTA.
 #pragma once
-#include "fwd_r128.cuh"
+#include "r128_common.cuh"
 
 namespace bffc {
 

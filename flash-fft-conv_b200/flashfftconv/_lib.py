@@ -39,7 +39,6 @@ SYMBOLS = {
     'bffc_host_workspace_bytes': (_c.c_size_t, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     'bffc_fwd_host': (_c.c_int, [_c.c_void_p] * 6 + [_c.c_int] * 3 + [_c.c_void_p, _c.c_size_t, _c.c_void_p]),
     'bffc_last_launch_count': (_c.c_int, []),
-    'bffc_debug_fwd_stages': (_c.c_int, [_c.c_void_p] * 4 + [_c.c_int] * 3 + [_c.c_void_p, _c.c_int, _c.c_void_p]),
 }
 
 

@@ -167,14 +167,6 @@ int bffc_fwd_host(const bffc_plan* plan, const void* u_host, const void* kf_engi
 /* Number of kernel launches the last bffc_fwd / bffc_bwd / bffc_fwd_host on this thread enqueued (bench.py). */
 int bffc_last_launch_count(void);
 
-/*
- * Debug/bring-up hook (tests only): runs the forward for ONE (b-pair, h) unit and dumps the
- * fp32 TMEM accumulator image after every MMA stage into `dump` (stages x 128 lanes x 128 cols
- * floats).  Returns the number of stages written, or a negative error code.
- */
-int bffc_debug_fwd_stages(const bffc_plan* plan, const void* u, const void* kf_engine, void* y,
-                          int B, int H, int L, float* dump, int max_stages, void* stream);
-
 #ifdef __cplusplus
 }
 #endif
