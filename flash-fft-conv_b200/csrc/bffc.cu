@@ -1058,22 +1058,22 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
   dx.conj = kf_conj ? 0 : 1;
   const void* kfc = kf_conj ? kf_conj : kf;
   uint8_t *gate_x = nullptr, *gate_d = nullptr;
-  if (!gated) {
+  if (p->nlev > 0) {
+    // composite sizes: all passes share the transformed rows, chunk by chunk, below
+  } else if (!gated) {
     if (int rc = conv_forward(p, dout, kfc, nullptr, nullptr, du, B, H, L, workspace, st, &launches, dx)) return rc;
   } else {
     // y = q * conv(u*p, k)  (conv.py:3856-3939; kernels_bf16/..._bwd_kernel_bf16.h:836-906; host recompute
     // monarch_cuda_interface_bwd_bf16.cu:798-808).  With dx = corr(dout*q, k):
     //   dpostgate = dout * conv(u*p, k)                        — one pass of the forward path
     //   du = p * dx  and  dpregate = u * dx                    — ONE more pass with two gated outputs
-    // seqlen <= 8192: the dk_f kernel below needs u*p and dout*q — the gated inputs of these two passes, which store
-    // them into the tail of the workspace on the way (composite sizes gate inside their outer stages instead)
+    // the dk_f kernel below needs u*p and dout*q — the gated inputs of these two passes, which store them into the
+    // tail of the workspace on the way
     PassOpts p1;
-    if (p->nlev == 0) {
-      gate_x = static_cast<uint8_t*>(workspace) + (p->N < kInner ? small_fold_bytes(p, B, H) : 0);
-      gate_d = gate_x + gate_scratch_bytes(B, H, L) / 2;
-      p1.xg_out = gate_x;
-      dx.xg_out = gate_d;
-    }
+    gate_x = static_cast<uint8_t*>(workspace) + (p->N < kInner ? small_fold_bytes(p, B, H) : 0);
+    gate_d = gate_x + gate_scratch_bytes(B, H, L) / 2;
+    p1.xg_out = gate_x;
+    dx.xg_out = gate_d;
     if (int rc = conv_forward(p, u, kf, pregate, dout, dpostgate, B, H, L, workspace, st, &launches, p1)) return rc;
     dx.postgate2 = u;
     dx.y2 = dpregate;
@@ -1107,11 +1107,15 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
     CUDA_TRY(cudaGetLastError());
     launches += 1;
   } else {
-    // chunk by chunk: transformed u rows -> set U, transformed dout rows -> set D (set 0 is the level-0 intermediate
-    // when nlev == 2), then the dk_f kernel on the chunk's rows; batch chunks of a channel add into the same rows
+    // chunk by chunk: the outer stages turn u (* pregate) and dout (* postgate) into complex 8192-point rows ONCE
+    // (set U, set D; set 0 is the level-0 intermediate when nlev == 2).  The dk_f kernel reads both sets first; the
+    // convolution passes then run on the same rows in place — rows of dout with conj k_f -> inverse outer stages -> du
+    // (gated: x pregate, and x u -> dpregate from the same pass), gated: rows of u with k_f -> x dout -> dpostgate
+    // (conv.py:3856-3939; kernels_bf16/..._bwd_kernel_bf16.h:836-906).  Batch chunks of a channel add into the same dk_f rows.
     const View c = chunk_view(p, B, H, p->nlev + 1);
     const size_t bstride = size_t(H) * L * 2;
     auto at = [&](const void* t, int b0) { return t ? static_cast<const uint8_t*>(t) + size_t(b0) * bstride : nullptr; };
+    auto atw = [&](void* t, int b0) { return t ? static_cast<uint8_t*>(t) + size_t(b0) * bstride : nullptr; };
     for (int b0 = 0; b0 < B; b0 += c.B)
       for (int h0 = 0; h0 < H; h0 += c.H) {
         const View v{B - b0 < c.B ? B - b0 : c.B, H - h0 < c.H ? H - h0 : c.H, H, h0};
@@ -1121,11 +1125,7 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
         PlaneSet sD = plane_set(p, workspace, p->nlev == 2 ? 2 : 1, c.B, c.H);
         PlaneSet ru, rd;
         if (int rc = transform_fwd(p, at(u, b0), at(pregate, b0), v, L, s0, sU, &ru, st, &launches)) return rc;
-        if (p->nlev == 2) {
-          if (int rc = transform_fwd(p, at(dout, b0), at(postgate, b0), v, L, s0, sD, &rd, st, &launches)) return rc;
-        } else {
-          if (int rc = transform_fwd(p, at(dout, b0), at(postgate, b0), v, L, sD, sD, &rd, st, &launches)) return rc;
-        }
+        if (int rc = transform_fwd(p, at(dout, b0), at(postgate, b0), v, L, p->nlev == 2 ? s0 : sD, sD, &rd, st, &launches)) return rc;
         const int rows = v.H * p->R;
         CUtensorMap tur, tui, tdr, tdi;
         if (int rc = make_map(p, &tur, ru.re, vpairs * rows, kInner)) return rc;
@@ -1141,6 +1141,16 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
         FMT_SWITCH(p->dtype, (dkf3_kernel<true, F><<<grid, kThreadsDkf3, kSmemTotalDkf3, st>>>(tur, tdr, tui, tdi, prm)););
         CUDA_TRY(cudaGetLastError());
         launches += 1;
+        const size_t kf_off = size_t(h0) * p->NE * 4;
+        if (gated) {
+          if (int rc = launch_planes(p, ru.re, ru.im, static_cast<const uint8_t*>(kf) + kf_off, vpairs, rows, st, 0)) return rc;
+          launches += 1;
+          if (int rc = transform_inv(p, atw(dpostgate, b0), at(dout, b0), v, L, p->nlev == 2 ? s0 : sU, sU, st, &launches)) return rc;
+        }
+        if (int rc = launch_planes(p, rd.re, rd.im, static_cast<const uint8_t*>(kfc) + kf_off, vpairs, rows, st, dx.conj)) return rc;
+        launches += 1;
+        if (int rc = transform_inv(p, atw(du, b0), at(pregate, b0), v, L, p->nlev == 2 ? s0 : sD, sD, st, &launches,
+                                   gated ? at(u, b0) : nullptr, gated ? atw(dpregate, b0) : nullptr)) return rc;
       }
   }
   g_launches = launches;
