@@ -1,5 +1,5 @@
 #!/bin/bash
-touch flash-fft-conv_b200/libbffc.so
+# (the library is rebuilt on the box only if its source hash stamp disagrees with the tree)
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_parity_gpu.py -q -m gpu -k "kf_from_filter or dk_from_dkf or filter_fft" --maxfail=8 2>&1 | tail -5
 timeout 600 python tools/filter_bench.py 2>&1 | tail -40 | tee gpurun_out/filter_bench.log

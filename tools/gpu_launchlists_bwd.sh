@@ -1,5 +1,5 @@
 #!/bin/bash
-touch flash-fft-conv_b200/libbffc.so
+# (the library is rebuilt on the box only if its source hash stamp disagrees with the tree)
 mkdir -p gpurun_out
 for w in c2 c3 c4; do
   W=$w ITERS=2 timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 150 --csv --log-file gpurun_out/launches_fb_$w.csv \

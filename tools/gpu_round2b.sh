@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU visit: parity tests, fwd4 bring-up (BFFC_INNER=4), bench, same-box reference kernels
-touch flash-fft-conv_b200/libbffc.so
+# (the library is rebuilt on the box only if its source hash stamp disagrees with the tree)
 mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -q -m gpu --maxfail=12 2>&1 | tail -25 > gpurun_out/tests.log; cat gpurun_out/tests.log
 timeout 600 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -3 gpurun_out/bench_default.err

@@ -1,5 +1,5 @@
 #!/bin/bash
-touch flash-fft-conv_b200/libbffc.so
+# (the library is rebuilt on the box only if its source hash stamp disagrees with the tree)
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -q -m gpu --maxfail=12 -k "bwd or backward or c2_full or c3_full or ragged or golden or error_table" 2>&1 | tail -8 > gpurun_out/tests_bwd.log; cat gpurun_out/tests_bwd.log
 timeout 120 python tools/step_breakdown.py 2>&1 | tail -12

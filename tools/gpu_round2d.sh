@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2-GPU visit: NCCL multi-rank parity test, bench at --gpus 2 (both arms), PCIe probe with both ranks copying
-touch flash-fft-conv_b200/libbffc.so
+# (the library is rebuilt on the box only if its source hash stamp disagrees with the tree)
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo.txt 2>&1; head -12 gpurun_out/topo.txt
 timeout 900 python -m pytest tests/test_multigpu_gpu.py -q -m gpu 2>&1 | tail -5

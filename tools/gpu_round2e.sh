@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU visit: filter-side FFT tests first (fast fail), then the whole suite, bench
-touch flash-fft-conv_b200/libbffc.so
+# (the library is rebuilt on the box only if its source hash stamp disagrees with the tree)
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_parity_gpu.py -q -m gpu -k "kf_from_filter or dk_from_dkf or filter_fft" --maxfail=8 2>&1 | tail -25 > gpurun_out/tests_filter.log; cat gpurun_out/tests_filter.log
 timeout 1800 python -m pytest tests -q -m gpu --maxfail=12 2>&1 | tail -25 > gpurun_out/tests.log; cat gpurun_out/tests.log

@@ -1,5 +1,5 @@
 #!/bin/bash
-touch flash-fft-conv_b200/libbffc.so
+# (the library is rebuilt on the box only if its source hash stamp disagrees with the tree)
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_parity_full_gpu.py -q -m gpu -k "gated or Gated or table or fp16 or hyena or c3" --maxfail=10 2>&1 | tail -25 > gpurun_out/tests_gated.log; cat gpurun_out/tests_gated.log
 timeout 1800 python -m pytest tests -q -m gpu --maxfail=12 2>&1 | tail -8 > gpurun_out/tests.log; cat gpurun_out/tests.log
