@@ -84,7 +84,8 @@ def main():
     # ---- timing at the BASELINE configs (forward, k_f included as both modules do it per call; fwd+bwd)
     for name, (N, B, H, L, gated) in {'c2': (8192, 16, 768, 8192, False), 'c3': (32768, 8, 1024, 16384, True),
                                       'c4': (1048576, 2, 128, 1048576, False), 'c5': (4194304, 8, 16, 4194304, False),
-                                      'r1k': (1024, 64, 768, 1024, True), 'r8k': (8192, 64, 768, 8192, True)}.items():
+                                      'r256': (256, 64, 768, 256, True), 'r1k': (1024, 64, 768, 1024, True),
+                                      'r4k': (4096, 64, 768, 4096, True), 'r8k': (8192, 64, 768, 8192, True)}.items():
         torch.manual_seed(1)
         u = torch.randn(B, H, L, device=dev).to(torch.bfloat16)
         k = torch.randn(H, L, device=dev) / L ** 0.5

@@ -38,7 +38,7 @@ WORKLOADS = {
     'c4': (1048576, 2, 128, 1048576, False),  # configs[3]: HyenaDNA long range, B x H shard over 1..4 GPUs
     'c5': (4194304, 8, 64, 4194304, False),   # configs[4]: 8 x B200 B x H shard (H = 64 / n_gpus per rank)
     # the shape of the reference's own published table (README.md:224-231: gated conv, forward, "batch size 64, hidden
-    # dimension 768", H100-SXM: 0.29 ms at N=1K, 3.58 ms at N=8K) — the small-size path (folded linear convolution in
+    # dimension 768", H100-SXM: 0.29 ms at N=1K, 3.58 ms at N=8K) — the small-size path (8192/N batch members per unit of
     # the 8192-point engine) and the gated 8192 kernel get a measured line too
     'r1k': (1024, 64, 768, 1024, True),
     'r8k': (8192, 64, 768, 8192, True),

@@ -117,7 +117,7 @@ uint16_t f2bf(double x) {  // round-to-nearest-even float -> bf16 bits
 // kHalf: the source holds only frequencies 0..N/2 of a real filter (torch.fft.rfft); k > N/2 is conj(src[N-k]).
 template <bool kHalf, int kFmt>
 __global__ void kf_pack_kernel(const float2* __restrict__ kf_nat, uint4* __restrict__ kf_eng, int N, int R0, int R1,
-                               float scale, int conj) {
+                               float scale, int conj, int rblk) {
   const int h = blockIdx.y;
   const int R = R0 * R1;
   const float2* src = kf_nat + size_t(h) * (kHalf ? (N / 2 + 1) : N);
@@ -129,7 +129,8 @@ __global__ void kf_pack_kernel(const float2* __restrict__ kf_nat, uint4* __restr
     float2 e[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      int k = c0 + R0 * (c1 + R1 * (k1 + 128 * (4 * cc + i)));
+      // small sizes (rblk = seqlen/64 < 128): K_seqlen[f] = K_8192[f * 128/rblk] at f = (k1 mod rblk) + rblk k2
+      int k = c0 + R0 * (c1 + R1 * (((k1 & (rblk - 1)) + rblk * (4 * cc + i)) * (128 / rblk)));
       float sg = conj ? -1.f : 1.f;
       if (kHalf && k > N / 2) { k = N - k; sg = -sg; }
       const float2 t = src[k];
@@ -147,45 +148,6 @@ __global__ void kf_pack_kernel(const float2* __restrict__ kf_nat, uint4* __restr
 // through shared memory and both sides are accessed in 256-byte runs.
 // grid: (8192/2/32 word-pair tiles, R0/32 * R1, H)
 constexpr int kInnerWords = 8192;
-
-// small sizes: y[b,h,n] = t[n] + t[(n + off) mod 8192] (* postgate), n < L, inside the segment of batch member b:
-// scratch row = 2*(h*G + g) + (b & 1), segment s = (b >> 1) % S starting at s*2N, g = b / (2S).  8 elements per thread.
-template <int kFmt>
-__global__ void fold_kernel(const uint4* __restrict__ t, const uint4* __restrict__ postgate, uint4* __restrict__ y,
-                            const uint4* __restrict__ postgate2, uint4* __restrict__ y2,
-                            int L, int N, int S, int G, int H, int off, size_t rows) {
-  const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int per = L / 8;
-  if (idx >= rows * per) return;
-  const size_t r = idx / per;                       // b*H + h
-  const int v = int(idx - r * per);
-  const int b_ = int(r / H), h = int(r - size_t(b_) * H);
-  const int g = b_ / (2 * S), sg = (b_ >> 1) % S;
-  const size_t trow = (size_t(h) * G + g) * 2 + (b_ & 1);
-  const int v0 = sg * (2 * N / 8) + v;
-  const uint4 a = t[trow * 1024 + v0], b = t[trow * 1024 + ((v0 + off / 8) & 1023)];
-  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
-  uint32_t o[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float a0, a1, b0, b1;
-    bffc::upk2(bffc::Num<kFmt>::unpack(aw[i]), a0, a1);
-    bffc::upk2(bffc::Num<kFmt>::unpack(bw[i]), b0, b1);
-    o[i] = bffc::Num<kFmt>::pack(a0 + b0, a1 + b1);
-  }
-  if (y2) {
-    const uint4 g = postgate2[r * per + v];
-    y2[r * per + v] = make_uint4(bffc::Num<kFmt>::hmul2(o[0], g.x), bffc::Num<kFmt>::hmul2(o[1], g.y),
-                                 bffc::Num<kFmt>::hmul2(o[2], g.z), bffc::Num<kFmt>::hmul2(o[3], g.w));
-  }
-  if (postgate) {
-    const uint4 g = postgate[r * per + v];
-    const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] = bffc::Num<kFmt>::hmul2(o[i], gw[i]);
-  }
-  y[r * per + v] = make_uint4(o[0], o[1], o[2], o[3]);
-}
 
 template <bool kHalf, int kFmt>
 __global__ void kf_pack_tiled_kernel(const float2* __restrict__ kf_nat, uint2* __restrict__ kf_eng, int N, int R0, int R1,
@@ -226,8 +188,9 @@ constexpr int kInner = 8192;   // the fused tcgen05 kernel's size
 struct bffc_level { int tc; int R; };   // tc = 1: tcgen05 radix-128 stage (outer_r128.cuh); 0: CUDA-core radix 2/4/8
 
 struct bffc_plan {
-  int NE;        // engine FFT size: N for N >= 8192; 8192 for the small sizes (256..4096), which run as a linear
-                 // convolution inside the 8192-point kernel followed by a fold  y[n] = t[n] + t[n + N]
+  int NE;        // engine FFT size: N for N >= 8192; 8192 for the small sizes (256..4096): 8192/N batch members of a
+                 // channel run as independent N-point circular convolutions inside one 8192-point unit (stage 1 =
+                 // block-diagonal I (x) F_{N/64}), see r128_common.cuh
   int N;
   int R;         // N = R * 8192: product of the outer radices around the fused 8192-point kernel
   int nlev;      // number of outer levels (0, 1 or 2), outermost first
@@ -306,13 +269,16 @@ int bffc_plan_create(bffc_plan** out, int seqlen, int dtype) {
   PLAN_TRY(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
 
   const double PI = 3.14159265358979323846;
-  // outer radix-128 DFT of the fused kernel, cos / sin planes (symmetric, K-major rows)
+  // stage-1 DFT of the fused kernel, cos / sin planes (symmetric, K-major rows): F_128, or for the small sizes the
+  // block-diagonal I_{8192/N} (x) F_r, r = N/64 (one block per batch member sharing the unit)
   std::vector<uint16_t> c(128 * 128), s(128 * 128);
+  const int rblk = seqlen < kInner ? seqlen / 64 : 128;
   for (int m = 0; m < 128; ++m)
     for (int k = 0; k < 128; ++k) {
-      const double ang = 2.0 * PI * double((m * k) & 127) / 128.0;
-      c[m * 128 + k] = f2h16(cos(ang), dtype);
-      s[m * 128 + k] = f2h16(sin(ang), dtype);
+      const bool same = m / rblk == k / rblk;
+      const double ang = 2.0 * PI * double(((m % rblk) * (k % rblk)) % rblk) / double(rblk);
+      c[m * 128 + k] = f2h16(same ? cos(ang) : 0.0, dtype);
+      s[m * 128 + k] = f2h16(same ? sin(ang) : 0.0, dtype);
     }
   PLAN_TRY(cudaMalloc(&p->dftC, c.size() * 2));
   PLAN_TRY(cudaMalloc(&p->dftS, s.size() * 2));
@@ -423,7 +389,8 @@ int bffc_kf_pack(const bffc_plan* p, const void* kf_natural, void* kf_engine, in
   dim3 grid((p->NE / 4 + 255) / 256 > 32 ? 32 : (p->NE / 4 + 255) / 256, H);
   FMT_SWITCH(p->dtype, (kf_pack_kernel<false, F><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float2*>(kf_natural), static_cast<uint4*>(kf_engine), p->NE, p->nlev >= 1 ? p->lev[0].R : 1,
-      p->nlev == 2 ? p->lev[1].R : 1, p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj)););
+      p->nlev == 2 ? p->lev[1].R : 1, p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->N) : 1.0f, conj,
+      p->N < kInner ? p->N / 64 : 128)););
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -441,7 +408,8 @@ int bffc_kf_pack_rfft(const bffc_plan* p, const void* kf_half, void* kf_engine, 
   dim3 grid((p->NE / 4 + 255) / 256 > 32 ? 32 : (p->NE / 4 + 255) / 256, H);
   FMT_SWITCH(p->dtype, (kf_pack_kernel<true, F><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float2*>(kf_half), static_cast<uint4*>(kf_engine), p->NE, p->nlev >= 1 ? p->lev[0].R : 1,
-      p->nlev == 2 ? p->lev[1].R : 1, p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f, conj)););
+      p->nlev == 2 ? p->lev[1].R : 1, p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->N) : 1.0f, conj,
+      p->N < kInner ? p->N / 64 : 128)););
   CUDA_TRY(cudaGetLastError());
   return BFFC_OK;
 }
@@ -467,11 +435,11 @@ int bffc_kf_from_filter(const bffc_plan* p, const void* k, int Lk, void* kf_engi
   if (Lk > p->N) return fail(BFFC_ERR_INVALID, "bffc_kf_from_filter: Lk=%d exceeds seqlen %d", Lk, p->N);
   using namespace bffc::ffft;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const float scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->NE) : 1.0f;
+  const float scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f / float(p->N) : 1.0f;
   g_launches = 0;
   if (p->NE == kInner) {
     FMT_SWITCH(p->dtype, (kf_from_filter_kernel<F><<<(H + 1) / 2, kThreads, kSmemBytes, st>>>(
-        static_cast<const float*>(k), Lk, static_cast<uint4*>(kf_engine), H, scale, conj, p->tw8192)););
+        static_cast<const float*>(k), Lk, static_cast<uint4*>(kf_engine), H, scale, conj, p->tw8192, p->N < kInner ? p->N : kInner)););
     CUDA_TRY(cudaGetLastError());
     g_launches = 1;
     return BFFC_OK;
@@ -502,11 +470,11 @@ int bffc_dk_from_dkf(const bffc_plan* p, const void* dkf_engine, void* dk, int L
   using namespace bffc::ffft;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // fp16: both spectra carry 1/sqrt(128) (fused kernel) and 1/sqrt(R) per outer level: undo the product
-  const float fscale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 128.0f * float(p->R);
+  const float fscale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : float(p->N < kInner ? p->N / 64 : 128) * float(p->R);
   g_launches = 0;
   if (p->NE == kInner) {
     dk_from_dkf_kernel<<<H, kThreads, kSmemBytes, st>>>(static_cast<const float2*>(dkf_engine), static_cast<float*>(dk), Lk,
-                                                         fscale, p->N < kInner ? kInner - p->N : 0, p->tw8192);
+                                                         fscale, p->N < kInner ? p->N : kInner, p->tw8192);
     CUDA_TRY(cudaGetLastError());
     g_launches = 1;
     return BFFC_OK;
@@ -532,6 +500,13 @@ int bffc_dk_from_dkf(const bffc_plan* p, const void* dkf_engine, void* dk, int L
 
 int bffc_dkf_unpack(const bffc_plan* p, const void* dkf_engine, void* dkf_natural, int H, void* stream) {
   if (!p || !dkf_engine || !dkf_natural || H <= 0) return fail(BFFC_ERR_INVALID, "bffc_dkf_unpack: bad argument");
+  if (p->N < kInner) {
+    bffc::r128::dkf_unpack_small_kernel<<<dim3(kInner / 256, H), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float2*>(dkf_engine), static_cast<float2*>(dkf_natural), p->N,
+        p->dtype == BFFC_DTYPE_BF16 ? 1.0f : float(p->N / 64), 0);
+    CUDA_TRY(cudaGetLastError());
+    return BFFC_OK;
+  }
   dim3 grid(64, H);
   bffc::r128::dkf_unpack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float2*>(dkf_engine), static_cast<float2*>(dkf_natural), p->NE,
@@ -544,6 +519,13 @@ int bffc_dkf_unpack(const bffc_plan* p, const void* dkf_engine, void* dkf_natura
 
 int bffc_dkf_unpack_half(const bffc_plan* p, const void* dkf_engine, void* dkf_half, int H, void* stream) {
   if (!p || !dkf_engine || !dkf_half || H <= 0) return fail(BFFC_ERR_INVALID, "bffc_dkf_unpack_half: bad argument");
+  if (p->N < kInner) {
+    bffc::r128::dkf_unpack_small_kernel<<<dim3(kInner / 2 / 256 + 1, H), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float2*>(dkf_engine), static_cast<float2*>(dkf_half), p->N,
+        p->dtype == BFFC_DTYPE_BF16 ? 1.0f : float(p->N / 64), 1);
+    CUDA_TRY(cudaGetLastError());
+    return BFFC_OK;
+  }
   const int R0 = p->nlev >= 1 ? p->lev[0].R : 1, R1 = p->nlev >= 2 ? p->lev[1].R : 1, R = R0 * R1;
   dim3 grid(R < 32 ? 1 : R / 32, 128 * 2, H);
   bffc::r128::dkf_unpack_half_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -589,17 +571,8 @@ static View chunk_view(const bffc_plan* p, int B, int H, int sets) {
 // u*pregate and dout*postgate for the dk_f kernel of a gated backward at seqlen <= 8192 (two (B,H,L) tensors)
 static size_t gate_scratch_bytes(int B, int H, int L) { return 2 * ((size_t(B) * H * L * 2 + 255) & ~size_t(255)); }
 
-static size_t small_fold_bytes(const bffc_plan* p, int B, int H) {
-  const int S = 4096 / p->N, G = (B + 2 * S - 1) / (2 * S);
-  return size_t(H) * G * 2 * kInner * 2;
-}
-
 extern "C" size_t bffc_workspace_bytes_ex(const bffc_plan* p, int B, int H, int L, int gated, int backward) {
   if (!p) return 0;
-  if (p->N < kInner) {   // small sizes: S = 4096/N batch members share one 8192-point slot; scratch of full output tiles,
-                         // gated backward: + the two gated inputs of the dk_f kernel
-    return small_fold_bytes(p, B, H) + ((gated && backward) ? gate_scratch_bytes(B, H, L) : 0);
-  }
   if (p->nlev == 0) return (gated && backward) ? gate_scratch_bytes(B, H, L) : 0;
   // plane sets (real + imaginary plane each) of ONE chunk: forward nlev sets; backward nlev + 1 (transformed u and dout)
   const View vf = chunk_view(p, B, H, p->nlev);
@@ -641,10 +614,13 @@ static void fill_params(const bffc_plan* p, bffc::FwdParams& prm, const void* kf
   prm.gtiles = p->gtiles;
   // Normalisation.  bf16: the whole 1/N is folded into k_f by the pack kernel (as the reference folds it into a
   // twiddle table, conv.py:146).  fp16 cannot hold k_f/N (underflow): every DFT stage is scaled by 1/sqrt(radix)
-  // instead so intermediates stay near the input level: 1/sqrt(128) in the twiddle tables (passes 1 and 5),
+  // instead so intermediates stay near the input level: 1/sqrt(stage-1 radix) in the twiddle tables (passes 1 and 5),
   // 1/64 with the (unscaled) k_f in pass 3, 1/sqrt(R) per direction in the outer stages.
   prm.kf_scale = 1.0f / 64.0f;
-  prm.tw_scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 0.08838834764831845f;
+  const int rblk = p->N < kInner ? p->N / 64 : 128;            // stage-1 radix
+  prm.tw_scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 1.0f / sqrtf(float(rblk));
+  prm.tw_n = rblk * 64;
+  prm.tw_mask = rblk - 1;
   prm.pregate = nullptr;
   prm.postgate = nullptr;
   prm.postgate2 = nullptr;
@@ -675,11 +651,11 @@ static void trace_dump(cudaStream_t st) {
 }
 #endif
 
-// Segment geometry of the input tiles: S = 4096/N batch members per 8192-point slot for the small sizes, else 1.
+// Segment geometry of the input tiles: S = 8192/N batch members per 8192-point unit for the small sizes, else 1.
 struct SegGeom { int S, seg_rows, groups, kmask; };
 static SegGeom seg_geom(const bffc_plan* p, int B, int L) {
   SegGeom g;
-  g.S = p->N < kInner ? 4096 / p->N : 1;
+  g.S = p->N < kInner ? kInner / p->N : 1;
   g.seg_rows = 128 / g.S;
   g.groups = (B + 2 * g.S - 1) / (2 * g.S);
   g.kmask = 0;
@@ -691,31 +667,28 @@ static SegGeom seg_geom(const bffc_plan* p, int B, int L) {
 
 // optional extras of one pass of the forward path
 struct PassOpts {
-  int corr = 0;                     // 1: correlation (the du path of the backward): fold offset of the small sizes
   int conj = 0;                     // 1: conjugate k_f inside the kernel's pointwise multiply (else kf is pre-conjugated)
   const void* postgate2 = nullptr;  // second gated output y2 = postgate2 * conv(...) from the same pass
   void* y2 = nullptr;
   void* xg_out = nullptr;           // seqlen <= 8192, gated: the pass also stores its gated input u * pregate here
 };
 
-// fused 8192-point kernel on (B, H, L) real sequences.  Small sizes (p->N < 8192): `y` is the fold scratch.
+// fused 8192-point kernel on (B, H, L) real sequences (seqlen <= 8192)
 static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const void* pregate, const void* postgate,
                         void* y, int B, int H, int L, cudaStream_t st,
                         const PassOpts& po = PassOpts()) {
   if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen <= 8192 in this build", L);
-  const bool small = p->N < kInner;
   const SegGeom sg = seg_geom(p, B, L);
   CUtensorMap tm_u, tm_y, tm_g;
   if (int rc = make_map(p, &tm_u, u, B * H, L, sg.seg_rows)) return rc;
-  if (small) { if (int rc = make_map(p, &tm_y, y, H * sg.groups * 2, kInner)) return rc; }
-  else if (int rc = make_map(p, &tm_y, y, B * H, L)) return rc;
+  if (int rc = make_map(p, &tm_y, y, B * H, L, sg.seg_rows)) return rc;
   if (int rc = make_map(p, &tm_g, pregate ? pregate : u, B * H, L, sg.seg_rows)) return rc;
   bffc::FwdParams prm;
   fill_params(p, prm, kf);
   prm.pregate = static_cast<const uint32_t*>(pregate);
   prm.postgate = static_cast<const uint32_t*>(postgate);
-  prm.postgate2 = small ? nullptr : static_cast<const uint32_t*>(po.postgate2);   // small sizes: applied by the fold
-  prm.y2 = small ? nullptr : static_cast<uint32_t*>(po.y2);
+  prm.postgate2 = static_cast<const uint32_t*>(po.postgate2);
+  prm.y2 = static_cast<uint32_t*>(po.y2);
   prm.kf_conj_mask = po.conj ? 0x80008000u : 0u;
   prm.xg_out = pregate ? po.xg_out : nullptr;
   prm.B = B; prm.H = H; prm.L = L;
@@ -723,19 +696,17 @@ static int launch_fused(const bffc_plan* p, const void* u, const void* kf, const
   prm.kmask = sg.kmask;
   prm.nseg = sg.S;
   prm.seg_bytes = sg.seg_rows * 128;
-  prm.small_out = small ? 1 : 0;
   prm.units = H * prm.pairs;
   using namespace bffc::r128;
   const bool gated = pregate || postgate || prm.y2;
   // gate tiles travel by TMA like the inputs: pregate with the (segmented) geometry of u, output gates with that of y
   GateMaps gm{tm_g, tm_u, tm_u, tm_u, tm_u};
   if (prm.xg_out) { if (int rc = make_map(p, &gm.xg, prm.xg_out, B * H, L, sg.seg_rows)) return rc; }
-  if (!small && postgate) { if (int rc = make_map(p, &gm.post, postgate, B * H, L)) return rc; }
+  if (postgate) { if (int rc = make_map(p, &gm.post, postgate, B * H, L, sg.seg_rows)) return rc; }
   if (prm.y2) {
-    if (int rc = make_map(p, &gm.post2, prm.postgate2, B * H, L)) return rc;
-    if (int rc = make_map(p, &gm.y2, prm.y2, B * H, L)) return rc;
+    if (int rc = make_map(p, &gm.post2, prm.postgate2, B * H, L, sg.seg_rows)) return rc;
+    if (int rc = make_map(p, &gm.y2, prm.y2, B * H, L, sg.seg_rows)) return rc;
   }
-  if (small) prm.postgate = nullptr;                  // small sizes: the fold applies the output gates
   int g3 = (prm.units + kPipes3 - 1) / kPipes3;
   if (g3 > p->num_sms) g3 = p->num_sms;
   FMT_SWITCH(p->dtype,
@@ -765,7 +736,7 @@ static int launch_planes(const bffc_plan* p, void* pre, void* pim, const void* k
   fill_params(p, prm, kf);
   prm.B = 2 * pairs; prm.H = kf_rows; prm.L = kInner;
   prm.pairs = pairs;
-  prm.kmask = 0xff; prm.nseg = 1; prm.seg_bytes = 16384; prm.small_out = 0;
+  prm.kmask = 0xff; prm.nseg = 1; prm.seg_bytes = 16384;
   prm.units = kf_rows * pairs;
   prm.kf_conj_mask = conj ? 0x80008000u : 0u;
   using namespace bffc::r128;
@@ -967,24 +938,6 @@ static int check_common(const bffc_plan* p, int B, int H, int L, const void* a, 
 static int conv_forward(const bffc_plan* p, const void* u, const void* kf, const void* pregate, const void* postgate,
                         void* y, int B, int H, int L, void* ws, cudaStream_t st, int* launches,
                         const PassOpts& po = PassOpts()) {
-  const int corr = po.corr;
-  if (p->N < kInner) {
-    // small sizes (reference: the 2-stage / r2r kernels for 256..2048 and 16_16_16 for 4096, conv.py:78-131): zero-padded
-    // operands make the 8192-point circular result a LINEAR (corr = 0) convolution or correlation (corr = 1, du path)
-    // of support < 2N; folding it modulo N gives the N-point circular result.
-    // S = 4096/N batch members of a channel share one 8192-point slot (spacing 2N), so a unit carries 2S sequences.
-    const int off = corr ? kInner - p->N : p->N;
-    const SegGeom sg = seg_geom(p, B, L);
-    // gated small sizes: the pregate is multiplied in the kernel's pass 0, the output gates by the fold
-    if (int rc = launch_fused(p, u, kf, pregate, nullptr, ws, B, H, L, st, po)) return rc;
-    const size_t rows = size_t(B) * H, total = rows * (L / 8);
-    FMT_SWITCH(p->dtype, (fold_kernel<F><<<unsigned((total + 255) / 256), 256, 0, st>>>(
-        static_cast<const uint4*>(ws), static_cast<const uint4*>(postgate), static_cast<uint4*>(y),
-        static_cast<const uint4*>(po.postgate2), static_cast<uint4*>(po.y2), L, p->N, sg.S, sg.groups, H, off, rows)););
-    CUDA_TRY(cudaGetLastError());
-    *launches += 2;
-    return BFFC_OK;
-  }
   if (p->nlev == 0) {
     *launches += 1;
     return launch_fused(p, u, kf, pregate, postgate, y, B, H, L, st, po);
@@ -1054,7 +1007,6 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
   // pointwise multiply (a pre-conjugated kf_engine_conj is still accepted)
   // (reference: kernels_bf16/monarch_cuda_32_16_16_bwd_kernel_bf16.h:740-815)
   PassOpts dx;
-  dx.corr = 1;
   dx.conj = kf_conj ? 0 : 1;
   const void* kfc = kf_conj ? kf_conj : kf;
   uint8_t *gate_x = nullptr, *gate_d = nullptr;
@@ -1070,7 +1022,7 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
     // the dk_f kernel below needs u*p and dout*q — the gated inputs of these two passes, which store them into the
     // tail of the workspace on the way
     PassOpts p1;
-    gate_x = static_cast<uint8_t*>(workspace) + (p->N < kInner ? small_fold_bytes(p, B, H) : 0);
+    gate_x = static_cast<uint8_t*>(workspace);
     gate_d = gate_x + gate_scratch_bytes(B, H, L) / 2;
     p1.xg_out = gate_x;
     dx.xg_out = gate_d;
@@ -1088,7 +1040,12 @@ int bffc_bwd(const bffc_plan* p, const void* dout, const void* u, const void* kf
   prm.gtiles = p->gtiles;
   prm.dkf = static_cast<float2*>(dkf);
   prm.pairs = pairs;
-  prm.tw_scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 0.08838834764831845f;
+  {
+    const int rblk = p->N < kInner ? p->N / 64 : 128;          // stage-1 radix, as fill_params
+    prm.tw_scale = p->dtype == BFFC_DTYPE_BF16 ? 1.0f : 1.0f / sqrtf(float(rblk));
+    prm.tw_n = rblk * 64;
+    prm.tw_mask = rblk - 1;
+  }
   using namespace bffc::r128;
   if (p->nlev == 0) {
     if (L % 64 != 0) return fail(BFFC_ERR_UNSUPPORTED, "L=%d must be a multiple of 64 for seqlen <= 8192 in this build", L);

@@ -44,6 +44,7 @@ struct DkfParams {
   int B, H, L, pairs, kmask;  // pairs = batch groups per channel; kmask as in FwdParams
   int nseg, seg_bytes;        // segmented tiles (small sizes), see load_tile()
   float tw_scale;            // see FwdParams::tw_scale; dkf_unpack compensates
+  int tw_n, tw_mask;         // see FwdParams
 };
 
 namespace r128 {
@@ -262,8 +263,10 @@ dkf3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     float s0, c0, s1, c1;
-    sincospif(-2.0f * float((lane * (16 * wg + 2 * q)) & 8191) / 8192.0f, &s0, &c0);
-    sincospif(-2.0f * float((lane * (16 * wg + 2 * q + 1)) & 8191) / 8192.0f, &s1, &c1);
+    const int kl = lane & p.tw_mask;
+    const float tw_inv = 1.0f / float(p.tw_n);
+    sincospif(-2.0f * float((kl * (16 * wg + 2 * q)) & (p.tw_n - 1)) * tw_inv, &s0, &c0);
+    sincospif(-2.0f * float((kl * (16 * wg + 2 * q + 1)) & (p.tw_n - 1)) * tw_inv, &s1, &c1);
     twc[q] = __floats2half2_rn(c0 * p.tw_scale, c1 * p.tw_scale);
     tws[q] = __floats2half2_rn(s0 * p.tw_scale, s1 * p.tw_scale);
   }
@@ -423,6 +426,34 @@ __global__ void dkf_unpack_half_kernel(const float2* __restrict__ eng, float2* _
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {        // the Nyquist bin (self-conjugate partner)
     const float2 a = eng[dkf_engine_index(h, N / 2, R0, R1)];
     out[N / 2] = make_float2(a.x * scale, 0.f);
+  }
+}
+
+
+// Small sizes (seqlen N < 8192, one engine row per channel): the 8192/N stage-1 blocks hold different batch members at the
+// same N-point frequency f = (k1 mod r) + r k2, r = N/64.  Natural-order output on the 8192-point grid the plan reports
+// as its fft size: X[f * 8192/N] = (8192/N) sum_blocks dk_f (zero elsewhere), so that ifft_8192(X).real[:Lk] = dk.
+// half = 0: all 8192 bins; half = 1: bins 0..4096 of the Hermitian part (X[k] + conj X[8192 - k]) / 2 (for irfft).
+__global__ void dkf_unpack_small_kernel(const float2* __restrict__ eng, float2* __restrict__ out, int N, float scale, int half) {
+  const int h = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = N >> 6, q8 = 8192 / N;
+  const float2* src = eng + size_t(h) * 8192;
+  auto X = [&](int kk) {
+    float2 acc = make_float2(0.f, 0.f);
+    if (kk % q8) return acc;
+    const int f = kk / q8, k1p = f & (r - 1), k2 = f / r;
+    for (int m = 0; m < q8; ++m) {
+      const float2 v = src[(((k2 >> 4) * 128 + k1p + r * m) << 4) + (k2 & 15)];
+      acc.x += v.x; acc.y += v.y;
+    }
+    const float sc = scale * float(q8);
+    return make_float2(acc.x * sc, acc.y * sc);
+  };
+  if (!half) {
+    if (k < 8192) out[size_t(h) * 8192 + k] = X(k);
+  } else if (k <= 4096) {
+    const float2 a = X(k), b = X((8192 - k) & 8191);
+    out[size_t(h) * 4097 + k] = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
   }
 }
 

@@ -130,9 +130,12 @@ DEVINL void fft8192(float2* buf, int tid, const float2* __restrict__ tw) {
 DEVINL int pos_of_freq(int f) { return 512 * (f & 15) + 32 * ((f >> 4) & 15) + (f >> 8); }
 
 // grid = ceil(H / 2): channels 2*blockIdx.x (real part) and 2*blockIdx.x + 1 (imaginary part)
+// N < 8192 (small sizes): the engine row holds the N-point spectrum K_N[f] = K_8192[f * 8192/N] (k has support < N) at
+// (lane k1, column k2) -> f = (k1 mod N/64) + (N/64) k2, i.e. replicated over the 8192/N stage-1 blocks of the kernel.
 template <int kFmt>
 __global__ void __launch_bounds__(kThreads, 3) kf_from_filter_kernel(const float* __restrict__ k, int Lk, uint4* __restrict__ kf_eng,
-                                                                     int H, float scale, int conj, const float2* __restrict__ tw) {
+                                                                     int H, float scale, int conj, const float2* __restrict__ tw,
+                                                                     int N) {
   extern __shared__ float2 fbuf[];
   const int tid = threadIdx.x, ha = 2 * blockIdx.x, hb = ha + 1;
   const float* ka = k + size_t(ha) * Lk;
@@ -155,12 +158,13 @@ __global__ void __launch_bounds__(kThreads, 3) kf_from_filter_kernel(const float
   // frequencies k1 + 128 (4c + j), j = 0..3, as (re01, im01, re23, im23)
   using NT = Num<kFmt>;
   const float sa = 0.5f * scale, sgn = conj ? -1.f : 1.f;
+  const int r = N >> 6, q8 = kN / N;                  // stage-1 block size, spectrum stride
   for (int v = tid; v < kN / 4; v += kThreads) {
     const int c = v >> 7, k1 = v & 127;
     float2 A[4], Bv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int f = k1 + 128 * (4 * c + j);
+      const int f = ((k1 & (r - 1)) + r * (4 * c + j)) * q8;
       const float2 z = fbuf[slot(pos_of_freq(f))], zc = fbuf[slot(pos_of_freq((kN - f) & (kN - 1)))];
       A[j] = make_float2((z.x + zc.x) * sa, (z.y - zc.y) * sa * sgn);
       Bv[j] = make_float2((z.y + zc.y) * sa, (zc.x - z.x) * sa * sgn);
@@ -173,26 +177,37 @@ __global__ void __launch_bounds__(kThreads, 3) kf_from_filter_kernel(const float
   }
 }
 
-// grid = H.  dk[n] = scale/8192 * Re( c[n] + (fold ? c[fold_off + n] : 0) ),  c = inverse DFT of dk_f, n < Lk.
-// Engine order of dk_f (dkf_r128.cuh): index ((qd*128 + k1)*16 + k2l) holds frequency k1 + 128 (16 qd + k2l).
+// grid = H.  dk[n] = scale/N * Re( sum_f D_N[f] e^{2 pi i f n / N} ), n < Lk.
+// Engine order of dk_f (dkf3_r128.cuh): index ((qd*128 + k1)*16 + k2l) holds (lane k1, column k2 = 16 qd + k2l).
+// N = 8192: frequency k1 + 128 k2.  N < 8192: the 8192/N stage-1 blocks hold different batch members at the same
+// N-point frequency f = (k1 mod r) + r k2, r = N/64; their sum D_N[f] goes to 8192-point frequency f * 8192/N (the rest
+// is zero), whose inverse transform is the N-periodic gradient.
 __global__ void __launch_bounds__(kThreads, 3) dk_from_dkf_kernel(const float2* __restrict__ dkf_eng, float* __restrict__ dk, int Lk,
-                                                                  float scale, int fold_off, const float2* __restrict__ tw) {
+                                                                  float scale, int N, const float2* __restrict__ tw) {
   extern __shared__ float2 fbuf[];
   const int tid = threadIdx.x, h = blockIdx.x;
   const float2* src = dkf_eng + size_t(h) * kN;
+  if (N == kN) {
 #pragma unroll 16
-  for (int e = tid; e < kN; e += kThreads) {
-    const int k2l = e & 15, k1 = (e >> 4) & 127, qd = e >> 11;
-    fbuf[slot(k1 + 128 * (16 * qd + k2l))] = __ldg(src + e);
+    for (int e = tid; e < kN; e += kThreads) {
+      const int k2l = e & 15, k1 = (e >> 4) & 127, qd = e >> 11;
+      fbuf[slot(k1 + 128 * (16 * qd + k2l))] = __ldg(src + e);
+    }
+  } else {
+    const int r = N >> 6, q8 = kN / N;
+    for (int e = tid; e < kN; e += kThreads) fbuf[slot(e)] = make_float2(0.f, 0.f);
+    __syncthreads();
+    for (int f = tid; f < N; f += kThreads) {
+      const int k1p = f & (r - 1), k2 = f / r;
+      float2 acc = make_float2(0.f, 0.f);
+      for (int m = 0; m < q8; ++m) acc = cadd(acc, __ldg(src + (((k2 >> 4) * 128 + k1p + r * m) << 4) + (k2 & 15)));
+      fbuf[slot(f * q8)] = acc;
+    }
   }
   __syncthreads();
   fft8192<1>(fbuf, tid, tw);
-  const float s = scale * (1.0f / float(kN));
-  for (int n = tid; n < Lk; n += kThreads) {
-    float c = fbuf[slot(pos_of_freq(n))].x;
-    if (fold_off) c += fbuf[slot(pos_of_freq((fold_off + n) & (kN - 1)))].x;
-    dk[size_t(h) * Lk + n] = c * s;
-  }
+  const float s = scale / float(N);
+  for (int n = tid; n < Lk; n += kThreads) dk[size_t(h) * Lk + n] = fbuf[slot(pos_of_freq(n))].x * s;
 }
 
 // =====================================================================================================================

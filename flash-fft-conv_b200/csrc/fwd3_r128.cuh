@@ -99,11 +99,10 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
   const int u_end = int((long long)p.units * (gp + 1) / GP);
   const uint32_t s_slot0 = sbase + pipe * 2 * kSlotBytes;
 
-  auto seq_index = [&](int unit, int which) {
+  auto seq_index = [&](int unit, int which) {      // complex-rows mode: plane row of the unit
     const int h = unit / p.pairs, pr = unit - h * p.pairs;
-    if (kPlanes) return pr * p.H + h;
-    if (p.small_out) return 2 * unit + which;
-    return (2 * pr + which) * p.H + h;
+    (void)which;
+    return pr * p.H + h;
   };
   auto issue_load = [&](int unit, int slot) {
     const uint32_t bar = bar_tma0 + 8 * slot;
@@ -156,17 +155,19 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     }
     tmem_st_wait();
   }
-  // twiddles W_N^{k1*j} (k1 = lane), factored as A[j >> 3] * B[j & 7]: B (8 columns, half2 pairs) is a table, A is
+  // twiddles W_N^{k1*j} (k1 = lane; small sizes: lane mod N/64, period N), factored as A[j >> 3] * B[j & 7]: B (8 columns, half2 pairs) is a table, A is
   // advanced block by block with the per-lane step W_N^{8*k1} (fp32 recurrence over 8 blocks).  10 registers instead of
   // 64: with the full shared-memory carve-out there is no L1 behind local memory, so spills cost an L2 round trip.
   f32x2 twBc[4], twBs[4];
   float stc, sts;
-  sincospif(-2.0f * float(lane * 8) / 8192.0f, &sts, &stc);
+  const int kl = lane & p.tw_mask;          // frequency index inside the stage-1 block (small sizes: N/64-point blocks)
+  const float tw_inv = 1.0f / float(p.tw_n);
+  sincospif(-2.0f * float(kl * 8) * tw_inv, &sts, &stc);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float s0, c0, s1, c1;
-    sincospif(-2.0f * float(lane * (2 * q)) / 8192.0f, &s0, &c0);
-    sincospif(-2.0f * float(lane * (2 * q + 1)) / 8192.0f, &s1, &c1);
+    sincospif(-2.0f * float(kl * (2 * q)) * tw_inv, &s0, &c0);
+    sincospif(-2.0f * float(kl * (2 * q + 1)) * tw_inv, &s1, &c1);
     twBc[q] = pk2(c0, c1);
     twBs[q] = pk2(s0, s1);
   }
@@ -216,6 +217,18 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     st_shared_v4(sX + kTileBytes + off, im4[0], im4[1], im4[2], im4[3]);
   };
 
+  // mirror of load_tile: the (up to two) tiles of a unit go back segment by segment, existing batch members only; rows
+  // beyond L/64 of a segment are outside the tensor map and dropped
+  auto store_tiles = [&](const CUtensorMap* my, uint32_t sT, int unit) {
+    const int uh = unit / p.pairs, ug = unit - uh * p.pairs;
+    for (int w = 0; w < 2; ++w)
+      for (int sg = 0; sg < p.nseg; ++sg) {
+        const int b = (ug * p.nseg + sg) * 2 + w;
+        if (b < p.B) tma_store_3d(my, sT + w * kTileBytes + sg * p.seg_bytes, 0, 0, b * p.H + uh);
+      }
+    tma_store_commit();
+  };
+
   if (lead_warp) mbar_wait(bar_g, 0);     // DFT-64 tiles have landed (long ago: hidden behind the table set-up)
 
   for (int unit = u_begin, n = 0; unit < u_end; ++unit, ++n) {
@@ -238,23 +251,15 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         sync_pipe_smem();                 // products visible to the tensor core; slot 1 is free again
       }
       if (emit_xg && lead_warp) {
-        if (elect_one()) {                // mirror of load_tile: segments of existing batch members only
-          const int ug = unit - h * p.pairs;
-          for (int w = 0; w < 2; ++w)
-            for (int sg = 0; sg < p.nseg; ++sg) {
-              const int b = (ug * p.nseg + sg) * 2 + w;
-              if (b < p.B) tma_store_3d(&gm.xg, sX + w * kTileBytes + sg * p.seg_bytes, 0, 0, b * p.H + h);
-            }
-          tma_store_commit();
-        }
+        if (elect_one()) store_tiles(&gm.xg, sX, unit);
         __syncwarp();
       }
       if (has_post && lead_warp) {
         if (elect_one()) {
           const int ug = unit - h * p.pairs;
           mbar_expect_tx(bar_gate, kSlotBytes);
-          load_tile(sGate, &gm.post, bar_gate, p.B, p.H, h, ug, 0, 1, 0);
-          load_tile(sGate + kTileBytes, &gm.post, bar_gate, p.B, p.H, h, ug, 1, 1, 0);
+          load_tile(sGate, &gm.post, bar_gate, p.B, p.H, h, ug, 0, p.nseg, p.seg_bytes);
+          load_tile(sGate + kTileBytes, &gm.post, bar_gate, p.B, p.H, h, ug, 1, p.nseg, p.seg_bytes);
         }
         __syncwarp();
       }
@@ -479,11 +484,13 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
       }
     };
     auto store_out = [&](const CUtensorMap* my) {
-      const int pr = unit - h * p.pairs;
-      tma_store_3d(my, sX, 0, 0, seq_index(unit, 0));
-      if (kPlanes) tma_store_3d(&tm_g, sX + kTileBytes, 0, 0, seq_index(unit, 1));
-      else if (p.small_out || 2 * pr + 1 < p.B) tma_store_3d(my, sX + kTileBytes, 0, 0, seq_index(unit, 1));
-      tma_store_commit();
+      if (kPlanes) {
+        tma_store_3d(my, sX, 0, 0, seq_index(unit, 0));
+        tma_store_3d(&tm_g, sX + kTileBytes, 0, 0, seq_index(unit, 1));
+        tma_store_commit();
+      } else {
+        store_tiles(my, sX, unit);
+      }
     };
     if (has_post) { mbar_wait(bar_gate, gate_phase); gate_phase ^= 1; }
     pass6(has_post);
@@ -495,8 +502,8 @@ fwd3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         if (has_post2) {                  // slot 1 has been read by every thread (barrier above): second gate -> slot 1
           const int ug = unit - h * p.pairs;
           mbar_expect_tx(bar_gate, kSlotBytes);
-          load_tile(sGate, &gm.post2, bar_gate, p.B, p.H, h, ug, 0, 1, 0);
-          load_tile(sGate + kTileBytes, &gm.post2, bar_gate, p.B, p.H, h, ug, 1, 1, 0);
+          load_tile(sGate, &gm.post2, bar_gate, p.B, p.H, h, ug, 0, p.nseg, p.seg_bytes);
+          load_tile(sGate + kTileBytes, &gm.post2, bar_gate, p.B, p.H, h, ug, 1, p.nseg, p.seg_bytes);
           tma_store_wait_read0();         // the first output has left slot 0
         }
       }

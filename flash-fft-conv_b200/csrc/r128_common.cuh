@@ -34,9 +34,9 @@ struct FwdParams {
   int B, H, L;               // batch, channels, sequence length
   int pairs;                 // ceil(B/2)
   int kmask;                 // bit s set: 16-row K step s of the input tile can be non-zero (the rest is skipped)
-  int nseg;                  // segments per tile (small sizes: 4096/N batch members share one 8192 slot), else 1
+  int nseg;                  // segments per tile (small sizes: 8192/N batch members share one 8192-point slot), else 1
   int seg_bytes;             // bytes of one segment inside a tile = (128 / nseg) rows x 128 B
-  int small_out;             // 1: store the full tiles to the fold scratch, row = 2*unit + which
+  int tw_n, tw_mask;         // stage-1 twiddles W_{tw_n}^{(lane & tw_mask) j}: 8192 / 127, small sizes N / (N/64 - 1)
   int units;                 // H * pairs
   uint32_t kf_conj_mask;     // 0x80008000: multiply by conj(k_f) (du path of the backward: correlation), else 0
   long long* trace;          // bring-up builds only (-DBFFC_BRINGUP): clock64 stamps of CTA 0, [pipe][warp 0|3][unit][16]
@@ -68,9 +68,11 @@ DEVINL void cmul(float ar, float ai, float br, float bi, float& cr, float& ci) {
 }
 DEVINL uint64_t tile_desc(uint32_t saddr) { return make_sdesc(saddr, kTileBytes, 1024, 2); }
 
-// One (128 x 64) input tile = nseg segments; segment s is the zero-padded (TMA out-of-bounds fill) start of batch member
-// b = (g*nseg + s)*2 + which of channel h.  nseg == 1 is the ordinary case b = 2g + which.  A member beyond the batch
-// is fetched from sequence index B*H, which is out of bounds for the tensor map: an all-zero tile.
+// One (128 x 64) input tile = nseg segments of 128/nseg rows; segment s holds batch member b = (g*nseg + s)*2 + which
+// of channel h (rows beyond L/64: TMA out-of-bounds zero fill = implicit padding).  nseg == 1 is the ordinary case
+// b = 2g + which.  Small sizes N < 8192: nseg = 8192/N members, each an independent N-point circular convolution —
+// stage 1 uses the block-diagonal matrix I_nseg (x) F_{N/64} instead of F_128, the rest of the kernel is unchanged.
+// A member beyond the batch is fetched from sequence index B*H, out of bounds for the tensor map: an all-zero tile.
 DEVINL void load_tile(uint32_t dst, const void* map, uint32_t bar, int B, int H, int h, int g, int which, int nseg,
                       int seg_bytes) {
   for (int s = 0; s < nseg; ++s) {

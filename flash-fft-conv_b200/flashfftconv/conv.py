@@ -102,7 +102,7 @@ class FlashFFTConv(torch.nn.Module):
         return self._plans[key]
 
     def fft_size(self, device):
-        """FFT size of the engine: seqlen, or 8192 for the small sizes (computed as a folded linear convolution)."""
+        """FFT size of the engine: seqlen, or 8192 for the small sizes (8192/seqlen batch members share one 8192-point unit)."""
         return _lib.lib().bffc_fft_size(self.plan(device).handle)
 
     def forward_host(self, u, k, pregate=None, postgate=None, out=None, device=None):
@@ -280,7 +280,7 @@ def _bwd(mod, dout, u, kf_engine, k_len, pregate, postgate):
         mod.last_launches = _lib.lib().bffc_last_launch_count()
         # the kernels accumulate unnormalised pair-packed spectra in engine order; the reference takes
         # ifft(dk_f).real[..., :k_len] (conv.py:1817-1820): inverse fp32 FFT straight from engine order, 1/N, real part
-        # (only the Hermitian part of dk_f contributes), fold of the small sizes, [:k_len]
+        # (only the Hermitian part of dk_f contributes), sum over the batch-member blocks of the small sizes, [:k_len]
         dk = torch.empty((H, k_len), dtype=torch.float32, device=u.device)
         fws, fws_bytes = _filter_workspace(plan, H, u.device)
         _lib.check(_lib.lib().bffc_dk_from_dkf(plan.handle, _ptr(dkf_engine), _ptr(dk), int(k_len), H, _ptr(fws), fws_bytes,

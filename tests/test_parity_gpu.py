@@ -253,7 +253,7 @@ def test_bwd_long_vs_oracle(ffc, N, B, H, L):
     _check(k.grad, dk_ref, f'dk N={N}')
 
 
-# ----------------------------------------------------------------------------- small sizes (folded linear convolution in the 8192 kernel)
+# ----------------------------------------------------------------------------- small sizes (8192/N batch members per unit, block-diagonal stage 1)
 @pytest.mark.parametrize('N,B,H,L', [(256, 2, 3, 256), (256, 3, 2, 128), (512, 2, 2, 512), (1024, 2, 16, 1024),
                                      (2048, 1, 3, 1024), (4096, 4, 5, 4096), (4096, 2, 2, 2048),
                                      # several batch members per 8192-point slot, ragged last group
@@ -398,11 +398,17 @@ OUTER = {8192: (1, 1), 16384: (2, 1), 32768: (4, 1), 65536: (8, 1), 131072: (8, 
          1048576: (128, 1), 2097152: (128, 2), 4194304: (128, 4)}
 
 
-def _engine_freqs(NE):
-    """(NE/4, 4) natural frequency held by component j of engine vector v of one channel: row = v // 2048 = c0*R1 + c1,
-    inside a row vector cc*128 + k1 holds inner frequencies k'' = k1 + 128*(4cc + j); k = c0 + R0*(c1 + R1*k'')."""
-    R0, R1 = OUTER[NE]
-    v = torch.arange(NE // 4)
+def _engine_freqs(N):
+    """(NE/4, 4) frequency of the N-point spectrum held by component j of engine vector v of one channel.
+    N >= 8192: row = v // 2048 = c0*R1 + c1, inside a row vector cc*128 + k1 holds inner frequencies
+    k'' = k1 + 128*(4cc + j); k = c0 + R0*(c1 + R1*k'').  N < 8192 (one row): lane k1 belongs to stage-1 block k1 // r,
+    r = N/64, and holds frequency (k1 mod r) + r*(4cc + j) — the N-point spectrum replicated over the 8192/N blocks."""
+    if N < 8192:
+        r = N // 64
+        rem = torch.arange(2048)
+        return ((rem % 128) % r)[:, None] + r * (4 * (rem // 128)[:, None] + torch.arange(4)[None, :])
+    R0, R1 = OUTER[N]
+    v = torch.arange(N // 4)
     row, rem = v // 2048, v % 2048
     inner = (rem % 128)[:, None] + 128 * (4 * (rem // 128)[:, None] + torch.arange(4)[None, :])
     return (row // R1)[:, None] + R0 * ((row % R1)[:, None] + R1 * inner)
@@ -413,7 +419,7 @@ def _rfft_natural(mod, k):
 
 
 KF_CASES = [(8192, 5, 8192, torch.bfloat16), (8192, 4, 1000, torch.bfloat16), (1024, 3, 1024, torch.bfloat16),
-            (8192, 2, 8192, torch.float16)] + \
+            (256, 2, 200, torch.bfloat16), (4096, 3, 4096, torch.float16), (8192, 2, 8192, torch.float16)] + \
            [(n, 3, n, torch.bfloat16) for n in sorted(OUTER) if n > 8192] + \
            [(16384, 2, 8192, torch.float16), (32768, 5, 16384, torch.bfloat16), (65536, 1, 1001, torch.bfloat16),
             (1048576, 2, 524288, torch.float16), (4194304, 1, 2097153, torch.bfloat16)]
@@ -431,14 +437,13 @@ def test_kf_from_filter_matches_fft(ffc, N, H, Lk, dtype, conj):
     torch.manual_seed(5)
     mod = ffc.FlashFFTConv(N, dtype=dtype).cuda()
     plan = mod.plan(torch.device('cuda', 0))
-    NE = mod.fft_size(torch.device('cuda', 0))
     k = (torch.randn(H, Lk) * torch.exp(-0.002 * torch.arange(Lk).clamp_max(4000))).cuda()
-    kf = torch.fft.fft(k.double().cpu(), n=NE)
+    kf = torch.fft.fft(k.double().cpu(), n=N)
     if dtype == torch.bfloat16:
-        kf = kf / NE
+        kf = kf / N
     if conj:
         kf = kf.conj()
-    want = kf[:, _engine_freqs(NE)]                                    # (H, NE/4, 4)
+    want = kf[:, _engine_freqs(N)]                                     # (H, NE/4, 4)
     want = torch.complex(want.real.float().to(dtype).float(), want.imag.float().to(dtype).float())
     ulp = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10    # largest relative spacing of the 16-bit format
     tol = ulp * want.abs().clamp_min(1e-30) * 1.5 + 2e-6 * want.abs().max()     # both components may flip one spacing
@@ -485,7 +490,14 @@ def test_dk_from_dkf_matches_unpack_ifft(ffc, N, H, Lk):
     ffc._lib.check(lib.bffc_dkf_unpack(plan.handle, dkf.data_ptr(), torch.view_as_real(nat).data_ptr(), H, None))
     c = torch.fft.ifft(nat.to(torch.complex128), dim=-1).real.float()
     if N < 8192:
-        c = c[..., :N] + c[..., 8192 - N:]
+        # independent statement for the small sizes: the 8192/N stage-1 blocks (lanes k1 = k1' + r m) hold different batch
+        # members at the same N-point frequency f = k1' + r k2; dk = ifft_N(sum over blocks).real
+        r = N // 64
+        eng = torch.view_as_complex(dkf.view(H, 4, 128, 16, 2).contiguous()).permute(0, 2, 1, 3).reshape(H, 128, 64)   # [h][k1][k2]
+        D = eng.reshape(H, 128 // r, r, 64).sum(1).permute(0, 2, 1).reshape(H, N)                      # f = k1' + r k2
+        c_small = torch.fft.ifft(D.to(torch.complex128), dim=-1).real.float()
+        assert torch.allclose(c[..., :N], c_small, rtol=1e-4, atol=2e-5 * c_small.abs().max().item())
+        c = c_small
     dk = torch.empty(H, Lk, device='cuda')
     nbytes = lib.bffc_filter_workspace_bytes(plan.handle, H)
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device='cuda')
