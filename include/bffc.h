@@ -64,8 +64,12 @@ int bffc_supported(int seqlen, int dtype);
  */
 int bffc_plan_create(bffc_plan** plan, int seqlen, int dtype);
 int bffc_plan_destroy(bffc_plan* plan);
-/* FFT size n the caller must use for k_f = rfft(k, n) / for the inverse FFT of dk_f: seqlen for seqlen >= 8192;
- * 8192 for the small sizes (256..4096), whose dk then is dk[i] = c[i] + c[8192 - seqlen + i], c = ifft(dk_f).real */
+/* FFT size n of the natural-order spectra at this boundary (k_f = rfft(k, n) handed to bffc_kf_pack*, the natural-order
+ * dk_f bffc_dkf_unpack* return, the H x n engine buffers): seqlen for seqlen >= 8192; 8192 for the small sizes (256..4096).
+ * A small size runs 8192/seqlen batch members per 8192-point unit as independent seqlen-point circular convolutions; its
+ * filter spectrum is the 8192-point spectrum of the zero-extended filter sampled at multiples of 8192/seqlen (the pack
+ * functions do that), and bffc_dkf_unpack* return the gradient spectrum on the same 8192-point grid (non-zero at those
+ * multiples only), so dk = ifft(dk_f, n).real[:, :Lk] holds for every size. */
 int bffc_fft_size(const bffc_plan* plan);
 /* L passed to bffc_fwd / bffc_bwd / bffc_fwd_host must be a multiple of this: 64 for seqlen <= 8192 (TMA tiles of 64
  * columns), 8 for 16K..512K (16-byte vectors of the CUDA-core outer stage), seqlen/128 for 1M / 2M / 4M (whole rows of the
@@ -104,7 +108,7 @@ int bffc_dkf_unpack_half(const bffc_plan* plan, const void* dkf_engine, void* dk
  *   bffc_kf_from_filter: k (H, Lk) fp32 device, Lk <= seqlen  ->  kf_engine  = bffc_kf_pack_rfft(rfft(k, n = fft size))
  *                        (replaces conv.py:572-575 + :640; two real channels share one complex FFT)
  *   bffc_dk_from_dkf:    dkf_engine (H, fft size) float2 as written by bffc_bwd  ->  dk (H, Lk) fp32
- *                        = ifft(unpack(dkf)).real[:, :Lk] incl. the fold of the small sizes (replaces conv.py:1817-1820)
+ *                        = ifft(unpack(dkf)).real[:, :Lk], small sizes summed over their batch-member blocks (replaces conv.py:1817-1820)
  * Plans with fft size 8192 (seqlen <= 8192): one launch, no workspace (NULL / 0).  Composite sizes N = R * 8192: per group
  * of channels one launch of R-point column FFTs and one of 8192-point row FFTs, with (channels, R/2 + 1, 8192) complex64
  * between them in `workspace`.  bffc_filter_workspace_bytes(plan, H) is the recommended size (a group that stays in L2,
