@@ -41,6 +41,25 @@ class _Plan:
         self.device = device
         with torch.cuda.device(device):
             _lib.check(_lib.lib().bffc_plan_create(ctypes.byref(self.handle), int(seqlen), _DT[dtype]))
+        # constants of the plan and memoised size queries: the per-call host path is a handful of ctypes calls, and at
+        # C2 a forward step is 0.16 ms of GPU work — Python overhead shows up as launch gaps (8 ranks per box: 0.18 ms)
+        self.fft_size = _lib.lib().bffc_fft_size(self.handle)
+        self.length_multiple = _lib.lib().bffc_length_multiple(self.handle)
+        self._ws_bytes = {}
+        self._filter_ws_bytes = {}
+
+    def workspace_bytes(self, B, H, L, gated, backward):
+        key = (B, H, L, gated, backward)
+        n = self._ws_bytes.get(key)
+        if n is None:
+            n = self._ws_bytes[key] = _lib.lib().bffc_workspace_bytes_ex(self.handle, B, H, L, int(gated), int(backward))
+        return n
+
+    def filter_workspace_bytes(self, H):
+        n = self._filter_ws_bytes.get(H)
+        if n is None:
+            n = self._filter_ws_bytes[H] = _lib.lib().bffc_filter_workspace_bytes(self.handle, int(H))
+        return n
 
     def __del__(self):
         try:
@@ -103,7 +122,7 @@ class FlashFFTConv(torch.nn.Module):
 
     def fft_size(self, device):
         """FFT size of the engine: seqlen, or 8192 for the small sizes (8192/seqlen batch members share one 8192-point unit)."""
-        return _lib.lib().bffc_fft_size(self.plan(device).handle)
+        return self.plan(device).fft_size
 
     def forward_host(self, u, k, pregate=None, postgate=None, out=None, device=None):
         """Forward on HOST tensors: y = forward(u.cuda(), k.cuda(), ...).cpu(), with the host->device copies, the
@@ -132,7 +151,7 @@ def _forward_host(mod, u, k, pregate, postgate, out, device):
     B, H, L = u.shape
     if k.dim() != 2 or k.shape[0] != H or k.shape[1] > mod.seqlen or L > mod.seqlen:
         raise RuntimeError(f'k must be (H={H}, Lk<={mod.seqlen}) and L <= seqlen, got {tuple(k.shape)}, L={L}')
-    if L % _lib.lib().bffc_length_multiple(mod.plan(device).handle):
+    if L % mod.plan(device).length_multiple:
         raise RuntimeError(f'forward_host: L={L} must be a multiple of bffc_length_multiple(); pad on the host or '
                            'use forward() with device tensors')
     if out is None:
@@ -185,7 +204,7 @@ def _pack_kf_from_natural(mod, plan, k_f, conj):
 
 
 def _filter_workspace(plan, H, device):
-    n = _lib.lib().bffc_filter_workspace_bytes(plan.handle, int(H))
+    n = plan.filter_workspace_bytes(H)
     return (torch.empty(n, dtype=torch.uint8, device=device) if n else None), n
 
 
@@ -193,9 +212,11 @@ def _pack_kf(mod, plan, k, conj=0):
     """k (H, Lk) fp32 device -> engine-order packed spectrum (H, N) int32 words by the library's own fp32 FFT
     (bffc_kf_from_filter): one launch for engine size 8192, column + row FFT launches per L2-sized channel group for
     the composite sizes (replaces conv.py:575 + :640)."""
-    k32 = k.detach().to(torch.float32).contiguous()
+    k32 = k.detach()
+    if k32.dtype != torch.float32 or not k32.is_contiguous():
+        k32 = k32.to(torch.float32).contiguous()
     H, Lk = k32.shape
-    kf_engine = torch.empty((H, mod.fft_size(k.device)), dtype=torch.int32, device=k.device)
+    kf_engine = torch.empty((H, plan.fft_size), dtype=torch.int32, device=k.device)
     ws, ws_bytes = _filter_workspace(plan, H, k.device)
     _lib.check(_lib.lib().bffc_kf_from_filter(plan.handle, _ptr(k32), int(Lk), _ptr(kf_engine), int(H), int(conj),
                                               _ptr(ws), ws_bytes, _stream()))
@@ -217,7 +238,7 @@ def _kf_engine_for(mod, plan, k, cache_key=None):
 
 
 def _pad_len(mod, device, L):
-    q = _lib.lib().bffc_length_multiple(mod.plan(device).handle)
+    q = mod.plan(device).length_multiple
     return (L + q - 1) // q * q
 
 
@@ -232,8 +253,23 @@ def _padded(t, Lp):
 
 
 def _workspace(plan, B, H, L, gated, backward, device):
-    n = _lib.lib().bffc_workspace_bytes_ex(plan.handle, B, H, L, int(gated), int(backward))
+    n = plan.workspace_bytes(B, H, L, gated, backward)
     return (torch.empty(n, dtype=torch.uint8, device=device) if n else None), n
+
+
+class _on_device:
+    """torch.cuda.device(dev) only when dev is not already current (the context manager costs several microseconds)."""
+
+    def __init__(self, device):
+        self.ctx = None if torch.cuda.current_device() == device.index else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
 
 
 def _fwd(mod, u, k, pregate, postgate):
@@ -244,7 +280,7 @@ def _fwd(mod, u, k, pregate, postgate):
         return y[..., :L0].contiguous(), kf
     B, H, L = u.shape
     plan = mod.plan(u.device)
-    with torch.cuda.device(u.device):
+    with _on_device(u.device):
         mod.last_launches = 0
         kf_engine = _kf_engine_for(mod, plan, k)
         y = torch.empty_like(u)
@@ -267,7 +303,7 @@ def _bwd(mod, dout, u, kf_engine, k_len, pregate, postgate):
     N = mod.fft_size(u.device)
     plan = mod.plan(u.device)
     dout = dout.contiguous()                                          # conv.py:1742
-    with torch.cuda.device(u.device):
+    with _on_device(u.device):
         du = torch.empty_like(u)
         dkf_engine = torch.empty((H, N, 2), dtype=torch.float32, device=u.device)
         dpre = torch.empty_like(u) if pregate is not None else None
