@@ -195,13 +195,17 @@ __global__ void __launch_bounds__(kThreads, 3) dk_from_dkf_kernel(const float2* 
     }
   } else {
     const int r = N >> 6, q8 = kN / N;
+#pragma unroll 8
     for (int e = tid; e < kN; e += kThreads) fbuf[slot(e)] = make_float2(0.f, 0.f);
     __syncthreads();
-    for (int f = tid; f < N; f += kThreads) {
-      const int k1p = f & (r - 1), k2 = f / r;
+    // task t -> (k2l fastest, then k1', then quarter): 16 consecutive threads read 128 contiguous bytes of every block
+    for (int t = tid; t < N; t += kThreads) {
+      const int k2l = t & 15, k1p = (t >> 4) & (r - 1), qd = t / (16 * r);
+      const float2* b0 = src + ((qd * 128 + k1p) << 4) + k2l;
       float2 acc = make_float2(0.f, 0.f);
-      for (int m = 0; m < q8; ++m) acc = cadd(acc, __ldg(src + (((k2 >> 4) * 128 + k1p + r * m) << 4) + (k2 & 15)));
-      fbuf[slot(f * q8)] = acc;
+#pragma unroll 4
+      for (int m = 0; m < q8; ++m) acc = cadd(acc, __ldg(b0 + ((r * m) << 4)));
+      fbuf[slot((k1p + r * (16 * qd + k2l)) * q8)] = acc;
     }
   }
   __syncthreads();
