@@ -538,3 +538,25 @@ def test_hyena_mixer_matches_callers_pattern(ffc, N, L):
     _check(y.detach(), ref.detach(), 'hyena mixer y')
     _check(proj.grad, p32.grad, 'hyena mixer d(projection)')
     _check(k.grad, k32.grad, 'hyena mixer dk')
+
+
+# ----------------------------------------------------------------------------- partial / frequency-sparse convolutions (f4)
+@pytest.mark.parametrize('L', [512, 4096, 16384])
+def test_partial_and_frequency_sparse_conv(ffc, L):
+    """The reference's two example operators (flashfftconv/sparse_conv.py:9-38), restated in fp32, against the engine-backed
+    classes of the same names."""
+    from flashfftconv import PartialFFTConv, FrequencySparseFFTConv
+    torch.manual_seed(8)
+    B, H, N = 3, 4, 2 * L
+    x = torch.randn(B, H, L, device='cuda').to(torch.bfloat16)
+    k = (torch.randn(H, L, device='cuda') / L ** 0.5)
+    x_f = torch.fft.rfft(x.float(), n=N)
+    n_part = L // 2
+    ref_partial = torch.fft.irfft(x_f * torch.fft.rfft(k[..., :n_part], n=N), n=N)[..., :L]
+    k_f = torch.fft.rfft(k, n=N)
+    k_f[..., n_part // 2:] = 0
+    ref_sparse = torch.fft.irfft(x_f * k_f, n=N)[..., :L]
+    for mod, ref in ((PartialFFTConv(n_part), ref_partial), (FrequencySparseFFTConv(n_part), ref_sparse)):
+        y = mod(x, k).float()
+        rel = ((y - ref).norm() / ref.norm()).item()
+        assert y.shape == ref.shape and rel <= REL_L2, f'{type(mod).__name__}: rel-L2 {rel:.3e}'
