@@ -258,7 +258,9 @@ def test_bwd_long_vs_oracle(ffc, N, B, H, L):
                                      (2048, 1, 3, 1024), (4096, 4, 5, 4096), (4096, 2, 2, 2048),
                                      # several batch members per 8192-point slot, ragged last group
                                      (256, 37, 2, 256), (512, 19, 3, 512), (1024, 9, 2, 1024), (1024, 16, 5, 512),
-                                     (2048, 7, 2, 2048)])
+                                     (2048, 7, 2, 2048),
+                                     # more than one unit per channel (8192/N members x 2 per unit), partial last unit, L < N
+                                     (256, 130, 2, 256), (256, 70, 1, 192), (512, 40, 2, 320), (4096, 9, 3, 4096)])
 def test_fwd_small_vs_oracle(ffc, N, B, H, L):
     d = orc.make_inputs(B, H, N, L, torch.bfloat16, seed=N + B, unit_scale=True)
     conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
@@ -277,7 +279,8 @@ def test_fwd_small_golden(ffc, golden_dir, name):
 
 
 @pytest.mark.parametrize('N,B,H,L,gated', [(1024, 2, 4, 1024, False), (4096, 3, 2, 2048, False), (512, 2, 2, 512, True),
-                                           (256, 35, 2, 256, False), (1024, 11, 3, 1024, True), (2048, 5, 2, 1024, False)])
+                                           (256, 35, 2, 256, False), (1024, 11, 3, 1024, True), (2048, 5, 2, 1024, False),
+                                           (256, 130, 2, 192, True), (1024, 33, 2, 512, True), (4096, 5, 2, 4096, True)])
 def test_bwd_small_vs_oracle(ffc, N, B, H, L, gated):
     d = orc.make_inputs(B, H, N, L, torch.bfloat16, seed=51 + B, gated=gated, unit_scale=True)
     conv = ffc.FlashFFTConv(N, dtype=torch.bfloat16).cuda()
