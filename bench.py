@@ -182,6 +182,13 @@ def dist_setup():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        # first collectives now, not inside the first timed loop's barrier: NCCL builds its communicator lazily and the
+        # launches right after that set-up are slow (seen as 0.18-0.19 ms instead of 0.157 ms per C2 step at 2 and 8 ranks;
+        # the same loop with the communicator warmed is rank-count independent, profiles/r2_step_diag.md)
+        t = torch.zeros(1, device=torch.device('cuda', local))
+        dist.all_reduce(t)
+        dist.barrier()
+        torch.cuda.synchronize()
     return rank, world, local
 
 
