@@ -119,3 +119,46 @@ def test_kernel_model_exact_and_quantised():
     yq, _, _ = km.model_fwd(xq, xq, kf, quant=True)
     r = km.ref_conv(xq, k)
     assert np.linalg.norm(yq - r) / np.linalg.norm(r) < 1e-2             # BASELINE.json tolerance
+
+
+# ----------------------------------------------------------------------------- executable models of the round-2 paths
+@pytest.mark.parametrize('Ns,L,Lk', [(256, 256, 256), (512, 320, 512), (1024, 1024, 700), (4096, 2048, 4096)])
+def test_small_size_block_diagonal_model(Ns, L, Lk):
+    """8192/Ns batch members per tile as independent Ns-point circular convolutions (block-diagonal stage 1, twiddles of
+    period Ns, sampled k_f): exact in float64, ~5e-3 with the kernel's roundings."""
+    rng = np.random.default_rng(Ns)
+    Q = km.N // Ns
+    xs0, xs1 = rng.standard_normal((Q, L)), rng.standard_normal((Q, L))
+    k = rng.standard_normal(Lk) / np.sqrt(Lk)
+    y0, y1 = km.model_fwd_small(xs0, xs1, k, Ns)
+    for m in range(Q):
+        assert np.abs(y0[m, :L] - km.ref_conv(xs0[m], k, Ns)).max() < 1e-10
+        assert np.abs(y1[m, :L] - km.ref_conv(xs1[m], k, Ns)).max() < 1e-10
+    xq = km.bf16_round(xs0)
+    yq, _ = km.model_fwd_small(xq, xq, k, Ns, quant=True)
+    ref = np.stack([km.ref_conv(xq[m], k, Ns) for m in range(Q)])
+    assert np.linalg.norm(yq[:, :L] - ref) / np.linalg.norm(ref) < 1e-2
+
+
+@pytest.mark.parametrize('Ns', [256, 1024, 4096])
+def test_small_size_dk_block_sum_model(Ns):
+    rng = np.random.default_rng(3)
+    blocks = rng.standard_normal((128, 64)) + 1j * rng.standard_normal((128, 64))
+    a, b = km.model_dk_small(blocks, Ns)
+    assert np.abs(a - b).max() < 1e-10 * np.abs(b).max() + 1e-12
+
+
+@pytest.mark.parametrize('Ntot,R0,R1,Lk', [(16384, 2, 1, 16384), (32768, 4, 1, 16384), (131072, 8, 2, 100000),
+                                           (1048576, 128, 1, 1048576), (2097152, 128, 2, 999999)])
+def test_composite_filter_fft_model(Ntot, R0, R1, Lk):
+    """Column DFTs + twiddle + 8192-point row FFTs for rho <= R/2, mirrored rows for the rest == the engine-order gather
+    of the full spectrum (k = rho + R k'', row = (rho % R0) R1 + rho // R0)."""
+    rng = np.random.default_rng(Ntot % 1000)
+    k = rng.standard_normal(Lk)
+    rows = km.model_filter_composite(k, Ntot, R0, R1)
+    X = np.fft.fft(k, Ntot)
+    R = R0 * R1
+    for rho in range(R):
+        want = X[rho + R * np.arange(km.N)]
+        got = rows[(rho % R0) * R1 + rho // R0]
+        assert np.abs(got - want).max() < 1e-8 * np.abs(X).max()
