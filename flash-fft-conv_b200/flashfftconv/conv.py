@@ -254,9 +254,7 @@ def _padded(t, Lp):
     tiling does not take directly (the reference only requires L even, README.md:270)."""
     if t is None or t.shape[-1] == Lp:
         return t
-    out = torch.zeros(t.shape[:-1] + (Lp,), dtype=t.dtype, device=t.device)
-    out[..., : t.shape[-1]] = t
-    return out
+    return torch.nn.functional.pad(t, (0, Lp - t.shape[-1]))          # one kernel: copy + zero tail
 
 
 def _workspace(plan, B, H, L, gated, backward, device):
