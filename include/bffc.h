@@ -12,9 +12,9 @@
  *   bffc_bwd          <- monarch_conv_backward_* ops (monarch.cpp:27-37; conv.py:1737-3233,
  *                        3856-4958) incl. the host-side dk_f.sum(0) and forward recompute
  *                        (monarch_cuda_interface_bwd_bf16.cu:798-808,1107-1114)
- *   bffc_kf_layout    <- the k_f Monarch digit permutations done in Python per call
- *                        (conv.py:640, :676, :1423-1424, :1632-1633) and their inverses
- *                        for dk_f (conv.py:1818, :1862, :2954)
+ *   bffc_kf_from_filter / bffc_kf_pack* <- torch.fft.fft of the filter + the k_f Monarch digit permutations done in
+ *                        Python per call (conv.py:575, :640, :676, :1423-1424, :1632-1633)
+ *   bffc_dk_from_dkf / bffc_dkf_unpack* <- their inverses for dk_f + torch.fft.ifft(...).real (conv.py:1817-1820, :1862, :2954)
  *   bffc_plan_*       <- FlashFFTConv.__init__ constant tables (conv.py:72-551)
  *
  * Conventions: plain pointers and sizes only, all data pointers are DEVICE pointers on the
@@ -122,9 +122,10 @@ int bffc_dk_from_dkf(const bffc_plan* plan, const void* dkf_engine, void* dk, in
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* Scratch the caller must provide.  bffc_workspace_bytes_ex: exact need of bffc_fwd (backward = 0) or bffc_bwd
- * (backward = 1) for a gated / ungated call (0 for the fully fused ungated sizes); bffc_workspace_bytes: enough for any
- * call with these shapes.  Composite sizes hold the outer stages' output as 16-bit plane pairs of ceil(B/2)*H*N elements:
- * forward nlev pairs, backward nlev + 1 (nlev = 1 for 16K..64K and 1M, 2 for 128K..512K, 2M, 4M). */
+ * (backward = 1) for a gated / ungated call; bffc_workspace_bytes: enough for any call with these shapes.
+ * seqlen <= 8192: 0, except the gated backward (two (B,H,L) tensors: the gated inputs handed to the dk_f kernel).
+ * Composite sizes hold the outer stages' output as 16-bit plane pairs of ceil(B/2)*H*N elements: forward nlev pairs,
+ * backward nlev + 1 (nlev = 1 for 16K..64K and 1M, 2 for 128K..512K, 2M, 4M). */
 size_t bffc_workspace_bytes(const bffc_plan* plan, int B, int H, int L);
 size_t bffc_workspace_bytes_ex(const bffc_plan* plan, int B, int H, int L, int gated, int backward);
 
